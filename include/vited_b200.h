@@ -1,0 +1,127 @@
+/* vited_b200.h -- C-ABI of the B200-native ViT-ED all-pairs scoring path.
+ *
+ * The reference (glmanhtu/vit-ed) has no FFI on this path: it sits behind a Python nn.Module API
+ *   build_model(config)                                    models/build.py:15-32
+ *   VisionTransformerCustom.__init__(img_size, patch_size, in_chans, num_classes, embed_dim, depth, c_depth,
+ *                                    num_heads, mlp_ratio, qkv_bias, ...)   models/vision_transformer.py:282-316
+ *   VisionTransformerCustom.forward(x, x2=None, forward_first_part=False)   models/vision_transformer.py:412-420
+ * and the two pair-grid loops evaluation.py:101-114 and hisfrag.py:189-246 that call it.
+ * This header is what a ctypes / cffi binding of a drop-in replacement binds; the Python mirror
+ * in vit-ed_b200/ keeps the reference's names and argument meaning on top of it.
+ *
+ * Conventions: all data pointers are DEVICE pointers owned by the caller (torch tensors kept alive by the caller);
+ * outputs are caller-allocated; work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default
+ * stream) and is asynchronous with respect to the host unless stated. Every function returns 0 on success and a
+ * non-zero status otherwise; vited_last_error() then holds a message. No exceptions cross the boundary. A handle is
+ * bound to one device and is not thread-safe (the reference runs one Python thread per GPU process).
+ */
+#ifndef VITED_B200_H
+#define VITED_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VITED_API __attribute__((visibility("default")))
+#else
+#define VITED_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vited_engine vited_engine;
+
+/* Mirrors the constructor arguments build_model() passes (models/build.py:19-32, defaults config.py:68-79). */
+typedef struct vited_config {
+  int32_t img_size;     /* DATA.IMG_SIZE            */
+  int32_t patch_size;   /* MODEL.PJS.PATCH_SIZE     */
+  int32_t in_chans;     /* MODEL.PJS.IN_CHANS (3)   */
+  int32_t num_classes;  /* MODEL.NUM_CLASSES        */
+  int32_t embed_dim;    /* MODEL.PJS.EMBED_DIM      */
+  int32_t depth;        /* MODEL.PJS.DEPTH          */
+  int32_t c_depth;      /* MODEL.PJS.C_DEPTH        */
+  int32_t num_heads;    /* MODEL.PJS.NUM_HEADS      */
+  float mlp_ratio;      /* MODEL.PJS.MLP_RATIO      */
+  int32_t qkv_bias;     /* MODEL.PJS.QKV_BIAS       */
+} vited_config;
+
+/* Grid modes of vited_score_grid. */
+enum {
+  /* puzzle: ordered pairs (i, j), i != j, i-major -- data/datasets/pieces_dataset.py:27-32 */
+  VITED_GRID_ORDERED_OFFDIAG = 0,
+  /* Hisfrag: pairs (a, b), a <= b, a-major, diagonal included -- hisfrag.py:166-167 (torch.combinations) */
+  VITED_GRID_UPPER_TRI_DIAG = 1
+};
+
+/* Options for vited_set_option. */
+enum {
+  VITED_OPT_GEMM_IMPL = 0,      /* 0 = tcgen05/TMA kernel (default), 1 = SIMT debugging reference kernel        */
+  VITED_OPT_ATTN_IMPL = 1,      /* 0 = tensor-core flash kernel (default), 1 = SIMT debugging reference kernel   */
+  VITED_OPT_CHUNK_ROWS = 2,     /* target token rows per decoder chunk (default 262144)                          */
+  VITED_OPT_CACHE_LAYER0 = 3    /* 1 (default) = run decoder layer 0's self-attention once per item, not per pair */
+};
+
+/* Library-wide last error message (thread-local). */
+VITED_API const char* vited_last_error(void);
+
+/* replaces: VisionTransformerCustom.__init__ (models/vision_transformer.py:282-376) + model.cuda() (evaluation.py:60) */
+VITED_API int vited_create(const vited_config* cfg, int device, vited_engine** out);
+VITED_API void vited_destroy(vited_engine* e);
+VITED_API int vited_set_option(vited_engine* e, int option, int64_t value);
+
+/* replaces: load_pretrained -> model.load_state_dict (misc/utils.py:48-127). `name` is the state_dict key
+ * (e.g. "cross_blocks.3.cross_attn.kv.weight"), `data` a device pointer to the fp32 tensor in PyTorch layout
+ * (Linear weights [out, in], conv weight [D, C, p, p]); the engine packs its own bf16 copy, the caller's tensor is
+ * only borrowed for the duration of the call (synchronises `stream`). Unknown keys are an error. */
+VITED_API int vited_load_weight(vited_engine* e, const char* name, const float* data, int64_t numel, void* stream);
+/* number of state_dict tensors the engine expects / has received; forward calls fail until they match */
+VITED_API int vited_num_weights_expected(vited_engine* e);
+VITED_API int vited_num_weights_loaded(vited_engine* e);
+/* i-th expected state_dict key (0 <= i < expected), NULL if out of range */
+VITED_API const char* vited_weight_name(vited_engine* e, int i);
+
+/* replaces: model(x, forward_first_part=True) -- forward_first_part, models/vision_transformer.py:382-388
+ * images [B, in_chans, S, S] f32 -> tokens [B, N_e, D] f32 (no cls token, no final norm). */
+VITED_API int vited_encode(vited_engine* e, const float* images, int B, float* out_tokens, void* stream);
+
+/* replaces: model(x1_tokens, x2_images) -- forward_second_part + forward_head, vision_transformer.py:403-405, :415-417
+ * ctx_tokens [B, N_e, D] f32, images [B, in_chans, S, S] f32 -> logits [B, num_classes] f32. */
+VITED_API int vited_decode(vited_engine* e, const float* ctx_tokens, const float* images, int B, float* out_logits,
+                 void* stream);
+
+/* replaces: model(pairs) one-shot -- forward_features + forward_head, vision_transformer.py:407-410, :418-420
+ * pairs [B, 2, in_chans, S, S] f32 -> logits [B, num_classes] f32. */
+VITED_API int vited_forward_pairs(vited_engine* e, const float* pairs, int B, float* out_logits, void* stream);
+
+/* replaces: the pair-grid loops evaluation.py:101-114 (mode ORDERED_OFFDIAG) and hisfrag.py:189-231 (mode
+ * UPPER_TRI_DIAG), for grid rows [row_begin, row_end) of an N-item grid.
+ * images [N, in_chans, S, S] f32 (all items, every rank holds them);
+ * out    [row_end - row_begin, N, num_classes] f32, out[(i - row_begin), j, :] = logits of pair (ctx = i, x2 = j).
+ * Entries that are not part of the mode's pair set (the diagonal, or j < i) are left untouched. */
+VITED_API int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int row_begin, int row_end, float* out,
+                     void* stream);
+
+/* number of kernels launched by this engine since creation (bench.py's gpu_launches) */
+VITED_API int64_t vited_launch_count(vited_engine* e);
+/* bytes of device workspace currently held */
+VITED_API int64_t vited_workspace_bytes(vited_engine* e);
+
+/* ---- single-kernel entry points (used by tests/ and profiles/ to check and time each kernel in isolation) ---- */
+/* C[M,N] bf16 = act(A[M,K] bf16 * W[N,K]^T bf16 + bias[N] f32); act: 0 none, 1 exact-erf GELU; impl as GEMM_IMPL */
+VITED_API int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,
+                  void* stream);
+/* x += delta (bf16, may be NULL); h = LayerNorm(x) * w + b as bf16 (w NULL => skipped). Split token layout. */
+VITED_API int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
+                      int n_patch, int has_cls, int D, float eps, void* stream);
+/* q/k/v/o bf16 in the split token layout; kv_index NULL => identity */
+VITED_API int vited_op_attention(const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o, int o_ld,
+                       int n_seq, int n_heads, int head_dim, int nq_patch, int q_has_cls, int nk_patch,
+                       int k_has_cls, int n_kv_seq, const int32_t* kv_index, float scale, int impl, void* stream);
+/* images [B,C,S,S] f32 -> [B*(S/p)^2, C*p*p] bf16 */
+VITED_API int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITED_B200_H */

@@ -1,0 +1,222 @@
+"""ORACLE -- test infrastructure only. NOT part of the product path.
+
+A plain fp32 CPU restatement of the reference algorithm for the all-pairs scoring path of glmanhtu/vit-ed. Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference`` leg may import it, and
+only as the checker / the reported CPU baseline; nothing under ``vit-ed_b200/`` imports it.
+
+Pinning (see tests/golden/make_golden.py and DESIGN.md): the reference publishes no golden vectors for this path
+(SURVEY 8c). The oracle is pinned against outputs of the reference's OWN ``models/vision_transformer.py`` executed in
+the build container (fixtures in tests/golden/*.npz) -- with one caveat: ``timm==0.9.2`` (requirements.txt:2) is
+absent, so the five timm symbols that file imports were stood in for by tests/golden/_timm_shim.py, a restatement of
+timm 0.9.2's published semantics. For the timm-owned arithmetic (PatchEmbed, Mlp, _pos_embed, forward_head,
+LayerNorm eps) parity is therefore UNPINNED by any reference-held vector; for the reference-owned code (Attention,
+Block, CrossAttention, CrossBlock, three-mode forward) and for the integer bookkeeping (pair enumeration, crop
+geometry, sampler split: real reference code imported unchanged) it is pinned.
+
+Every function cites the reference file:line it restates.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-6  # VisionTransformerCustom: norm_layer = partial(nn.LayerNorm, eps=1e-6) (vision_transformer.py:348)
+
+
+# ------------------------------------------------------------------------------------------------ model arithmetic
+def _ln(x, sd, prefix):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + '.weight'], sd[prefix + '.bias'], EPS)
+
+
+def _linear(x, sd, prefix):
+    return F.linear(x, sd[prefix + '.weight'], sd.get(prefix + '.bias'))
+
+
+def patch_embed(images, sd):
+    """timm PatchEmbed: Conv2d(k=s=p) -> flatten(2).transpose(1,2) (called at vision_transformer.py:383,391).
+    Written as im2col + matmul so the patch indexing contract is explicit."""
+    w = sd['patch_embed.proj.weight']
+    d, c, p, _ = w.shape
+    b, _, s, _ = images.shape
+    g = s // p
+    cols = images.reshape(b, c, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(b, g * g, c * p * p)
+    return cols @ w.reshape(d, c * p * p).t() + sd['patch_embed.proj.bias']
+
+
+def attention(x, sd, prefix, num_heads):
+    """Attention.forward (vision_transformer.py:56-80): qkv split (3, H, hd), softmax(q k^T * hd^-0.5) v, proj."""
+    b, n, c = x.shape
+    hd = c // num_heads
+    qkv = _linear(x, sd, prefix + '.qkv').reshape(b, n, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.unbind(0)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    attn = attn.softmax(dim=-1)
+    y = (attn @ v).transpose(1, 2).reshape(b, n, c)
+    return _linear(y, sd, prefix + '.proj')
+
+
+def cross_attention(x, context, sd, prefix, num_heads):
+    """CrossAttention.forward (vision_transformer.py:174-200): q from x, kv split (2, H, hd) from context."""
+    b, n, c = x.shape
+    nc = context.shape[1]
+    hd = c // num_heads
+    q = _linear(x, sd, prefix + '.q').reshape(b, n, num_heads, hd).permute(0, 2, 1, 3)
+    kv = _linear(context, sd, prefix + '.kv').reshape(b, nc, 2, num_heads, hd).permute(2, 0, 3, 1, 4)
+    k, v = kv.unbind(0)
+    attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    attn = attn.softmax(dim=-1)
+    y = (attn @ v).transpose(1, 2).reshape(b, n, c)
+    return _linear(y, sd, prefix + '.proj')
+
+
+def mlp(x, sd, prefix):
+    """timm Mlp: fc1 -> GELU (exact erf) -> fc2 (vision_transformer.py:115-120, :259-264)."""
+    return _linear(F.gelu(_linear(x, sd, prefix + '.fc1')), sd, prefix + '.fc2')
+
+
+def block(x, sd, prefix, num_heads):
+    """Block.forward (vision_transformer.py:124-127); LayerScale / DropPath are Identity."""
+    x = x + attention(_ln(x, sd, prefix + '.norm1'), sd, prefix + '.attn', num_heads)
+    x = x + mlp(_ln(x, sd, prefix + '.norm2'), sd, prefix + '.mlp')
+    return x
+
+
+def cross_block(x, context, sd, prefix, num_heads):
+    """CrossBlock.forward (vision_transformer.py:268-272)."""
+    x = x + attention(_ln(x, sd, prefix + '.norm1'), sd, prefix + '.attn', num_heads)
+    x = x + cross_attention(_ln(x, sd, prefix + '.norm_cross'), _ln(context, sd, prefix + '.norm_context'), sd,
+                            prefix + '.cross_attn', num_heads)
+    x = x + mlp(_ln(x, sd, prefix + '.norm2'), sd, prefix + '.mlp')
+    return x
+
+
+def _depths(sd):
+    depth = 1 + max(int(k.split('.')[1]) for k in sd if k.startswith('blocks.'))
+    c_depth = 1 + max(int(k.split('.')[1]) for k in sd if k.startswith('cross_blocks.'))
+    return depth, c_depth
+
+
+def forward_first_part(images, sd, num_heads):
+    """vision_transformer.py:382-388: patch_embed + pos_embed[:, 1:] (:378-380) + encoder blocks; no final norm."""
+    depth, _ = _depths(sd)
+    x = patch_embed(images, sd) + sd['pos_embed'][:, 1:]
+    for l in range(depth):
+        x = block(x, sd, f'blocks.{l}', num_heads)
+    return x
+
+
+def prepare_x2(images, sd):
+    """vision_transformer.py:390-395: patch_embed, cls token prepended, + pos_embed (timm _pos_embed)."""
+    x = patch_embed(images, sd)
+    x = torch.cat([sd['cls_token'].expand(x.shape[0], -1, -1), x], dim=1)
+    return x + sd['pos_embed']
+
+
+def forward_second_part(x1, images2, sd, num_heads):
+    """vision_transformer.py:397-405: cross blocks then final norm."""
+    _, c_depth = _depths(sd)
+    x2 = prepare_x2(images2, sd)
+    for l in range(c_depth):
+        x2 = cross_block(x2, x1, sd, f'cross_blocks.{l}', num_heads)
+    return _ln(x2, sd, 'norm')
+
+
+def forward_head(x, sd):
+    """timm forward_head with global_pool='token': x[:, 0] -> fc_norm (Identity) -> head."""
+    return _linear(x[:, 0], sd, 'head')
+
+
+@torch.no_grad()
+def forward(sd, num_heads, x, x2=None, first_part=False):
+    """VisionTransformerCustom.forward (vision_transformer.py:412-420), three modes."""
+    if first_part:
+        return forward_first_part(x, sd, num_heads)
+    if x2 is not None:
+        return forward_head(forward_second_part(x, x2, sd, num_heads), sd)
+    x1, xb = torch.unbind(x, 1)
+    return forward_head(forward_second_part(forward_first_part(x1, sd, num_heads), xb, sd, num_heads), sd)
+
+
+# ------------------------------------------------------------------------------------------------ grid drivers
+@torch.no_grad()
+def score_puzzle_grid(sd, num_heads, images, batch=64):
+    """evaluation.py:101-114 restated with the two-phase path: logits[i, j] for every ordered pair i != j."""
+    n = images.shape[0]
+    tokens = torch.cat([forward(sd, num_heads, images[i:i + batch], first_part=True) for i in range(0, n, batch)])
+    pairs = ordered_pairs(n)
+    out = torch.zeros((n, n, sd['head.weight'].shape[0]), dtype=torch.float32)
+    for p0 in range(0, len(pairs), batch):
+        sub = pairs[p0:p0 + batch]
+        logits = forward(sd, num_heads, tokens[sub[:, 0]], images[sub[:, 1]])
+        out[sub[:, 0], sub[:, 1]] = logits
+    return out
+
+
+@torch.no_grad()
+def score_fragment_grid(sd, num_heads, images, batch=16):
+    """hisfrag.py:189-231 + :281-292 restated: symmetric raw-logit similarity matrix from the a<=b pair set."""
+    n = images.shape[0]
+    tokens = torch.cat([forward(sd, num_heads, images[i:i + batch], first_part=True) for i in range(0, n, batch)])
+    pairs = upper_tri_pairs(n)
+    sim = torch.zeros((n, n), dtype=torch.float32)
+    for p0 in range(0, len(pairs), batch):
+        sub = pairs[p0:p0 + batch]
+        logits = forward(sd, num_heads, tokens[sub[:, 0]], images[sub[:, 1]])[:, 0]
+        sim[sub[:, 0], sub[:, 1]] = logits
+        sim[sub[:, 1], sub[:, 0]] = logits
+    return sim
+
+
+# ------------------------------------------------------------------------------------------------ integer bookkeeping
+def ordered_pairs(n):
+    """data/datasets/pieces_dataset.py:27-32 (nested loops, skip i == j)."""
+    return np.array([(i, j) for i in range(n) for j in range(n) if i != j], dtype=np.int64).reshape(-1, 2)
+
+
+def upper_tri_pairs(n):
+    """hisfrag.py:166-167: torch.combinations(arange(n), r=2, with_replacement=True)."""
+    return torch.combinations(torch.arange(n), r=2, with_replacement=True).numpy().astype(np.int64)
+
+
+def sampler_sizes(indexes, num_replicas):
+    """data/samplers.py:108-123 (DistributedIndicatesSampler.__init__ boundary computation)."""
+    indexes = torch.as_tensor(indexes)
+    n_samples_per_rep = math.ceil(len(indexes) / num_replicas)
+    indices = torch.split(indexes, n_samples_per_rep)
+    sizes = [0]
+    for i in range(1, len(indices)):
+        if indices[i][0] == indices[i - 1][-1]:
+            sizes.append(indices[i][0].item() - 1)
+        else:
+            sizes.append(indices[i][0].item())
+    sizes.append(indexes[-1].item() + 1)
+    return sizes
+
+
+def crop_geometry(img_h, img_w, piece_width, erosion):
+    """paikin_tal_solver/puzzle_importer.py:196-213 (grid), :224 (eroded side), :430-446 (centre_crop offset)."""
+    numb_cols = int(math.floor(img_w / piece_width))
+    numb_rows = int(math.floor(img_h / piece_width))
+    top = (img_h - numb_rows * piece_width) // 2
+    left = (img_w - numb_cols * piece_width) // 2
+    side = math.ceil(piece_width * (1 - erosion))
+    crop = side if side < piece_width else piece_width
+    off = int(round((piece_width - crop) / 2.0))
+    return numb_rows, numb_cols, top, left, crop, off
+
+
+def puzzle_distance_lookup(logits, i, j, side_i, side_j):
+    """evaluation.py:109-131: pred = 1 - sigmoid(logits[i, j]); side codes: 0 top, 1 right, 2 bottom, 3 left
+    (paikin_tal_solver/puzzle_piece.py PuzzlePieceSide values)."""
+    pred = 1.0 - torch.sigmoid(torch.as_tensor(logits[i][j], dtype=torch.float32)).numpy()
+    top, right, bottom, left = 0, 1, 2, 3
+    if side_j == left and side_i == right:
+        return pred[0] * 1000.
+    if side_j == right and side_i == left:
+        return pred[2] * 1000.
+    if side_j == top and side_i == bottom:
+        return pred[1] * 1000.
+    if side_j == bottom and side_i == top:
+        return pred[3] * 1000.
+    return float('inf')

@@ -1,0 +1,191 @@
+"""GPU: every kernel behind the C-ABI, in isolation, against plain torch on the same device (fp32 math on the same
+bf16-rounded operands). Tolerances are stated per test."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from vited_b200 import _lib
+    return _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _gemm(A, W, bias, act, impl):
+    L = _lib()
+    M, K = A.shape
+    N = W.shape[0]
+    C = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')
+    L.check(L.lib.vited_op_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(C), M, N, K, act, impl, _stream()), 'op_gemm')
+    torch.cuda.synchronize()
+    return C
+
+
+GEMM_SHAPES = [
+    # (M, N, K): every Linear of the two models + ragged / tiny edge cases
+    (128, 128, 64), (256, 384, 384), (1000, 1152, 384), (4160, 384, 384), (777, 1536, 384), (640, 384, 1536),
+    (65 * 37, 768, 384), (64 * 9, 384, 192), (300, 384, 768), (5, 32, 32), (130, 96, 3072), (1, 8, 8),
+    (129, 1152, 384), (20000, 1152, 384),
+]
+
+
+@pytest.mark.parametrize('impl', [0, 1], ids=['tcgen05', 'simt'])
+@pytest.mark.parametrize('act', [0, 1], ids=['none', 'gelu'])
+@pytest.mark.parametrize('shape', GEMM_SHAPES, ids=lambda s: 'x'.join(map(str, s)))
+def test_gemm(shape, act, impl):
+    M, N, K = shape
+    if impl == 1 and M * N * K > 3e9:
+        pytest.skip('debug kernel: skip the largest shape')
+    g = torch.Generator(device='cuda').manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device='cuda', generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device='cuda', generator=g)
+    C = _gemm(A, W, bias, act, impl)
+    ref = A.float() @ W.float().t() + bias
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    assert torch.isfinite(C.float()).all(), 'output has NaN/inf (unwritten tile?)'
+    # bf16 output rounding (2^-9 relative) + fp32 accumulation-order noise
+    err = (C.float() - ref).abs()
+    tol = 1e-2 * ref.abs() + 2e-2
+    bad = (err > tol)
+    assert not bad.any(), f'{int(bad.sum())} / {bad.numel()} mismatches, max err {float(err.max()):.4f}, ' \
+                          f'first bad index {bad.nonzero()[0].tolist()}'
+
+
+@pytest.mark.parametrize('bn', ['128', '192'])
+def test_gemm_tile_shapes_agree(bn, monkeypatch):
+    """Both BLOCK_N variants of the tcgen05 kernel must give the same answer (subprocess: the knob is read once)."""
+    import subprocess, sys, os
+    from tests.conftest import ROOT
+    code = (
+        "import torch, ctypes, math, sys; sys.path.insert(0, %r)\n"
+        "from vited_b200 import _lib as L\n"
+        "g = torch.Generator(device='cuda').manual_seed(1)\n"
+        "M, N, K = 1111, 1152, 384\n"
+        "A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
+        "b = torch.randn(N, device='cuda', generator=g); C = torch.zeros(M, N, dtype=torch.bfloat16, device='cuda')\n"
+        "st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, 0, None)\n"
+        "torch.cuda.synchronize(); assert st == 0, L.last_error()\n"
+        "ref = A.float() @ W.float().t() + b\n"
+        "err = (C.float() - ref).abs().max().item(); print('maxerr', err); assert err < 0.06\n"
+    ) % ROOT
+    env = dict(os.environ, VITED_GEMM_BN=bn)
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize('D', [384, 768, 32, 96])
+@pytest.mark.parametrize('has_cls', [0, 1])
+def test_resid_ln(D, has_cls):
+    L = _lib()
+    n_seq, n_patch = 37, 9
+    rows = n_seq * n_patch + (n_seq if has_cls else 0)
+    g = torch.Generator(device='cuda').manual_seed(D + has_cls)
+    x = torch.randn(rows, D, device='cuda', generator=g)
+    delta = torch.randn(rows, D, device='cuda', generator=g).to(torch.bfloat16)
+    w = 1 + 0.1 * torch.randn(D, device='cuda', generator=g)
+    b = 0.1 * torch.randn(D, device='cuda', generator=g)
+    x_ref = x + delta.float()
+    h_ref = torch.nn.functional.layer_norm(x_ref, (D,), w, b, 1e-6)
+    h = torch.zeros(rows, D, dtype=torch.bfloat16, device='cuda')
+    L.check(L.lib.vited_op_resid_ln(_ptr(x), _ptr(delta), _ptr(w), _ptr(b), _ptr(h), n_seq, n_patch, has_cls, D, 1e-6,
+                                    _stream()), 'op_resid_ln')
+    torch.cuda.synchronize()
+    assert torch.equal(x, x_ref), 'residual update must be exact fp32'
+    # bf16 rounding of the normalised row: 2^-9 relative
+    assert (h.float() - h_ref).abs().max().item() <= 1e-2 * h_ref.abs().max().item() + 1e-3
+
+
+def _attn_reference(q, k, v, scale):
+    # q [B,H,Nq,hd] etc, fp32 math on bf16-rounded inputs
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    return s.softmax(dim=-1) @ v.float()
+
+
+@pytest.mark.parametrize('impl', [0, 1], ids=['mma', 'simt'])
+@pytest.mark.parametrize('cfg', [
+    # (n_seq, H, hd, n_patch, has_cls)  -- self-attention
+    (7, 12, 32, 64, 1), (3, 6, 64, 1024, 1), (5, 12, 32, 64, 0), (2, 6, 64, 1024, 0), (4, 1, 32, 4, 1),
+    (3, 3, 32, 16, 1), (2, 2, 64, 100, 1), (1, 2, 32, 130, 0),
+], ids=lambda c: 'x'.join(map(str, c)))
+def test_self_attention(cfg, impl):
+    L = _lib()
+    n_seq, H, hd, n_patch, has_cls = cfg
+    D = H * hd
+    rows = n_seq * n_patch + (n_seq if has_cls else 0)
+    g = torch.Generator(device='cuda').manual_seed(sum(cfg))
+    qkv = torch.randn(rows, 3 * D, device='cuda', generator=g).to(torch.bfloat16)
+    o = torch.full((rows, D), float('nan'), dtype=torch.bfloat16, device='cuda')
+    scale = hd ** -0.5
+    st = L.lib.vited_op_attention(_ptr(qkv), 3 * D, ctypes.c_void_p(qkv.data_ptr() + 2 * D), 3 * D,
+                                  ctypes.c_void_p(qkv.data_ptr() + 4 * D), 3 * D, _ptr(o), D, n_seq, H, hd, n_patch,
+                                  has_cls, n_patch, has_cls, n_seq, None, scale, impl, _stream())
+    L.check(st, 'op_attention')
+    torch.cuda.synchronize()
+    # reference in the logical [B, N, D] layout: token 0 = cls
+    patch = qkv[:n_seq * n_patch].view(n_seq, n_patch, 3 * D)
+    seq = torch.cat([qkv[n_seq * n_patch:].view(n_seq, 1, 3 * D), patch], dim=1) if has_cls else patch
+    q, k, v = [seq[..., i * D:(i + 1) * D].reshape(n_seq, -1, H, hd).permute(0, 2, 1, 3) for i in range(3)]
+    ref = _attn_reference(q, k, v, scale).permute(0, 2, 1, 3).reshape(n_seq, -1, D)
+    got_patch = o[:n_seq * n_patch].view(n_seq, n_patch, D).float()
+    got = torch.cat([o[n_seq * n_patch:].view(n_seq, 1, D).float(), got_patch], dim=1) if has_cls else got_patch
+    assert torch.isfinite(got).all()
+    # P is rounded to bf16 before P.V and the output is bf16: 2e-2 absolute on O(1) values
+    assert (got - ref).abs().max().item() < 2e-2, f'max err {(got - ref).abs().max().item()}'
+
+
+@pytest.mark.parametrize('impl', [0, 1], ids=['mma', 'simt'])
+@pytest.mark.parametrize('cfg', [
+    # (n_pairs, n_ctx, H, hd, n_patch)
+    (9, 4, 12, 32, 64), (5, 3, 6, 64, 1024), (6, 2, 1, 32, 4), (4, 4, 2, 64, 16),
+], ids=lambda c: 'x'.join(map(str, c)))
+def test_cross_attention(cfg, impl):
+    L = _lib()
+    P, n_ctx, H, hd, n_patch = cfg
+    D = H * hd
+    rows = P * (n_patch + 1)
+    g = torch.Generator(device='cuda').manual_seed(sum(cfg))
+    qb = torch.randn(rows, D, device='cuda', generator=g).to(torch.bfloat16)
+    kv = torch.randn(n_ctx * n_patch, 2 * D, device='cuda', generator=g).to(torch.bfloat16)
+    idx = torch.randint(0, n_ctx, (P,), device='cuda', generator=g, dtype=torch.int32)
+    o = torch.full((rows, D), float('nan'), dtype=torch.bfloat16, device='cuda')
+    scale = hd ** -0.5
+    st = L.lib.vited_op_attention(_ptr(qb), D, _ptr(kv), 2 * D, ctypes.c_void_p(kv.data_ptr() + 2 * D), 2 * D, _ptr(o),
+                                  D, P, H, hd, n_patch, 1, n_patch, 0, n_ctx, _ptr(idx), scale, impl, _stream())
+    L.check(st, 'op_attention')
+    torch.cuda.synchronize()
+    seq = torch.cat([qb[P * n_patch:].view(P, 1, D), qb[:P * n_patch].view(P, n_patch, D)], dim=1)
+    q = seq.reshape(P, n_patch + 1, H, hd).permute(0, 2, 1, 3)
+    kvs = kv.view(n_ctx, n_patch, 2, H, hd)[idx.long()]
+    k = kvs[:, :, 0].permute(0, 2, 1, 3)
+    v = kvs[:, :, 1].permute(0, 2, 1, 3)
+    ref = _attn_reference(q, k, v, scale).permute(0, 2, 1, 3).reshape(P, n_patch + 1, D)
+    got = torch.cat([o[P * n_patch:].view(P, 1, D), o[:P * n_patch].view(P, n_patch, D)], dim=1).float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-2, f'max err {(got - ref).abs().max().item()}'
+
+
+@pytest.mark.parametrize('cfg', [(3, 3, 64, 8), (2, 3, 512, 16), (5, 3, 64, 32)])
+def test_im2col_patch_indexing_is_exact(cfg):
+    L = _lib()
+    B, C, S, p = cfg
+    g = torch.Generator(device='cuda').manual_seed(0)
+    img = torch.randn(B, C, S, S, device='cuda', generator=g)
+    G = S // p
+    out = torch.zeros(B * G * G, C * p * p, dtype=torch.bfloat16, device='cuda')
+    L.check(L.lib.vited_op_im2col(_ptr(img), _ptr(out), B, C, S, p, _stream()), 'op_im2col')
+    torch.cuda.synchronize()
+    ref = img.reshape(B, C, G, p, G, p).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, C * p * p).to(torch.bfloat16)
+    assert torch.equal(out, ref), 'patch indexing must be bit-exact (SURVEY 8b)'

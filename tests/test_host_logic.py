@@ -1,0 +1,166 @@
+"""CPU: host-side mirror of the reference interface -- key set, integer bookkeeping, consumer layouts, sharding."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tests import helpers
+from tests.conftest import GOLDEN
+import vited_b200
+from vited_b200 import grid, pieces
+
+
+@pytest.mark.parametrize('name', helpers.MODEL_CASES)
+def test_state_dict_layout_matches_reference(name):
+    z, kw = helpers.load_model_case(name)
+    model = vited_b200.VisionTransformerCustom(mlp_ratio=4., qkv_bias=True, **kw)
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == [str(k) for k in z['keys']]
+    assert len(sd) == int(z['n_state_dict'])
+    assert sum(p.numel() for p in model.parameters()) == int(z['n_params'])
+    shapes = helpers.shapes_from_kwargs(kw)
+    for k, v in sd.items():
+        assert tuple(v.shape) == shapes[k], k
+
+
+def test_build_model_and_unsupported_options():
+    for name in ('puzzle', 'hisfrag', 'test'):
+        cfg = vited_b200.get_config(name)
+        m = vited_b200.build_model(cfg)
+        assert m.embed_dim == cfg.MODEL.PJS.EMBED_DIM and m.num_classes == cfg.MODEL.NUM_CLASSES
+    cfg = vited_b200.get_config('puzzle')
+    cfg.MODEL.TYPE = 'resnet'
+    with pytest.raises(NotImplementedError):
+        vited_b200.build_model(cfg)
+    with pytest.raises(NotImplementedError):
+        vited_b200.VisionTransformerCustom(img_size=64, patch_size=8, embed_dim=384, qk_norm=True)
+    with pytest.raises(AssertionError):
+        vited_b200.VisionTransformerCustom(img_size=64, patch_size=8, embed_dim=100, num_heads=12)
+
+
+def test_pair_enumeration_and_sampler_against_reference_vectors():
+    z = np.load(os.path.join(GOLDEN, 'integer_paths.npz'))
+    for n in (1, 2, 5, 9):
+        got = grid.ordered_pairs(n)
+        np.testing.assert_array_equal(got, z[f'entries_{n}'].reshape(-1, 2))
+        for idx, (i, j) in enumerate(got):
+            assert grid.ordered_pair_index(int(i), int(j), n) == idx
+    for n in (1, 4, 7):
+        np.testing.assert_array_equal(grid.upper_tri_pairs(n), z[f'combos_{n}'])
+    assert len(grid.ordered_pairs(540)) == 291060 and len(grid.upper_tri_pairs(4096)) == 8390656
+    for n, world in z['sampler_cases']:
+        ref = z[f'sampler_{n}_{world}']
+        for rank in range(int(world)):
+            lo, hi = grid.hisfrag_row_range(int(n), int(world), rank)
+            if ref[rank, 0] == -2:
+                assert lo == hi
+            else:
+                assert [lo, hi] == ref[rank].tolist()
+
+
+def test_equal_row_range_covers_everything():
+    for n, world in ((540, 1), (540, 8), (1000, 8), (7, 8), (20000, 4)):
+        rows = []
+        for r in range(world):
+            lo, hi = grid.equal_row_range(n, world, r)
+            rows.extend(range(lo, hi))
+        assert rows == list(range(n))
+
+
+def test_piece_preparation_bit_exact_with_reference():
+    z = np.load(os.path.join(GOLDEN, 'integer_paths.npz'))
+    img = z['puzzle_image']
+    for erosion, tag in ((0.0, '0p0'), (0.07, '0p07'), (0.14, '0p14')):
+        lab, grid_size = pieces.make_pieces_lab(img, 64, erosion)
+        assert list(grid_size) == z[f'grid_{tag}'].tolist()
+        np.testing.assert_array_equal(np.stack(lab), z[f'pieces_lab_{tag}'])       # uint8, bit-exact
+        i, j = z[f'pair_entry_{tag}']
+        pair = torch.stack([pieces.piece_to_tensor(lab[int(i)], 64), pieces.piece_to_tensor(lab[int(j)], 64)])
+        np.testing.assert_array_equal(pair.numpy(), z[f'pair_tensor_{tag}'])       # fp32, bit-exact
+    assert pieces.erosion_crop(64, 0.07) == (60, 2) and pieces.erosion_crop(64, 0.14) == (56, 4)
+    with pytest.raises(ValueError):
+        pieces.grid_geometry(10, 10, 64)
+
+
+def test_consumer_layouts():
+    from oracle import vited_oracle as orc
+
+    class Side:
+        top, right, bottom, left = 0, 1, 2, 3
+
+    class Piece:
+        def __init__(self, i):
+            self.origin_piece_id = i
+
+    logits = torch.randn(3, 3, 4, generator=torch.Generator().manual_seed(0))
+    dist = grid.puzzle_distance(logits)
+    fn = grid.make_distance_function(dist, Side)
+    for i in range(3):
+        for j in range(3):
+            for si in range(4):
+                for sj in range(4):
+                    want = orc.puzzle_distance_lookup(logits.numpy(), i, j, si, sj)
+                    got = fn(Piece(i), si, Piece(j), sj)
+                    assert got == pytest.approx(want, rel=1e-6) or (got == want == float('inf'))
+    upper = torch.triu(torch.randn(5, 5, generator=torch.Generator().manual_seed(1)))
+    sim = grid.mirror_upper(upper)
+    assert torch.equal(sim, sim.t()) and torch.equal(torch.triu(sim), upper)
+    d = grid.similarity_to_distance(sim)
+    assert d.dtype == np.float16 and np.array_equal(d, (1 - sim.type(torch.float16)).numpy())
+
+
+class _FakeModel:
+    """Stands in for the engine so the sharding / gather logic can run on CPU with gloo: score(i, j) is a closed
+    form of (i, j, c)."""
+    num_classes = 4
+
+    def score_grid(self, images, mode, row_begin, row_end):
+        n = images.shape[0]
+        i = torch.arange(row_begin, row_end).view(-1, 1, 1).float()
+        j = torch.arange(n).view(1, -1, 1).float()
+        c = torch.arange(self.num_classes).view(1, 1, -1).float()
+        full = i * 1000 + j + c / 10
+        if mode == vited_b200.GRID_ORDERED_OFFDIAG:
+            mask = (i != j).expand_as(full)
+        else:
+            mask = (j >= i).expand_as(full)
+        return torch.where(mask, full, torch.zeros_like(full))
+
+
+def _gloo_worker(rank, world, n, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model = _FakeModel()
+        images = torch.zeros(n, 3, 8, 8)
+        puzzle = grid.score_puzzle(model, images)
+        model.num_classes = 1
+        frag = grid.score_fragments(model, images)
+        q.put((rank, puzzle.numpy(), frag.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharding_and_gather_world2_gloo():
+    n, world = 11, 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, n, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single = _FakeModel()
+    want_puzzle = single.score_grid(torch.zeros(n, 3, 8, 8), vited_b200.GRID_ORDERED_OFFDIAG, 0, n)
+    single.num_classes = 1
+    want_frag = grid.mirror_upper(single.score_grid(torch.zeros(n, 3, 8, 8), vited_b200.GRID_UPPER_TRI_DIAG, 0, n)[..., 0])
+    for rank, puzzle, frag in results:
+        assert np.array_equal(puzzle, want_puzzle.numpy()), f'rank {rank} puzzle grid differs'
+        assert np.array_equal(frag, want_frag.numpy()), f'rank {rank} fragment grid differs'

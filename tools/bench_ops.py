@@ -1,0 +1,96 @@
+"""Times each kernel of the path in isolation with CUDA events (GPU box only). Prints one JSON line per op with the
+achieved TFLOP/s or GB/s against MEASURED_PEAKS.json. Used to fill profiles/ and DESIGN.md, not a test."""
+import ctypes
+import json
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vited_b200 import _lib as L  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d['hbm_gbs'], d['bf16_tflops'], 'measured'
+    return 6650.0, 1590.0, 'fallback'
+
+
+def timeit(fn, iters=20, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    hbm, tf, src = peaks()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
+    st = None
+    M = 4032 * 65
+    out = []
+    for name, N, K, act in (('qkv', 1152, 384, 0), ('proj', 384, 384, 0), ('fc1_gelu', 1536, 384, 1),
+                            ('fc2', 384, 1536, 0), ('kv', 768, 384, 0)):
+        A = torch.randn(M, K, device='cuda').bfloat16()
+        W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+        b = torch.randn(N, device='cuda')
+        C = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+        for impl in (0,):
+            ms = timeit(lambda: L.check(L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K,
+                                                              act, impl, st), 'gemm'), flush=flush)
+            fl = 2.0 * M * N * K
+            by = 2.0 * (M * K + N * K + M * N)
+            out.append(dict(op=f'gemm_{name}', M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9, tflops_frac=fl / ms / 1e9 / tf,
+                            gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm, bn=os.environ.get('VITED_GEMM_BN', 'auto')))
+        ms = timeit(lambda: torch.matmul(A, W.t(), out=C), flush=flush)
+        out.append(dict(op=f'cublas_{name}', M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9))
+    # resid + LN
+    D = 384
+    x = torch.randn(M, D, device='cuda')
+    delta = torch.randn(M, D, device='cuda').bfloat16()
+    w = torch.ones(D, device='cuda'); bb = torch.zeros(D, device='cuda')
+    h = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+    ms = timeit(lambda: L.check(L.lib.vited_op_resid_ln(x.data_ptr(), delta.data_ptr(), w.data_ptr(), bb.data_ptr(), h.data_ptr(),
+                                                         4032, 64, 1, D, 1e-6, st), 'ln'), flush=flush)
+    by = M * D * (4 + 2 + 4 + 2)
+    out.append(dict(op='resid_ln', rows=M, ms=ms, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+    # attention (puzzle): self and cross
+    P, H, hd, Np = 4032, 12, 32, 64
+    qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
+    o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+    for impl in (0, 1):
+        ms = timeit(lambda: L.check(L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D,
+                                                              3 * D, o.data_ptr(), D, P, H, hd, Np, 1, Np, 1, P, None, hd ** -0.5, impl, st),
+                                    'attn'), flush=flush, iters=5 if impl else 20)
+        fl = 4.0 * P * H * 65 * 65 * hd
+        by = M * D * 2 * 4
+        out.append(dict(op=f'attn_self_impl{impl}', ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+    kv = torch.randn(540 * Np, 2 * D, device='cuda').bfloat16()
+    q = torch.randn(M, D, device='cuda').bfloat16()
+    idx = (torch.arange(P, device='cuda') // 539).int()
+    ms = timeit(lambda: L.check(L.lib.vited_op_attention(q.data_ptr(), D, kv.data_ptr(), 2 * D, kv.data_ptr() + 2 * D, 2 * D, o.data_ptr(), D,
+                                                          P, H, hd, Np, 1, Np, 0, 540, idx.data_ptr(), hd ** -0.5, 0, st), 'attn'), flush=flush)
+    out.append(dict(op='attn_cross_impl0', ms=ms, tflops=4.0 * P * H * 65 * 64 * hd / ms / 1e9, gbs=M * D * 2 * 2 / ms / 1e6))
+    for r in out:
+        r['peaks'] = src
+        print(json.dumps(r))
+
+
+if __name__ == '__main__':
+    main()

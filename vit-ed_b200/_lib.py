@@ -1,0 +1,93 @@
+"""ctypes binding of the C-ABI in include/vited_b200.h (the only way Python reaches the CUDA kernels).
+
+There is no CPU or PyTorch fallback: if ``lib/libvited_b200.so`` is missing or fails to load, importing this module
+raises, and every compute entry point raises when it returns a non-zero status.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvited_b200.so")
+
+
+class VitedError(RuntimeError):
+    pass
+
+
+class Config(ctypes.Structure):
+    """``vited_config`` (include/vited_b200.h) -- the constructor arguments of models/build.py:19-32."""
+
+    _fields_ = [
+        ("img_size", ctypes.c_int32),
+        ("patch_size", ctypes.c_int32),
+        ("in_chans", ctypes.c_int32),
+        ("num_classes", ctypes.c_int32),
+        ("embed_dim", ctypes.c_int32),
+        ("depth", ctypes.c_int32),
+        ("c_depth", ctypes.c_int32),
+        ("num_heads", ctypes.c_int32),
+        ("mlp_ratio", ctypes.c_float),
+        ("qkv_bias", ctypes.c_int32),
+    ]
+
+
+GRID_ORDERED_OFFDIAG = 0
+GRID_UPPER_TRI_DIAG = 1
+OPT_GEMM_IMPL = 0
+OPT_ATTN_IMPL = 1
+OPT_CHUNK_ROWS = 2
+OPT_CACHE_LAYER0 = 3
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f = ctypes.c_float
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "vited_last_error": (ctypes.c_char_p, []),
+    "vited_create": (_i, [ctypes.POINTER(Config), _i, ctypes.POINTER(_vp)]),
+    "vited_destroy": (None, [_vp]),
+    "vited_set_option": (_i, [_vp, _i, _i64]),
+    "vited_load_weight": (_i, [_vp, ctypes.c_char_p, _vp, _i64, _vp]),
+    "vited_num_weights_expected": (_i, [_vp]),
+    "vited_num_weights_loaded": (_i, [_vp]),
+    "vited_weight_name": (ctypes.c_char_p, [_vp, _i]),
+    "vited_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "vited_decode": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "vited_forward_pairs": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "vited_score_grid": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "vited_launch_count": (_i64, [_vp]),
+    "vited_workspace_bytes": (_i64, [_vp]),
+    "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "vited_op_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "vited_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i, _vp]),
+    "vited_op_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise VitedError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or vit-ed_b200/csrc/build.sh). This package has no CPU / PyTorch fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    msg = lib.vited_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise VitedError(f"{what} failed: {last_error()}")

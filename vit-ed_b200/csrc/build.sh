@@ -1,0 +1,13 @@
+#!/usr/bin/env bash
+# Builds the C-ABI shared library for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../lib"
+mkdir -p "$OUT"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --threads 4 \
+  -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -shared -cudart static \
+  ${VITED_PTXAS_V:+-Xptxas -v} \
+  -o "$OUT/libvited_b200.so" \
+  "$HERE/engine.cu" "$HERE/gemm_tc.cu" "$HERE/attention.cu" "$HERE/rowops.cu"
+echo "built $OUT/libvited_b200.so"

@@ -1,0 +1,659 @@
+// Host-side engine behind the C-ABI (include/vited_b200.h): weight packing, workspace, and the launch sequences for
+// encode / decode / one-shot / all-pairs grid scoring. Everything here is plumbing around the kernels in
+// gemm_tc.cu, attention.cu and rowops.cu; there is no CPU compute path.
+//
+// Data layout in HBM:
+//   * token rows use the "split" layout: n_seq*N_e patch rows followed by n_seq class-token rows, so that 64/1024
+//     patch tokens per sequence tile exactly into 64-row attention tiles and GEMMs run over one flat row space;
+//   * residual stream x is fp32 [rows, D]; every GEMM operand/result is bf16; sub-block outputs are written as a
+//     bf16 `delta` and folded into x by the fused residual+LayerNorm kernel;
+//   * per grid: Xsrc = decoder input of every item (after layer-0 self-attention when cached), fp32 split layout;
+//     KV[l] = kv(norm_context(enc_tokens)) for the current block of context rows, bf16 [rows*N_e, 2D].
+#include "../../include/vited_b200.h"
+#include "kernels.h"
+
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace vited {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3);  // 12.5% headroom against re-allocation churn
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+      return 1;
+    }
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Linear { bf16* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct LNorm { float* w = nullptr; float* b = nullptr; };
+struct EncBlock { LNorm norm1, norm2; Linear qkv, proj, fc1, fc2; };
+struct DecBlock { LNorm norm1, norm_cross, norm_context, norm2; Linear qkv, proj, q, kv, cproj, fc1, fc2; };
+
+struct Slot {
+  void* dst;
+  bool to_bf16;
+  int64_t numel;
+  bool loaded;
+};
+
+}  // namespace vited
+
+using namespace vited;
+
+struct vited_engine {
+  vited_config cfg;
+  int device = 0;
+  int D = 0, H = 0, hd = 0, G = 0, Ne = 0, Nd = 0, Kpe = 0, hidden = 0, C = 0;
+  float scale = 1.f;
+  Linear patch;
+  float* pos = nullptr;
+  float* cls = nullptr;
+  std::vector<EncBlock> enc;
+  std::vector<DecBlock> dec;
+  LNorm norm;
+  float* head_w = nullptr;
+  float* head_b = nullptr;
+  std::vector<void*> owned;  // weight allocations
+  std::map<std::string, Slot> slots;
+  std::vector<std::string> names;
+  int loaded = 0;
+  // options
+  int gemm_impl = IMPL_FAST, attn_impl = IMPL_FAST;
+  int64_t chunk_rows = 262144;
+  int cache_layer0 = 1;
+  int64_t launches = 0;
+  // workspace
+  DevBuf x, h, qkv, o, q, delta, hid, col, tok, xsrc, enc_tok, kv, ci, xj, tmp_tok;
+
+  int64_t workspace_bytes() const {
+    return (int64_t)(x.cap + h.cap + qkv.cap + o.cap + q.cap + delta.cap + hid.cap + col.cap + tok.cap + xsrc.cap +
+                     enc_tok.cap + kv.cap + ci.cap + xj.cap + tmp_tok.cap);
+  }
+};
+
+namespace vited {
+
+#define TRY(expr)            \
+  do {                       \
+    if ((expr) != 0) return 1; \
+  } while (0)
+
+static int alloc_f32(vited_engine* e, float** p, size_t n) {
+  VITED_CUDA_OK(cudaMalloc(p, n * sizeof(float)));
+  VITED_CUDA_OK(cudaMemset(*p, 0, n * sizeof(float)));
+  e->owned.push_back(*p);
+  return 0;
+}
+static int alloc_bf16(vited_engine* e, bf16** p, size_t n) {
+  VITED_CUDA_OK(cudaMalloc(p, n * sizeof(bf16)));
+  VITED_CUDA_OK(cudaMemset(*p, 0, n * sizeof(bf16)));
+  e->owned.push_back(*p);
+  return 0;
+}
+static void reg(vited_engine* e, const std::string& name, void* dst, bool to_bf16, int64_t numel) {
+  e->slots[name] = Slot{dst, to_bf16, numel, false};
+  e->names.push_back(name);
+}
+static int make_linear(vited_engine* e, const std::string& prefix, Linear* l, int out, int in, bool bias) {
+  l->out = out;
+  l->in = in;
+  TRY(alloc_bf16(e, &l->w, (size_t)out * in));
+  TRY(alloc_f32(e, &l->b, out));  // stays zero when the reference layer has no bias (qkv_bias=False)
+  reg(e, prefix + ".weight", l->w, true, (int64_t)out * in);
+  if (bias) reg(e, prefix + ".bias", l->b, false, out);
+  return 0;
+}
+static int make_ln(vited_engine* e, const std::string& prefix, LNorm* n, int D) {
+  TRY(alloc_f32(e, &n->w, D));
+  TRY(alloc_f32(e, &n->b, D));
+  reg(e, prefix + ".weight", n->w, false, D);
+  reg(e, prefix + ".bias", n->b, false, D);
+  return 0;
+}
+
+static int build(vited_engine* e) {
+  const vited_config& c = e->cfg;
+  VITED_CHECK(c.img_size > 0 && c.patch_size > 0 && c.img_size % c.patch_size == 0,
+              "img_size %d must be a positive multiple of patch_size %d", c.img_size, c.patch_size);
+  VITED_CHECK(c.embed_dim > 0 && c.num_heads > 0 && c.embed_dim % c.num_heads == 0,
+              "dim should be divisible by num_heads (embed_dim=%d num_heads=%d)", c.embed_dim, c.num_heads);
+  VITED_CHECK(c.embed_dim % 8 == 0, "embed_dim %d must be a multiple of 8", c.embed_dim);
+  VITED_CHECK(c.depth >= 1 && c.c_depth >= 1 && c.num_classes >= 1 && c.in_chans >= 1, "bad depth/classes/channels");
+  e->D = c.embed_dim;
+  e->H = c.num_heads;
+  e->hd = e->D / e->H;
+  VITED_CHECK(e->hd == 32 || e->hd == 64, "head_dim %d unsupported (the attention kernels are built for 32 and 64)",
+              e->hd);
+  e->G = c.img_size / c.patch_size;
+  e->Ne = e->G * e->G;
+  e->Nd = e->Ne + 1;
+  e->Kpe = c.in_chans * c.patch_size * c.patch_size;
+  e->hidden = (int)(c.embed_dim * c.mlp_ratio);
+  VITED_CHECK(e->hidden % 8 == 0 && e->Kpe % 8 == 0, "hidden %d / patch K %d must be multiples of 8", e->hidden, e->Kpe);
+  e->C = c.num_classes;
+  e->scale = 1.0f / sqrtf((float)e->hd);
+  const int D = e->D;
+  const bool qb = c.qkv_bias != 0;
+
+  TRY(alloc_f32(e, &e->cls, D));
+  reg(e, "cls_token", e->cls, false, D);
+  TRY(alloc_f32(e, &e->pos, (size_t)e->Nd * D));
+  reg(e, "pos_embed", e->pos, false, (int64_t)e->Nd * D);
+  TRY(make_linear(e, "patch_embed.proj", &e->patch, D, e->Kpe, true));
+  e->enc.resize(c.depth);
+  for (int l = 0; l < c.depth; ++l) {
+    const std::string p = "blocks." + std::to_string(l);
+    EncBlock& b = e->enc[l];
+    TRY(make_ln(e, p + ".norm1", &b.norm1, D));
+    TRY(make_linear(e, p + ".attn.qkv", &b.qkv, 3 * D, D, qb));
+    TRY(make_linear(e, p + ".attn.proj", &b.proj, D, D, true));
+    TRY(make_ln(e, p + ".norm2", &b.norm2, D));
+    TRY(make_linear(e, p + ".mlp.fc1", &b.fc1, e->hidden, D, true));
+    TRY(make_linear(e, p + ".mlp.fc2", &b.fc2, D, e->hidden, true));
+  }
+  e->dec.resize(c.c_depth);
+  for (int l = 0; l < c.c_depth; ++l) {
+    const std::string p = "cross_blocks." + std::to_string(l);
+    DecBlock& b = e->dec[l];
+    TRY(make_ln(e, p + ".norm1", &b.norm1, D));
+    TRY(make_linear(e, p + ".attn.qkv", &b.qkv, 3 * D, D, qb));
+    TRY(make_linear(e, p + ".attn.proj", &b.proj, D, D, true));
+    TRY(make_ln(e, p + ".norm_cross", &b.norm_cross, D));
+    TRY(make_ln(e, p + ".norm_context", &b.norm_context, D));
+    TRY(make_linear(e, p + ".cross_attn.q", &b.q, D, D, qb));
+    TRY(make_linear(e, p + ".cross_attn.kv", &b.kv, 2 * D, D, qb));
+    TRY(make_linear(e, p + ".cross_attn.proj", &b.cproj, D, D, true));
+    TRY(make_ln(e, p + ".norm2", &b.norm2, D));
+    TRY(make_linear(e, p + ".mlp.fc1", &b.fc1, e->hidden, D, true));
+    TRY(make_linear(e, p + ".mlp.fc2", &b.fc2, D, e->hidden, true));
+  }
+  TRY(make_ln(e, "norm", &e->norm, D));
+  TRY(alloc_f32(e, &e->head_w, (size_t)e->C * D));
+  TRY(alloc_f32(e, &e->head_b, e->C));
+  reg(e, "head.weight", e->head_w, false, (int64_t)e->C * D);
+  reg(e, "head.bias", e->head_b, false, e->C);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// launch helpers (count every kernel for bench.py's gpu_launches)
+// ------------------------------------------------------------------------------------------------------------
+static int L_gemm(vited_engine* e, const bf16* A, const Linear& l, bf16* Cout, int M, int act, cudaStream_t s) {
+  e->launches++;
+  return gemm_bf16(A, l.w, l.b, Cout, M, l.out, l.in, act, e->gemm_impl, s);
+}
+static int L_resid_ln(vited_engine* e, float* x, const bf16* delta, const float* gsrc, const int* gidx, int n_src,
+                      const LNorm* ln, bf16* h, int n_seq, int has_cls, int write_x, cudaStream_t s) {
+  ResidLnArgs a;
+  a.x = x; a.delta = delta; a.gather_src = gsrc; a.gather_idx = gidx; a.n_src_seq = n_src;
+  a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
+  a.n_seq = n_seq; a.n_patch = e->Ne; a.has_cls = has_cls; a.D = e->D; a.write_x = write_x; a.eps = 1e-6f;
+  e->launches++;
+  return resid_ln(a, s);
+}
+static int L_attn_self(vited_engine* e, const bf16* qkv, bf16* o, int n_seq, int has_cls, cudaStream_t s) {
+  AttnArgs a;
+  const int D = e->D;
+  a.q = qkv; a.q_ld = 3 * D; a.k = qkv + D; a.k_ld = 3 * D; a.v = qkv + 2 * D; a.v_ld = 3 * D; a.o = o; a.o_ld = D;
+  a.n_seq = n_seq; a.n_heads = e->H; a.head_dim = e->hd;
+  a.nq_patch = e->Ne; a.q_has_cls = has_cls; a.nk_patch = e->Ne; a.k_has_cls = has_cls;
+  a.n_kv_seq = n_seq; a.kv_index = nullptr; a.scale = e->scale;
+  e->launches++;
+  return attention(a, e->attn_impl, s);
+}
+static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o, int n_seq, int n_kv_seq,
+                        const int* kv_index, cudaStream_t s) {
+  AttnArgs a;
+  const int D = e->D;
+  a.q = q; a.q_ld = D; a.k = kv; a.k_ld = 2 * D; a.v = kv + D; a.v_ld = 2 * D; a.o = o; a.o_ld = D;
+  a.n_seq = n_seq; a.n_heads = e->H; a.head_dim = e->hd;
+  a.nq_patch = e->Ne; a.q_has_cls = 1; a.nk_patch = e->Ne; a.k_has_cls = 0;
+  a.n_kv_seq = n_kv_seq; a.kv_index = kv_index; a.scale = e->scale;
+  e->launches++;
+  return attention(a, e->attn_impl, s);
+}
+
+static int ensure_rows(vited_engine* e, size_t rows) {
+  const size_t D = e->D;
+  TRY(e->x.ensure(rows * D * 4));
+  TRY(e->h.ensure(rows * D * 2));
+  TRY(e->qkv.ensure(rows * 3 * D * 2));
+  TRY(e->o.ensure(rows * D * 2));
+  TRY(e->q.ensure(rows * D * 2));
+  TRY(e->delta.ensure(rows * D * 2));
+  TRY(e->hid.ensure(rows * (size_t)e->hidden * 2));
+  return 0;
+}
+
+static int check_ready(vited_engine* e) {
+  VITED_CHECK(e != nullptr, "null engine");
+  VITED_CHECK(e->loaded == (int)e->names.size(), "weights not loaded: %d of %d state_dict tensors received", e->loaded,
+              (int)e->names.size());
+  VITED_CUDA_OK(cudaSetDevice(e->device));
+  return 0;
+}
+
+// items per sub-batch so that token rows stay near chunk_rows
+static int items_per_batch(vited_engine* e) {
+  int64_t n = e->chunk_rows / e->Nd;
+  return (int)(n < 1 ? 1 : n);
+}
+
+// patch tokens of B images -> e->tok (bf16 [B*Ne, D]); img_stride = elements between consecutive images
+static int patch_tokens(vited_engine* e, const float* images, size_t img_stride, int B, cudaStream_t s) {
+  const vited_config& c = e->cfg;
+  const size_t rows = (size_t)B * e->Ne;
+  TRY(e->col.ensure(rows * e->Kpe * 2));
+  TRY(e->tok.ensure(rows * e->D * 2));
+  const size_t img_elems = (size_t)c.in_chans * c.img_size * c.img_size;
+  if (img_stride == img_elems) {
+    e->launches++;
+    TRY(im2col_patches(images, e->col.as<bf16>(), B, c.in_chans, c.img_size, c.patch_size, s));
+  } else {
+    for (int b = 0; b < B; ++b) {
+      e->launches++;
+      TRY(im2col_patches(images + (size_t)b * img_stride, e->col.as<bf16>() + (size_t)b * e->Ne * e->Kpe, 1, c.in_chans,
+                         c.img_size, c.patch_size, s));
+    }
+  }
+  TRY(L_gemm(e, e->col.as<bf16>(), e->patch, e->tok.as<bf16>(), (int)rows, ACT_NONE, s));
+  return 0;
+}
+
+// forward_first_part (vision_transformer.py:382-388) for a sub-batch whose patch tokens are in e->tok.
+static int encoder_stack(vited_engine* e, int B, float* out_tokens, cudaStream_t s) {
+  const size_t rows = (size_t)B * e->Ne;
+  TRY(ensure_rows(e, rows));
+  float* x = e->x.as<float>();
+  bf16* h = e->h.as<bf16>();
+  bf16* delta = e->delta.as<bf16>();
+  e->launches++;
+  TRY(assemble_tokens(e->tok.as<bf16>(), e->pos, e->cls, x, B, e->Ne, e->D, 0, s));
+  for (size_t l = 0; l < e->enc.size(); ++l) {
+    EncBlock& b = e->enc[l];
+    TRY(L_resid_ln(e, x, l == 0 ? nullptr : delta, nullptr, nullptr, 0, &b.norm1, h, B, 0, l == 0 ? 0 : 1, s));
+    TRY(L_gemm(e, h, b.qkv, e->qkv.as<bf16>(), (int)rows, ACT_NONE, s));
+    TRY(L_attn_self(e, e->qkv.as<bf16>(), e->o.as<bf16>(), B, 0, s));
+    TRY(L_gemm(e, e->o.as<bf16>(), b.proj, delta, (int)rows, ACT_NONE, s));
+    TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, B, 0, 1, s));
+    TRY(L_gemm(e, h, b.fc1, e->hid.as<bf16>(), (int)rows, ACT_GELU, s));
+    TRY(L_gemm(e, e->hid.as<bf16>(), b.fc2, delta, (int)rows, ACT_NONE, s));
+  }
+  e->launches++;
+  TRY(add_delta_out(x, delta, out_tokens, rows, e->D, s));
+  return 0;
+}
+
+// prepare_x2 (vision_transformer.py:390-395) [+ decoder layer 0's self-attention sub-block when cached] for a
+// sub-batch whose patch tokens are in e->tok. Result (split layout, B sequences) is left in e->x.
+static int decoder_item_state(vited_engine* e, int B, cudaStream_t s) {
+  const size_t rows = (size_t)B * e->Nd;
+  TRY(ensure_rows(e, rows));
+  float* x = e->x.as<float>();
+  e->launches++;
+  TRY(assemble_tokens(e->tok.as<bf16>(), e->pos, e->cls, x, B, e->Ne, e->D, 1, s));
+  if (e->cache_layer0) {
+    DecBlock& b = e->dec[0];
+    TRY(L_resid_ln(e, x, nullptr, nullptr, nullptr, 0, &b.norm1, e->h.as<bf16>(), B, 1, 0, s));
+    TRY(L_gemm(e, e->h.as<bf16>(), b.qkv, e->qkv.as<bf16>(), (int)rows, ACT_NONE, s));
+    TRY(L_attn_self(e, e->qkv.as<bf16>(), e->o.as<bf16>(), B, 1, s));
+    TRY(L_gemm(e, e->o.as<bf16>(), b.proj, e->delta.as<bf16>(), (int)rows, ACT_NONE, s));
+    TRY(L_resid_ln(e, x, e->delta.as<bf16>(), nullptr, nullptr, 0, nullptr, nullptr, B, 1, 1, s));
+  }
+  return 0;
+}
+
+// copy a sub-batch in split layout (B sequences in e->x) into rows [i0, i0+B) of a split-layout buffer of N sequences
+static int scatter_split(vited_engine* e, float* dst, int N, int i0, int B, cudaStream_t s) {
+  const size_t D = e->D, Ne = e->Ne;
+  const float* x = e->x.as<float>();
+  VITED_CUDA_OK(cudaMemcpyAsync(dst + (size_t)i0 * Ne * D, x, (size_t)B * Ne * D * 4, cudaMemcpyDeviceToDevice, s));
+  VITED_CUDA_OK(cudaMemcpyAsync(dst + ((size_t)N * Ne + i0) * D, x + (size_t)B * Ne * D, (size_t)B * D * 4,
+                                cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+// kv(norm_context(ctx)) for every decoder layer (vision_transformer.py:270, :178): ctx [n*Ne, D] f32 ->
+// e->kv, layer l at offset l * n*Ne*2D (bf16)
+static int build_kv(vited_engine* e, const float* ctx, int n, cudaStream_t s) {
+  const size_t rows = (size_t)n * e->Ne;
+  const size_t per_layer = rows * 2 * e->D;
+  TRY(e->kv.ensure(per_layer * e->dec.size() * 2));
+  TRY(e->h.ensure(rows * e->D * 2));
+  for (size_t l = 0; l < e->dec.size(); ++l) {
+    DecBlock& b = e->dec[l];
+    TRY(L_resid_ln(e, const_cast<float*>(ctx), nullptr, nullptr, nullptr, 0, &b.norm_context, e->h.as<bf16>(), n, 0, 0,
+                   s));
+    TRY(L_gemm(e, e->h.as<bf16>(), b.kv, e->kv.as<bf16>() + l * per_layer, (int)rows, ACT_NONE, s));
+  }
+  return 0;
+}
+
+// cross_part + head (vision_transformer.py:397-401, :415-417) for P pairs.
+//   ci[p]: context sequence inside the current KV block; xj[p]: item whose decoder state seeds the pair.
+static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, const float* xsrc, int n_src,
+                        int n_kv_seq, HeadArgs head, cudaStream_t s) {
+  const size_t rows = (size_t)P * e->Nd;
+  TRY(ensure_rows(e, rows));
+  float* x = e->x.as<float>();
+  bf16* h = e->h.as<bf16>();
+  bf16* delta = e->delta.as<bf16>();
+  const size_t kv_per_layer = (size_t)n_kv_seq * e->Ne * 2 * e->D;
+  for (size_t l = 0; l < e->dec.size(); ++l) {
+    DecBlock& b = e->dec[l];
+    const bool first = (l == 0);
+    if (first && e->cache_layer0) {
+      TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s));
+    } else {
+      if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
+      else TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
+      TRY(L_gemm(e, h, b.qkv, e->qkv.as<bf16>(), (int)rows, ACT_NONE, s));
+      TRY(L_attn_self(e, e->qkv.as<bf16>(), e->o.as<bf16>(), P, 1, s));
+      TRY(L_gemm(e, e->o.as<bf16>(), b.proj, delta, (int)rows, ACT_NONE, s));
+      TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm_cross, h, P, 1, 1, s));
+    }
+    TRY(L_gemm(e, h, b.q, e->q.as<bf16>(), (int)rows, ACT_NONE, s));
+    TRY(L_attn_cross(e, e->q.as<bf16>(), e->kv.as<bf16>() + l * kv_per_layer, e->o.as<bf16>(), P, n_kv_seq, ci, s));
+    TRY(L_gemm(e, e->o.as<bf16>(), b.cproj, delta, (int)rows, ACT_NONE, s));
+    TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, P, 1, 1, s));
+    TRY(L_gemm(e, h, b.fc1, e->hid.as<bf16>(), (int)rows, ACT_GELU, s));
+    TRY(L_gemm(e, e->hid.as<bf16>(), b.fc2, delta, (int)rows, ACT_NONE, s));
+  }
+  head.x = x + (size_t)P * e->Ne * e->D;
+  head.delta = delta + (size_t)P * e->Ne * e->D;
+  head.ln_w = e->norm.w; head.ln_b = e->norm.b; head.head_w = e->head_w; head.head_b = e->head_b;
+  head.P = P; head.D = e->D; head.C = e->C; head.eps = 1e-6f;
+  e->launches++;
+  TRY(head_logits(head, s));
+  return 0;
+}
+
+static int upload_ints(DevBuf& buf, const std::vector<int>& v, cudaStream_t s) {
+  TRY(buf.ensure(v.size() * sizeof(int) + 16));
+  VITED_CUDA_OK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  VITED_CUDA_OK(cudaStreamSynchronize(s));  // the host vector may die right after this call
+  return 0;
+}
+
+}  // namespace vited
+
+// =====================================================================================================================
+// C-ABI
+// =====================================================================================================================
+extern "C" {
+
+const char* vited_last_error(void) { return get_error(); }
+
+int vited_create(const vited_config* cfg, int device, vited_engine** out) {
+  VITED_CHECK(cfg != nullptr && out != nullptr, "vited_create: null argument");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  VITED_CHECK(ce == cudaSuccess && ndev > 0, "vited_create: no CUDA device available (%s); this path has no CPU fallback",
+              cudaGetErrorString(ce));
+  VITED_CHECK(device >= 0 && device < ndev, "vited_create: device %d out of range (%d devices)", device, ndev);
+  VITED_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VITED_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  VITED_CHECK(prop.major == 10, "vited_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+              prop.major, prop.minor);
+  vited_engine* e = new vited_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  const char* cr = getenv("VITED_CHUNK_ROWS");
+  if (cr && atoll(cr) > 0) e->chunk_rows = atoll(cr);
+  if (build(e) != 0) {
+    vited_destroy(e);
+    return 1;
+  }
+  *out = e;
+  return 0;
+}
+
+void vited_destroy(vited_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (void* p : e->owned) cudaFree(p);
+  DevBuf* bufs[] = {&e->x, &e->h, &e->qkv, &e->o, &e->q, &e->delta, &e->hid, &e->col, &e->tok, &e->xsrc, &e->enc_tok,
+                    &e->kv, &e->ci, &e->xj, &e->tmp_tok};
+  for (DevBuf* b : bufs) b->release();
+  delete e;
+}
+
+int vited_set_option(vited_engine* e, int option, int64_t value) {
+  VITED_CHECK(e != nullptr, "null engine");
+  switch (option) {
+    case VITED_OPT_GEMM_IMPL: e->gemm_impl = value ? IMPL_REF : IMPL_FAST; return 0;
+    case VITED_OPT_ATTN_IMPL: e->attn_impl = value ? IMPL_REF : IMPL_FAST; return 0;
+    case VITED_OPT_CHUNK_ROWS:
+      VITED_CHECK(value >= 1, "chunk_rows must be positive");
+      e->chunk_rows = value;
+      return 0;
+    case VITED_OPT_CACHE_LAYER0: e->cache_layer0 = value ? 1 : 0; return 0;
+    default: set_error("unknown option %d", option); return 1;
+  }
+}
+
+int vited_load_weight(vited_engine* e, const char* name, const float* data, int64_t numel, void* stream) {
+  VITED_CHECK(e != nullptr && name != nullptr && data != nullptr, "vited_load_weight: null argument");
+  VITED_CUDA_OK(cudaSetDevice(e->device));
+  auto it = e->slots.find(name);
+  VITED_CHECK(it != e->slots.end(), "unexpected key in state_dict: %s", name);
+  Slot& sl = it->second;
+  VITED_CHECK(sl.numel == numel, "size mismatch for %s: expected %lld elements, got %lld", name, (long long)sl.numel,
+              (long long)numel);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (sl.to_bf16) {
+    TRY(f32_to_bf16(data, reinterpret_cast<bf16*>(sl.dst), (size_t)numel, s));
+  } else {
+    VITED_CUDA_OK(cudaMemcpyAsync(sl.dst, data, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  VITED_CUDA_OK(cudaStreamSynchronize(s));
+  if (!sl.loaded) {
+    sl.loaded = true;
+    e->loaded++;
+  }
+  return 0;
+}
+
+int vited_num_weights_expected(vited_engine* e) { return e ? (int)e->names.size() : 0; }
+int vited_num_weights_loaded(vited_engine* e) { return e ? e->loaded : 0; }
+const char* vited_weight_name(vited_engine* e, int i) {
+  if (!e || i < 0 || i >= (int)e->names.size()) return nullptr;
+  return e->names[i].c_str();
+}
+
+int vited_encode(vited_engine* e, const float* images, int B, float* out_tokens, void* stream) {
+  TRY(check_ready(e));
+  VITED_CHECK(B >= 0 && (B == 0 || (images && out_tokens)), "vited_encode: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
+  const int step = items_per_batch(e);
+  for (int i0 = 0; i0 < B; i0 += step) {
+    const int n = (B - i0 < step) ? (B - i0) : step;
+    TRY(patch_tokens(e, images + (size_t)i0 * img, img, n, s));
+    TRY(encoder_stack(e, n, out_tokens + (size_t)i0 * e->Ne * e->D, s));
+  }
+  return 0;
+}
+
+static int decode_impl(vited_engine* e, const float* ctx_tokens, const float* images, size_t img_stride, int B,
+                       float* out_logits, cudaStream_t s) {
+  const int step = items_per_batch(e);
+  for (int i0 = 0; i0 < B; i0 += step) {
+    const int n = (B - i0 < step) ? (B - i0) : step;
+    // decoder input state of the n x2 images
+    TRY(patch_tokens(e, images + (size_t)i0 * img_stride, img_stride, n, s));
+    TRY(decoder_item_state(e, n, s));
+    TRY(e->xsrc.ensure((size_t)n * e->Nd * e->D * 4));
+    VITED_CUDA_OK(cudaMemcpyAsync(e->xsrc.p, e->x.p, (size_t)n * e->Nd * e->D * 4, cudaMemcpyDeviceToDevice, s));
+    TRY(build_kv(e, ctx_tokens + (size_t)i0 * e->Ne * e->D, n, s));
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    TRY(upload_ints(e->ci, idx, s));
+    HeadArgs head = {};
+    head.out = out_logits + (size_t)i0 * e->C;
+    head.ci = nullptr; head.xj = nullptr; head.row_begin = 0; head.n_items = 0;
+    TRY(decode_chunk(e, n, e->ci.as<int>(), e->ci.as<int>(), e->xsrc.as<float>(), n, n, head, s));
+  }
+  return 0;
+}
+
+int vited_decode(vited_engine* e, const float* ctx_tokens, const float* images, int B, float* out_logits,
+                 void* stream) {
+  TRY(check_ready(e));
+  VITED_CHECK(B >= 0 && (B == 0 || (ctx_tokens && images && out_logits)), "vited_decode: bad arguments");
+  const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
+  return decode_impl(e, ctx_tokens, images, img, B, out_logits, (cudaStream_t)stream);
+}
+
+int vited_forward_pairs(vited_engine* e, const float* pairs, int B, float* out_logits, void* stream) {
+  TRY(check_ready(e));
+  VITED_CHECK(B >= 0 && (B == 0 || (pairs && out_logits)), "vited_forward_pairs: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
+  const int step = items_per_batch(e);
+  for (int i0 = 0; i0 < B; i0 += step) {
+    const int n = (B - i0 < step) ? (B - i0) : step;
+    const float* base = pairs + (size_t)i0 * 2 * img;
+    TRY(e->tmp_tok.ensure((size_t)n * e->Ne * e->D * 4));
+    TRY(patch_tokens(e, base, 2 * img, n, s));            // x1 = pairs[:, 0]
+    TRY(encoder_stack(e, n, e->tmp_tok.as<float>(), s));
+    TRY(decode_impl(e, e->tmp_tok.as<float>(), base + img, 2 * img, n, out_logits + (size_t)i0 * e->C, s));  // x2 = pairs[:, 1]
+  }
+  return 0;
+}
+
+int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int row_begin, int row_end, float* out,
+                     void* stream) {
+  TRY(check_ready(e));
+  VITED_CHECK(mode == VITED_GRID_ORDERED_OFFDIAG || mode == VITED_GRID_UPPER_TRI_DIAG, "unknown grid mode %d", mode);
+  VITED_CHECK(N >= 0 && row_begin >= 0 && row_begin <= row_end && row_end <= N, "bad row range [%d, %d) for N=%d",
+              row_begin, row_end, N);
+  if (N == 0 || row_begin == row_end) return 0;
+  VITED_CHECK(images && out, "vited_score_grid: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
+  const size_t D = e->D, Ne = e->Ne, Nd = e->Nd;
+  const int step = items_per_batch(e);
+
+  // 1) decoder input state of every item (columns of the grid): computed once per item, reused by every pair
+  TRY(e->xsrc.ensure((size_t)N * Nd * D * 4));
+  for (int i0 = 0; i0 < N; i0 += step) {
+    const int n = (N - i0 < step) ? (N - i0) : step;
+    TRY(patch_tokens(e, images + (size_t)i0 * img, img, n, s));
+    TRY(decoder_item_state(e, n, s));
+    TRY(scatter_split(e, e->xsrc.as<float>(), N, i0, n, s));
+  }
+
+  // 2) context rows in blocks whose per-layer K/V cache stays within ~8 GB
+  const size_t kv_bytes_per_item = e->dec.size() * Ne * 2 * D * 2;
+  int rb = (int)((size_t)8e9 / kv_bytes_per_item);
+  if (rb < 1) rb = 1;
+  const int pairs_per_chunk = items_per_batch(e);
+  for (int r0 = row_begin; r0 < row_end; r0 += rb) {
+    const int r1 = (r0 + rb < row_end) ? (r0 + rb) : row_end;
+    const int nr = r1 - r0;
+    // encoder tokens of the block's items
+    TRY(e->enc_tok.ensure((size_t)nr * Ne * D * 4));
+    for (int i0 = 0; i0 < nr; i0 += step) {
+      const int n = (nr - i0 < step) ? (nr - i0) : step;
+      TRY(patch_tokens(e, images + (size_t)(r0 + i0) * img, img, n, s));
+      TRY(encoder_stack(e, n, e->enc_tok.as<float>() + (size_t)i0 * Ne * D, s));
+    }
+    TRY(build_kv(e, e->enc_tok.as<float>(), nr, s));
+    // pair list of the block, i-major (data/datasets/pieces_dataset.py:27-32 / hisfrag.py:166-167)
+    std::vector<int> ci, xj;
+    if (mode == VITED_GRID_ORDERED_OFFDIAG) {
+      ci.reserve((size_t)nr * (N - 1));
+      xj.reserve((size_t)nr * (N - 1));
+      for (int i = r0; i < r1; ++i)
+        for (int j = 0; j < N; ++j)
+          if (j != i) { ci.push_back(i - r0); xj.push_back(j); }
+    } else {
+      for (int i = r0; i < r1; ++i)
+        for (int j = i; j < N; ++j) { ci.push_back(i - r0); xj.push_back(j); }
+    }
+    if (ci.empty()) continue;
+    TRY(upload_ints(e->ci, ci, s));
+    TRY(upload_ints(e->xj, xj, s));
+    const size_t total = ci.size();
+    for (size_t p0 = 0; p0 < total; p0 += pairs_per_chunk) {
+      const int P = (int)((total - p0 < (size_t)pairs_per_chunk) ? (total - p0) : pairs_per_chunk);
+      HeadArgs head = {};
+      head.out = out + (size_t)(r0 - row_begin) * N * e->C;
+      head.ci = e->ci.as<int>() + p0;
+      head.xj = e->xj.as<int>() + p0;
+      head.row_begin = 0;  // ci is already relative to r0
+      head.n_items = N;
+      TRY(decode_chunk(e, P, e->ci.as<int>() + p0, e->xj.as<int>() + p0, e->xsrc.as<float>(), N, nr, head, s));
+    }
+  }
+  return 0;
+}
+
+int64_t vited_launch_count(vited_engine* e) { return e ? e->launches : 0; }
+int64_t vited_workspace_bytes(vited_engine* e) { return e ? e->workspace_bytes() : 0; }
+
+// ---- single-kernel entry points ----
+int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,
+                  void* stream) {
+  return gemm_bf16((const bf16*)A, (const bf16*)W, bias, (bf16*)C, M, N, K, act, impl, (cudaStream_t)stream);
+}
+
+int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
+                      int n_patch, int has_cls, int D, float eps, void* stream) {
+  ResidLnArgs a;
+  a.x = x; a.delta = (const bf16*)delta; a.gather_src = nullptr; a.gather_idx = nullptr; a.n_src_seq = 0;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.h = (bf16*)h; a.n_seq = n_seq; a.n_patch = n_patch; a.has_cls = has_cls; a.D = D;
+  a.write_x = 1; a.eps = eps;
+  return resid_ln(a, (cudaStream_t)stream);
+}
+
+int vited_op_attention(const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o, int o_ld,
+                       int n_seq, int n_heads, int head_dim, int nq_patch, int q_has_cls, int nk_patch,
+                       int k_has_cls, int n_kv_seq, const int32_t* kv_index, float scale, int impl, void* stream) {
+  AttnArgs a;
+  a.q = (const bf16*)q; a.q_ld = q_ld; a.k = (const bf16*)k; a.k_ld = k_ld; a.v = (const bf16*)v; a.v_ld = v_ld;
+  a.o = (bf16*)o; a.o_ld = o_ld; a.n_seq = n_seq; a.n_heads = n_heads; a.head_dim = head_dim;
+  a.nq_patch = nq_patch; a.q_has_cls = q_has_cls; a.nk_patch = nk_patch; a.k_has_cls = k_has_cls;
+  a.n_kv_seq = n_kv_seq; a.kv_index = kv_index; a.scale = scale;
+  return attention(a, impl, (cudaStream_t)stream);
+}
+
+int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, void* stream) {
+  return im2col_patches(images, (bf16*)out, B, C, S, p, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators
+// in TMEM, double buffered) -> tcgen05.ld epilogue (bias / exact-erf GELU) -> swizzled smem staging -> TMA store.
+//
+// Computes what every Linear on the ViT-ED hot path computes (reference: models/vision_transformer.py:34,38 qkv/proj,
+// :151-156 q/kv/proj, timm Mlp fc1/fc2, timm PatchEmbed conv-as-GEMM):  C = act(A * W^T + bias).
+//   A [M,K] bf16 row-major (activations), W [N,K] bf16 row-major (PyTorch Linear layout) -> both operands K-major.
+//
+// Warp roles (384 threads, 1 CTA / SM):
+//   warp 0 lane 0 : TMA producer            warp 1 lane 0 : tcgen05.mma issuer
+//   warp 2        : TMEM allocator          warps 4..11   : epilogue (warp%4 = TMEM lane quarter, 2 column halves)
+#include "kernels.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace vited {
+
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static int g_num_sms = 0;
+static std::once_flag g_once;
+static int g_init_status = 0;
+
+static void init_driver_once() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    g_init_status = 1;
+    return;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+}
+
+int gemm_num_sms() {
+  std::call_once(g_once, init_driver_once);
+  return g_num_sms;
+}
+
+// 2-D bf16 tensor map: inner dim = cols (contiguous), outer dim = rows, 128B swizzle, box = 64 cols x box_rows.
+static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                     uint32_t box_rows) {
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p cols=%llu rows=%llu stride=%llu box_rows=%u", (int)r, ptr,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_rows);
+    return 1;
+  }
+  return 0;
+}
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 128) ? 6 : 4;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t C_BYTES = BM * BN * 2;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t SMEM_BYTES = 1024 + kStages * STAGE_BYTES + C_BYTES + 256;
+};
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = smem + kStages * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + Cfg::C_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_blks = (M + BM - 1) / BM;
+  const int n_blks = (N + BN - 1) / BN;
+  const int num_tiles = m_blks * n_blks;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], kEpiWarps);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 10);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(&tmA, &full[stage], a_dst, kb * BK, m_blk * BM);
+          tma_load_2d(&tmB, &full[stage], b_dst, kb * BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1, 20);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 21);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int hf = ew >> 2;   // column half
+    const int r = q * 32 + lane;
+    constexpr int NCHUNK = BN / 64;  // 32-column chunks per warp
+    uint32_t as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+      const int n_base = n_blk * BN;
+      mbar_wait(&tfull[as], aphase, 30);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int col = hf * (BN / 2) + ch * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + as * BN + col + (static_cast<uint32_t>(q * 32) << 16), v);
+        tmem_ld_wait();
+        const int n0 = n_base + col;
+        float f[32];
+        if (n0 + 32 <= N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float b = (n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+            f[i] = __uint_as_float(v[i]) + b;
+          }
+        }
+        if (ACT == ACT_GELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+        }
+        // staging layout == what a 128B-swizzled TMA store box {64 cols, 128 rows} expects
+        uint8_t* rowp = sC + (col >> 6) * (BM * 128) + r * 128;
+        const int cc0 = (col & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 pk;
+          pk.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+          pk.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+          pk.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+          pk.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+          *reinterpret_cast<uint4*>(rowp + (((cc0 + i) ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      // this warp's part of the accumulator stage is drained
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (ew == 0 && lane == 0) {
+#pragma unroll
+        for (int sl = 0; sl < BN / 64; ++sl) {
+          if (n_base + sl * 64 < N) tma_store_2d(&tmC, sC + sl * (BM * 128), n_base + sl * 64, m_blk * BM);
+        }
+        tma_store_commit();
+        tma_store_wait_read();
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (ew == 0 && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int ACT>
+static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
+                     int N, int K, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_tc_kernel<BN, ACT><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act,
+              cudaStream_t stream);
+
+static int g_block_n = 0;  // 0 = auto; VITED_GEMM_BN=128|192 overrides (tuning knob)
+
+int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
+              cudaStream_t stream) {
+  VITED_CHECK(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  if (impl == IMPL_REF) return gemm_simt(A, W, bias, C, M, N, K, act, stream);
+  std::call_once(g_once, init_driver_once);
+  if (g_init_status) return 1;
+  VITED_CHECK(K % 8 == 0 && N % 8 == 0, "gemm_bf16: K and N must be multiples of 8 (TMA 16-byte strides), got K=%d N=%d",
+              K, N);
+  VITED_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+              "gemm_bf16: operands must be 16-byte aligned");
+  if (g_block_n == 0) {
+    const char* e = getenv("VITED_GEMM_BN");
+    g_block_n = e ? atoi(e) : -1;
+  }
+  int bn = 128;
+  if (g_block_n == 192 || (g_block_n < 0 && N % 192 == 0 && N % 128 != 0)) bn = 192;
+  if (g_block_n == 128) bn = 128;
+  CUtensorMap tA, tB, tC;
+  if (make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, BM)) return 1;
+  if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)bn)) return 1;
+  if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, BM)) return 1;
+  if (bn == 128) {
+    return act == ACT_GELU ? launch_tc<128, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                           : launch_tc<128, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+  }
+  return act == ACT_GELU ? launch_tc<192, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                         : launch_tc<192, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+}
+
+}  // namespace vited

@@ -1,0 +1,80 @@
+// Internal launcher interface between the engine (engine.cu) and the kernels. Everything takes raw device
+// pointers and a cudaStream_t; every launcher returns 0 on success and sets vited::set_error() otherwise.
+#pragma once
+#include "common.cuh"
+
+namespace vited {
+
+enum { ACT_NONE = 0, ACT_GELU = 1 };
+enum { IMPL_FAST = 0, IMPL_REF = 1 };  // IMPL_REF: plain SIMT kernels kept as on-device debugging references
+
+// ---- GEMM: C[M,N] (bf16) = act(A[M,K] (bf16, row-major) * W[N,K]^T (bf16, row-major) + bias[N] (f32)) ----
+// IMPL_FAST: persistent warp-specialised tcgen05/TMEM kernel fed by TMA (gemm_tc.cu).
+int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
+              cudaStream_t stream);
+int gemm_num_sms();
+
+// ---- row-wise kernels (rowops.cu) ----
+// x[r,:] = (gather ? src[map(r),:] : x[r,:]) + delta[r,:]; optionally h[r,:] = LayerNorm(x[r,:]) * w + b (bf16).
+// Row space is the "split" layout: n_seq*n_patch patch rows followed by n_cls cls rows (n_cls = n_seq or 0).
+struct ResidLnArgs {
+  float* x;              // [R, D] residual stream (fp32), updated in place when write_x
+  const bf16* delta;     // [R, D] or null
+  const float* gather_src;   // split-layout source [n_src_seq*n_patch (+ n_src_seq cls rows), D] or null
+  const int* gather_idx;     // [n_seq] source sequence of every destination sequence
+  int n_src_seq;
+  const float* ln_w;     // null -> no LayerNorm output
+  const float* ln_b;
+  bf16* h;               // [R, D]
+  int n_seq, n_patch, has_cls, D;
+  int write_x;
+  float eps;
+};
+int resid_ln(const ResidLnArgs& a, cudaStream_t stream);
+
+// images [B,3,S,S] f32 -> patch matrix [B*G*G, 3*p*p] bf16, column = c*p*p + py*p + px (Conv2d weight.view order)
+int im2col_patches(const float* images, bf16* out, int B, int C, int S, int p, cudaStream_t stream);
+
+// x0 (f32, split layout, B sequences): patch rows = tok (bf16 [B*Np, D]) + pos[1+t]; cls rows = cls + pos[0]
+int assemble_tokens(const bf16* tok, const float* pos_embed, const float* cls_token, float* x, int B, int n_patch,
+                    int D, int with_cls, cudaStream_t stream);
+
+// final: y = LayerNorm(x_cls + delta_cls); logits = y * Wh^T + bh; scattered into the score matrix.
+struct HeadArgs {
+  const float* x;       // cls rows [P, D] f32
+  const bf16* delta;    // cls rows [P, D] or null
+  const float* ln_w;
+  const float* ln_b;
+  const float* head_w;  // [C, D]
+  const float* head_b;  // [C]
+  float* out;
+  const int* ci;        // pair -> ctx item (row of the grid); null => linear output out[p*C + c]
+  const int* xj;        // pair -> x2 item (column)
+  int row_begin, n_items;
+  int P, D, C;
+  float eps;
+};
+int head_logits(const HeadArgs& a, cudaStream_t stream);
+
+// plain copy/convert helpers
+int f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t stream);
+int add_delta_out(const float* x, const bf16* delta, float* out, size_t rows, int D, cudaStream_t stream);
+
+// ---- attention (attention.cu) ----
+// Sequences live in the split layout. Logical token s of sequence b: s==0 && has_cls ? cls row : patch row.
+struct AttnArgs {
+  const bf16* q; int q_ld;      // row stride in elements
+  const bf16* k; int k_ld;
+  const bf16* v; int v_ld;
+  bf16* o; int o_ld;
+  int n_seq;                    // number of query sequences (pairs / items)
+  int n_heads, head_dim;
+  int nq_patch, q_has_cls;      // query tokens per sequence = nq_patch + q_has_cls
+  int nk_patch, k_has_cls;      // key tokens per sequence
+  int n_kv_seq;                 // number of key/value sequences in the k/v buffers
+  const int* kv_index;          // [n_seq] key/value sequence per query sequence; null => identity
+  float scale;
+};
+int attention(const AttnArgs& a, int impl, cudaStream_t stream);
+
+}  // namespace vited

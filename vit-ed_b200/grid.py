@@ -1,0 +1,165 @@
+"""All-pairs grid drivers: what replaces the pair loops of evaluation.py:101-131 (puzzle) and hisfrag.py:161-296
+(Hisfrag20), plus the integer bookkeeping around them (pair enumeration, row sharding, consumer layouts).
+
+Multi-GPU: the grid shards by rows with no data-path collective; every rank encodes all items itself and scores its
+row block; ONE all-gather of the score blocks at the end replaces the shared-filesystem polling of
+hisfrag.py:251-276.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------------------- pair enumeration
+def ordered_pairs(n):
+    """[(i, j) for i for j if i != j], i-major (data/datasets/pieces_dataset.py:27-32) as int32 [n(n-1), 2]."""
+    i = np.repeat(np.arange(n, dtype=np.int32), n)
+    j = np.tile(np.arange(n, dtype=np.int32), n)
+    keep = i != j
+    return np.stack([i[keep], j[keep]], axis=1)
+
+
+def ordered_pair_index(i, j, n):
+    """entry index of (i, j) in ordered_pairs(n): i*(n-1) + (j if j < i else j-1)."""
+    return i * (n - 1) + (j if j < i else j - 1)
+
+
+def upper_tri_pairs(n):
+    """torch.combinations(arange(n), r=2, with_replacement=True) (hisfrag.py:166-167): rows (a, b), a <= b, a-major."""
+    a, b = np.triu_indices(n)
+    return np.stack([a.astype(np.int32), b.astype(np.int32)], axis=1)
+
+
+# --------------------------------------------------------------------------------------------- row sharding
+def indicates_row_ranges(indexes, num_replicas):
+    """Row boundaries computed exactly like DistributedIndicatesSampler (data/samplers.py:108-137): split the sorted
+    first-column ``indexes`` into ceil(P/world)-sized chunks and snap each boundary to a row. Returns ``sizes`` with
+    len(chunks)+1 entries; rank r owns rows [sizes[r], sizes[r+1]). (When a row straddles two chunks the reference
+    moves the boundary to ``row - 1``; kept as is.)"""
+    indexes = np.asarray(indexes)
+    n_per = math.ceil(len(indexes) / num_replicas)
+    starts = list(range(0, len(indexes), n_per))
+    sizes = [0]
+    for c in range(1, len(starts)):
+        first = int(indexes[starts[c]])
+        prev_last = int(indexes[starts[c] - 1])
+        sizes.append(first - 1 if first == prev_last else first)
+    sizes.append(int(indexes[-1]) + 1)
+    return sizes
+
+
+def hisfrag_row_range(n, world, rank):
+    """Rows of the upper-triangular grid owned by ``rank`` (hisfrag.py:166-170)."""
+    sizes = indicates_row_ranges(upper_tri_pairs(n)[:, 0], world)
+    if rank + 1 >= len(sizes):
+        return n, n  # fewer chunks than ranks: this rank has nothing (the reference would raise IndexError)
+    return sizes[rank], sizes[rank + 1]
+
+
+def equal_row_range(n_rows, world, rank):
+    """Contiguous equal split (every puzzle row has N-1 pairs)."""
+    per = math.ceil(n_rows / world)
+    lo = min(rank * per, n_rows)
+    return lo, min(lo + per, n_rows)
+
+
+# --------------------------------------------------------------------------------------------- collectives
+def _all_gather_rows(block, ranges, n_rows):
+    """all-gather variable-height row blocks -> [n_rows, ...] on every rank (pads to the tallest block)."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    tallest = max(hi - lo for lo, hi in ranges)
+    padded = block.new_zeros((tallest,) + tuple(block.shape[1:]))
+    padded[:block.shape[0]] = block
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded)
+    out = block.new_zeros((n_rows,) + tuple(block.shape[1:]))
+    for (lo, hi), buf in zip(ranges, bufs):
+        out[lo:hi] = buf[:hi - lo]
+    return out
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+# --------------------------------------------------------------------------------------------- grid entries
+@torch.no_grad()
+def score_puzzle(model, images, gather=True):
+    """images [N,3,S,S] (all pieces, same on every rank) -> logits [N, N, C] fp32, logits[i, j] = model pair (i, j);
+    the diagonal is zero (the reference never scores i == j). Replaces evaluation.py:101-107."""
+    rank, world = _dist_info()
+    n = images.shape[0]
+    ranges = [equal_row_range(n, world, r) for r in range(world)]
+    lo, hi = ranges[rank]
+    block = model.score_grid(images, _lib.GRID_ORDERED_OFFDIAG, lo, hi)
+    if world == 1 or not gather:
+        return block
+    return _all_gather_rows(block, ranges, n)
+
+
+@torch.no_grad()
+def score_fragments(model, images, gather=True):
+    """images [N,3,S,S] -> symmetric similarity logits [N, N] fp32 (raw logits, no sigmoid: hisfrag.py:230-231,
+    :281-292). Rows are sharded as DistributedIndicatesSampler does (hisfrag.py:170)."""
+    rank, world = _dist_info()
+    n = images.shape[0]
+    if world == 1:
+        ranges = [(0, n)]
+    else:
+        sizes = indicates_row_ranges(upper_tri_pairs(n)[:, 0], world)
+        ranges = [(sizes[r], sizes[r + 1]) if r + 1 < len(sizes) else (n, n) for r in range(world)]
+    lo, hi = ranges[rank]
+    block = model.score_grid(images, _lib.GRID_UPPER_TRI_DIAG, lo, hi)[..., 0]
+    if world > 1 and gather:
+        upper = _all_gather_rows(block, ranges, n)
+    elif world > 1:
+        return block
+    else:
+        upper = block
+    return mirror_upper(upper)
+
+
+def mirror_upper(upper):
+    """sim[a, b] = sim[b, a] = score(a, b) for a <= b (hisfrag.py:291-292)."""
+    tri = torch.triu(upper)
+    return tri + torch.triu(upper, diagonal=1).transpose(0, 1)
+
+
+# --------------------------------------------------------------------------------------------- consumer layouts
+def puzzle_distance(logits):
+    """1 - sigmoid(logit) (evaluation.py:109-114), fp32 [N, N, 4] on the host as numpy."""
+    return (1.0 - torch.sigmoid(logits)).cpu().numpy()
+
+
+def make_distance_function(distance, side_enum):
+    """The closure of evaluation.py:116-131 as an array lookup. ``distance[i, j]`` is indexed by origin_piece_id;
+    bin 0: i.right-j.left, 1: i.bottom-j.top, 2: i.left-j.right, 3: i.top-j.bottom; x1000; inf otherwise."""
+    def distance_function(piece_i, piece_i_side, piece_j, piece_j_side):
+        pred = distance[piece_i.origin_piece_id][piece_j.origin_piece_id]
+        if piece_j_side == side_enum.left:
+            if piece_i_side == side_enum.right:
+                return pred[0] * 1000.
+        if piece_j_side == side_enum.right:
+            if piece_i_side == side_enum.left:
+                return pred[2] * 1000.
+        if piece_j_side == side_enum.top:
+            if piece_i_side == side_enum.bottom:
+                return pred[1] * 1000.
+        if piece_j_side == side_enum.bottom:
+            if piece_i_side == side_enum.top:
+                return pred[3] * 1000.
+        return float('inf')
+    return distance_function
+
+
+def similarity_to_distance(sim):
+    """fp16 similarity matrix then ``1 - sim`` (hisfrag.py:281-296) -> numpy fp16 [N, N]."""
+    sim16 = sim.detach().to('cpu').type(torch.float16)
+    return (1 - sim16).numpy()

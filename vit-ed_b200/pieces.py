@@ -1,0 +1,66 @@
+"""Host-side piece preparation for the puzzle grid: crop geometry, LAB->RGB, resize, normalise.
+
+The reference redoes this work 2*N*(N-1) times inside DataLoader workers (data/datasets/pieces_dataset.py:34-56); it
+is deterministic per piece, so here it runs once per piece (O(N)) with the same cv2 / PIL / torchvision calls and the
+result is uploaded once. Integer geometry is bit-exact with paikin_tal_solver/puzzle_importer.py:182-232, :430-446.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+def grid_geometry(img_h, img_w, piece_width):
+    """(numb_rows, numb_cols, top, left): floor grid, centred (puzzle_importer.py:196-213)."""
+    numb_cols = int(math.floor(img_w / piece_width))
+    numb_rows = int(math.floor(img_h / piece_width))
+    if numb_cols == 0 or numb_rows == 0:
+        raise ValueError("Image size is too small for the image.  Check your setup")
+    top = (img_h - numb_rows * piece_width) // 2
+    left = (img_w - numb_cols * piece_width) // 2
+    return numb_rows, numb_cols, top, left
+
+
+def erosion_crop(piece_width, erosion):
+    """(eroded side, offset): ceil(w*(1-e)) and Python-round centre crop (puzzle_importer.py:224, :430-446)."""
+    side = math.ceil(piece_width * (1 - erosion))
+    side = side if side < piece_width else piece_width
+    off = int(round((piece_width - side) / 2.0))
+    return side, off
+
+
+def make_pieces_lab(img_bgr, piece_width, erosion=0.0):
+    """BGR uint8 image -> (list of eroded LAB uint8 pieces in row-major piece-id order, (rows, cols)).
+    Mirrors Puzzle._load_puzzle_image + make_pieces (puzzle_importer.py:136-156, :182-232)."""
+    import cv2
+    lab = cv2.cvtColor(img_bgr, cv2.COLOR_BGR2LAB)
+    h, w = img_bgr.shape[:2]
+    rows, cols, top, left = grid_geometry(h, w, piece_width)
+    side, off = erosion_crop(piece_width, erosion)
+    pieces = []
+    for r in range(rows):
+        for c in range(cols):
+            y0 = top + r * piece_width + off
+            x0 = left + c * piece_width + off
+            pieces.append(lab[y0:y0 + side, x0:x0 + side, :])
+    return pieces, (rows, cols)
+
+
+def piece_to_tensor(lab_piece, img_size):
+    """LAB uint8 [s,s,3] -> fp32 [3,S,S] in [-1,1]; same calls as PiecesDataset.__getitem__ + TwoImgSyncEval
+    (pieces_dataset.py:35-46, data/transforms.py:14-18)."""
+    import cv2
+    from torchvision import transforms
+    rgb = cv2.cvtColor(np.ascontiguousarray(lab_piece), cv2.COLOR_LAB2RGB)
+    pil = transforms.ToPILImage()(rgb)
+    norm = transforms.Compose([
+        transforms.Resize(img_size),
+        transforms.ToTensor(),
+        transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+    ])
+    return norm(pil)
+
+
+def pieces_to_batch(lab_pieces, img_size):
+    """[N,3,S,S] fp32 (CPU); upload once with .cuda()."""
+    return torch.stack([piece_to_tensor(p, img_size) for p in lab_pieces], dim=0)
