@@ -59,7 +59,8 @@ enum {
   VITED_OPT_GEMM_IMPL = 0,      /* 0 = tcgen05/TMA kernel (default), 1 = SIMT debugging reference kernel        */
   VITED_OPT_ATTN_IMPL = 1,      /* 0 = tensor-core flash kernel (default), 1 = SIMT debugging reference kernel   */
   VITED_OPT_CHUNK_ROWS = 2,     /* target token rows per decoder chunk (default 262144)                          */
-  VITED_OPT_CACHE_LAYER0 = 3    /* 1 (default) = run decoder layer 0's self-attention once per item, not per pair */
+  VITED_OPT_CACHE_LAYER0 = 3,   /* 1 (default) = run decoder layer 0's self-attention once per item, not per pair */
+  VITED_OPT_PROFILE = 4         /* 1 = record a CUDA event before every launch (see vited_profile_json); default 0   */
 };
 
 /* Library-wide last error message (thread-local). */
@@ -104,6 +105,10 @@ VITED_API int vited_score_grid(vited_engine* e, const float* images, int N, int 
 
 /* number of kernels launched by this engine since creation (bench.py's gpu_launches) */
 VITED_API int64_t vited_launch_count(vited_engine* e);
+/* Per-kernel-class device time since profiling was switched on / last read, as a JSON object
+ * {"<class>": {"ms":, "flops":, "bytes":, "launches":}, ...} (algorithmic flops / bytes of the launches). Synchronises
+ * `stream`, resets the counters. The string is owned by the engine and valid until the next call. */
+VITED_API const char* vited_profile_json(vited_engine* e, void* stream);
 /* bytes of device workspace currently held */
 VITED_API int64_t vited_workspace_bytes(vited_engine* e);
 

@@ -37,6 +37,7 @@ OPT_GEMM_IMPL = 0
 OPT_ATTN_IMPL = 1
 OPT_CHUNK_ROWS = 2
 OPT_CACHE_LAYER0 = 3
+OPT_PROFILE = 4
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -57,6 +58,7 @@ SIGNATURES = {
     "vited_decode": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "vited_forward_pairs": (_i, [_vp, _vp, _i, _vp, _vp]),
     "vited_score_grid": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "vited_profile_json": (ctypes.c_char_p, [_vp, _vp]),
     "vited_launch_count": (_i64, [_vp]),
     "vited_workspace_bytes": (_i64, [_vp]),
     "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

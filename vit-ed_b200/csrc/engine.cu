@@ -93,6 +93,14 @@ struct vited_engine {
   int64_t chunk_rows = 262144;
   int cache_layer0 = 1;
   int64_t launches = 0;
+  // optional per-kernel timing (bench.py's roofline): one event before every launch, intervals summed per class
+  int profile = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct ProfRec { cudaEvent_t ev; int cls; double flops; double bytes; };
+  std::vector<ProfRec> recs;
+  std::vector<std::string> cls_names;
+  std::string profile_json;
   // workspace
   DevBuf x, h, qkv, o, q, delta, hid, col, tok, xsrc, enc_tok, kv, ci, xj, tmp_tok;
 
@@ -209,8 +217,33 @@ static int build(vited_engine* e) {
 // ------------------------------------------------------------------------------------------------------------
 // launch helpers (count every kernel for bench.py's gpu_launches)
 // ------------------------------------------------------------------------------------------------------------
-static int L_gemm(vited_engine* e, const bf16* A, const Linear& l, bf16* Cout, int M, int act, cudaStream_t s) {
+static int prof_class(vited_engine* e, const std::string& name) {
+  for (size_t i = 0; i < e->cls_names.size(); ++i)
+    if (e->cls_names[i] == name) return (int)i;
+  e->cls_names.push_back(name);
+  return (int)e->cls_names.size() - 1;
+}
+static void prof_mark(vited_engine* e, const char* name, double flops, double bytes, cudaStream_t s) {
   e->launches++;
+  if (!e->profile) return;
+  if (e->ev_used == e->ev_pool.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->ev_pool.push_back(ev);
+  }
+  cudaEvent_t ev = e->ev_pool[e->ev_used++];
+  cudaEventRecord(ev, s);
+  e->recs.push_back({ev, prof_class(e, name), flops, bytes});
+}
+
+static int L_gemm(vited_engine* e, const bf16* A, const Linear& l, bf16* Cout, int M, int act, cudaStream_t s) {
+  if (e->profile) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "gemm_n%d_k%d%s", l.out, l.in, act == ACT_GELU ? "_gelu" : "");
+    prof_mark(e, nm, 2.0 * M * (double)l.out * l.in, 2.0 * ((double)M * l.in + (double)l.out * l.in + (double)M * l.out), s);
+  } else {
+    e->launches++;
+  }
   return gemm_bf16(A, l.w, l.b, Cout, M, l.out, l.in, act, e->gemm_impl, s);
 }
 static int L_resid_ln(vited_engine* e, float* x, const bf16* delta, const float* gsrc, const int* gidx, int n_src,
@@ -219,7 +252,11 @@ static int L_resid_ln(vited_engine* e, float* x, const bf16* delta, const float*
   a.x = x; a.delta = delta; a.gather_src = gsrc; a.gather_idx = gidx; a.n_src_seq = n_src;
   a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
   a.n_seq = n_seq; a.n_patch = e->Ne; a.has_cls = has_cls; a.D = e->D; a.write_x = write_x; a.eps = 1e-6f;
-  e->launches++;
+  {
+    const double rows = (double)n_seq * (e->Ne + (has_cls ? 1 : 0));
+    const double per_row = e->D * (4.0 + (delta ? 2.0 : 0.0) + (write_x ? 4.0 : 0.0) + (ln ? 2.0 : 0.0));
+    prof_mark(e, "resid_ln", 0.0, rows * per_row, s);
+  }
   return resid_ln(a, s);
 }
 static int L_attn_self(vited_engine* e, const bf16* qkv, bf16* o, int n_seq, int has_cls, cudaStream_t s) {
@@ -229,7 +266,10 @@ static int L_attn_self(vited_engine* e, const bf16* qkv, bf16* o, int n_seq, int
   a.n_seq = n_seq; a.n_heads = e->H; a.head_dim = e->hd;
   a.nq_patch = e->Ne; a.q_has_cls = has_cls; a.nk_patch = e->Ne; a.k_has_cls = has_cls;
   a.n_kv_seq = n_seq; a.kv_index = nullptr; a.scale = e->scale;
-  e->launches++;
+  {
+    const double n = e->Ne + (has_cls ? 1 : 0);
+    prof_mark(e, "attn_self", 4.0 * n_seq * n * n * e->D, (double)n_seq * n * e->D * 2.0 * 4.0, s);
+  }
   return attention(a, e->attn_impl, s);
 }
 static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o, int n_seq, int n_kv_seq,
@@ -240,7 +280,7 @@ static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o,
   a.n_seq = n_seq; a.n_heads = e->H; a.head_dim = e->hd;
   a.nq_patch = e->Ne; a.q_has_cls = 1; a.nk_patch = e->Ne; a.k_has_cls = 0;
   a.n_kv_seq = n_kv_seq; a.kv_index = kv_index; a.scale = e->scale;
-  e->launches++;
+  prof_mark(e, "attn_cross", 4.0 * n_seq * (double)e->Nd * e->Ne * e->D, (double)n_seq * e->Nd * e->D * 2.0 * 2.0, s);
   return attention(a, e->attn_impl, s);
 }
 
@@ -278,11 +318,11 @@ static int patch_tokens(vited_engine* e, const float* images, size_t img_stride,
   TRY(e->tok.ensure(rows * e->D * 2));
   const size_t img_elems = (size_t)c.in_chans * c.img_size * c.img_size;
   if (img_stride == img_elems) {
-    e->launches++;
+    prof_mark(e, "im2col", 0.0, (double)rows * e->Kpe * 6.0, s);
     TRY(im2col_patches(images, e->col.as<bf16>(), B, c.in_chans, c.img_size, c.patch_size, s));
   } else {
     for (int b = 0; b < B; ++b) {
-      e->launches++;
+      prof_mark(e, "im2col", 0.0, (double)e->Ne * e->Kpe * 6.0, s);
       TRY(im2col_patches(images + (size_t)b * img_stride, e->col.as<bf16>() + (size_t)b * e->Ne * e->Kpe, 1, c.in_chans,
                          c.img_size, c.patch_size, s));
     }
@@ -298,7 +338,7 @@ static int encoder_stack(vited_engine* e, int B, float* out_tokens, cudaStream_t
   float* x = e->x.as<float>();
   bf16* h = e->h.as<bf16>();
   bf16* delta = e->delta.as<bf16>();
-  e->launches++;
+  prof_mark(e, "assemble", 0.0, (double)rows * e->D * 6.0, s);
   TRY(assemble_tokens(e->tok.as<bf16>(), e->pos, e->cls, x, B, e->Ne, e->D, 0, s));
   for (size_t l = 0; l < e->enc.size(); ++l) {
     EncBlock& b = e->enc[l];
@@ -310,7 +350,7 @@ static int encoder_stack(vited_engine* e, int B, float* out_tokens, cudaStream_t
     TRY(L_gemm(e, h, b.fc1, e->hid.as<bf16>(), (int)rows, ACT_GELU, s));
     TRY(L_gemm(e, e->hid.as<bf16>(), b.fc2, delta, (int)rows, ACT_NONE, s));
   }
-  e->launches++;
+  prof_mark(e, "add_delta_out", 0.0, (double)rows * e->D * 10.0, s);
   TRY(add_delta_out(x, delta, out_tokens, rows, e->D, s));
   return 0;
 }
@@ -321,7 +361,7 @@ static int decoder_item_state(vited_engine* e, int B, cudaStream_t s) {
   const size_t rows = (size_t)B * e->Nd;
   TRY(ensure_rows(e, rows));
   float* x = e->x.as<float>();
-  e->launches++;
+  prof_mark(e, "assemble", 0.0, (double)rows * e->D * 6.0, s);
   TRY(assemble_tokens(e->tok.as<bf16>(), e->pos, e->cls, x, B, e->Ne, e->D, 1, s));
   if (e->cache_layer0) {
     DecBlock& b = e->dec[0];
@@ -338,6 +378,7 @@ static int decoder_item_state(vited_engine* e, int B, cudaStream_t s) {
 static int scatter_split(vited_engine* e, float* dst, int N, int i0, int B, cudaStream_t s) {
   const size_t D = e->D, Ne = e->Ne;
   const float* x = e->x.as<float>();
+  if (e->profile) { prof_mark(e, "copy", 0.0, (double)B * (Ne + 1) * D * 8.0, s); e->launches--; }
   VITED_CUDA_OK(cudaMemcpyAsync(dst + (size_t)i0 * Ne * D, x, (size_t)B * Ne * D * 4, cudaMemcpyDeviceToDevice, s));
   VITED_CUDA_OK(cudaMemcpyAsync(dst + ((size_t)N * Ne + i0) * D, x + (size_t)B * Ne * D, (size_t)B * D * 4,
                                 cudaMemcpyDeviceToDevice, s));
@@ -394,7 +435,7 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
   head.delta = delta + (size_t)P * e->Ne * e->D;
   head.ln_w = e->norm.w; head.ln_b = e->norm.b; head.head_w = e->head_w; head.head_b = e->head_b;
   head.P = P; head.D = e->D; head.C = e->C; head.eps = 1e-6f;
-  e->launches++;
+  prof_mark(e, "head", 0.0, (double)P * e->D * 6.0, s);
   TRY(head_logits(head, s));
   return 0;
 }
@@ -448,6 +489,7 @@ void vited_destroy(vited_engine* e) {
   DevBuf* bufs[] = {&e->x, &e->h, &e->qkv, &e->o, &e->q, &e->delta, &e->hid, &e->col, &e->tok, &e->xsrc, &e->enc_tok,
                     &e->kv, &e->ci, &e->xj, &e->tmp_tok};
   for (DevBuf* b : bufs) b->release();
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -461,6 +503,11 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
       e->chunk_rows = value;
       return 0;
     case VITED_OPT_CACHE_LAYER0: e->cache_layer0 = value ? 1 : 0; return 0;
+    case VITED_OPT_PROFILE:
+      e->profile = value ? 1 : 0;
+      e->recs.clear();
+      e->ev_used = 0;
+      return 0;
     default: set_error("unknown option %d", option); return 1;
   }
 }
@@ -621,6 +668,42 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
     }
   }
   return 0;
+}
+
+const char* vited_profile_json(vited_engine* e, void* stream) {
+  if (!e) return "{}";
+  cudaSetDevice(e->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  struct Acc { double ms = 0, flops = 0, bytes = 0; long n = 0; };
+  std::vector<Acc> acc(e->cls_names.size());
+  if (!e->recs.empty()) {
+    cudaEvent_t fin;
+    cudaEventCreate(&fin);
+    cudaEventRecord(fin, s);
+    cudaEventSynchronize(fin);
+    for (size_t i = 0; i < e->recs.size(); ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e->recs[i].ev, i + 1 < e->recs.size() ? e->recs[i + 1].ev : fin);
+      Acc& a = acc[e->recs[i].cls];
+      a.ms += ms; a.flops += e->recs[i].flops; a.bytes += e->recs[i].bytes; a.n++;
+    }
+    cudaEventDestroy(fin);
+  }
+  std::string js = "{";
+  bool first = true;
+  for (size_t c = 0; c < acc.size(); ++c) {
+    if (acc[c].n == 0) continue;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e, \"launches\": %ld}", first ? "" : ", ",
+             e->cls_names[c].c_str(), acc[c].ms, acc[c].flops, acc[c].bytes, acc[c].n);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  e->profile_json = js;
+  e->recs.clear();
+  e->ev_used = 0;
+  return e->profile_json.c_str();
 }
 
 int64_t vited_launch_count(vited_engine* e) { return e ? e->launches : 0; }

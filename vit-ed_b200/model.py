@@ -259,6 +259,13 @@ class VisionTransformerCustom(nn.Module):
             self._ensure_engine(next(self.parameters()).device)
         _lib.check(_lib.lib.vited_set_option(self._engine, int(option), int(value)), 'vited_set_option')
 
+    def profile_read(self):
+        """dict: per-kernel-class device time / algorithmic flops / bytes since OPT_PROFILE was set (resets)."""
+        import json
+        if self._engine is None:
+            return {}
+        return json.loads(_lib.lib.vited_profile_json(self._engine, self._stream()).decode())
+
     def launch_count(self):
         return int(_lib.lib.vited_launch_count(self._engine)) if self._engine is not None else 0
 
@@ -327,6 +334,8 @@ class VisionTransformerCustom(nn.Module):
         self._check_images(images)
         n = images.shape[0]
         row_end = n if row_end is None else row_end
+        if not (0 <= row_begin <= row_end <= n):
+            raise _lib.VitedError(f'bad row range [{row_begin}, {row_end}) for N={n}')
         eng = self._ensure_engine(images.device)
         if out is None:
             out = torch.zeros((row_end - row_begin, n, self.num_classes), dtype=torch.float32, device=images.device)
