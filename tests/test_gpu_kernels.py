@@ -64,7 +64,7 @@ def test_gemm(shape, act, impl):
                           f'first bad index {bad.nonzero()[0].tolist()}'
 
 
-@pytest.mark.parametrize('bn', ['128', '192'])
+@pytest.mark.parametrize('bn', ['128', '192', '256'])
 def test_gemm_tile_shapes_agree(bn, monkeypatch):
     """Both BLOCK_N variants of the tcgen05 kernel must give the same answer (subprocess: the knob is read once)."""
     import subprocess, sys, os
@@ -73,7 +73,7 @@ def test_gemm_tile_shapes_agree(bn, monkeypatch):
         "import torch, ctypes, math, sys; sys.path.insert(0, %r)\n"
         "from vited_b200 import _lib as L\n"
         "g = torch.Generator(device='cuda').manual_seed(1)\n"
-        "M, N, K = 1111, 1152, 384\n"
+        "M, N, K = 1111, 1536, 384\n"
         "A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
         "b = torch.randn(N, device='cuda', generator=g); C = torch.zeros(M, N, dtype=torch.bfloat16, device='cuda')\n"
         "st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, 0, None)\n"

@@ -14,116 +14,174 @@ namespace vited {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros, nothing read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int HD>
-__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a) {
-  constexpr int LD = HD + 8;        // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B strides)
+struct AttnSmem {
+  static constexpr int LD = HD + 8;            // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B)
+  static constexpr int TILE = 64 * LD;         // one 64-row tile (elements)
+  static constexpr int STAGE = 3 * TILE + 3 * HD;  // Q, K, V tiles + class-token q/k/v vectors
+  static constexpr int BYTES = (2 * STAGE + TILE) * 2;  // two stages + output staging
+};
+
+// Persistent: every CTA walks a strided list of work items (sequence, head, 64-query block); the K/V chunk (and, on
+// an item's first chunk, the Q tile and class-token vectors) of step s+1 is fetched with cp.async while step s is
+// being computed, so global-load latency overlaps the MMAs instead of serialising with them.
+template <int HD>
+__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) {
+  using SM = AttnSmem<HD>;
+  constexpr int LD = SM::LD;
   constexpr int PIECES = HD / 8;    // 16-byte pieces per head row
-  __shared__ __align__(16) bf16 Qs[64 * LD];
-  __shared__ __align__(16) bf16 Ks[64 * LD];
-  __shared__ __align__(16) bf16 Vs[64 * LD];
-  __shared__ float qcls[HD], kcls[HD], vcls[HD];
+  extern __shared__ __align__(16) uint8_t attn_smem_raw[];
+  __shared__ float qc[HD];          // class-token query vector, fp32, lives across the chunks of one item
+  bf16* smem = reinterpret_cast<bf16*>(attn_smem_raw);
+  bf16* sO = smem + 2 * SM::STAGE;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qblocks = (a.nq_patch + 63) / 64;
-  const int b = blockIdx.x / qblocks, qb = blockIdx.x % qblocks;
-  const int h = blockIdx.y;
-  const int q0 = qb * 64;
-  const int kvb = a.kv_index ? a.kv_index[b] : b;
-  const bool do_cls_q = a.q_has_cls && qb == 0;
+  const int n_chunks = (a.nk_patch + 63) / 64;
   const float sl2 = a.scale * kLog2e;
-
-  // ---- stage the Q tile and the class-token vectors ----
-  for (int idx = tid; idx < 64 * PIECES; idx += 160) {
-    const int row = idx / PIECES, pc = idx % PIECES;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (q0 + row < a.nq_patch)
-      val = *reinterpret_cast<const uint4*>(a.q + ((size_t)b * a.nq_patch + q0 + row) * a.q_ld + h * HD + pc * 8);
-    *reinterpret_cast<uint4*>(&Qs[row * LD + pc * 8]) = val;
-  }
-  if (tid < HD) {
-    if (do_cls_q) qcls[tid] = __bfloat162float(a.q[((size_t)a.n_seq * a.nq_patch + b) * a.q_ld + h * HD + tid]);
-    if (a.k_has_cls) {
-      const size_t krow = (size_t)a.n_kv_seq * a.nk_patch + kvb;
-      kcls[tid] = __bfloat162float(a.k[krow * a.k_ld + h * HD + tid]);
-      vcls[tid] = __bfloat162float(a.v[krow * a.v_ld + h * HD + tid]);
-    }
-  }
-  __syncthreads();
-
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, ri = lane & 7;
 
-  // ---- per-warp state ----
+  auto issue_loads = [&](int item, int kc, bf16* st) {
+    const int qb = item % qblocks;
+    const int hh = (item / qblocks) % a.n_heads;
+    const int bb = item / (qblocks * a.n_heads);
+    const int kvb = a.kv_index ? __ldg(a.kv_index + bb) : bb;
+    bf16* Qs = st;
+    bf16* Ks = st + SM::TILE;
+    bf16* Vs = st + 2 * SM::TILE;
+    bf16* cls = st + 3 * SM::TILE;
+    if (kc == 0) {
+      const int q0 = qb * 64;
+      for (int idx = tid; idx < 64 * PIECES; idx += 160) {
+        const int row = idx / PIECES, pc = idx % PIECES;
+        const bool ok = q0 + row < a.nq_patch;
+        const bf16* src = ok ? a.q + ((size_t)bb * a.nq_patch + q0 + row) * a.q_ld + hh * HD + pc * 8 : a.q;
+        cp_async16(&Qs[row * LD + pc * 8], src, ok);
+      }
+      if (tid < 3 * PIECES) {
+        const int which = tid / PIECES, pc = tid % PIECES;
+        bool ok;
+        const bf16* src;
+        if (which == 0) {
+          ok = a.q_has_cls && qb == 0;
+          src = a.q + ((size_t)a.n_seq * a.nq_patch + bb) * a.q_ld + hh * HD + pc * 8;
+        } else if (which == 1) {
+          ok = a.k_has_cls;
+          src = a.k + ((size_t)a.n_kv_seq * a.nk_patch + kvb) * a.k_ld + hh * HD + pc * 8;
+        } else {
+          ok = a.k_has_cls;
+          src = a.v + ((size_t)a.n_kv_seq * a.nk_patch + kvb) * a.v_ld + hh * HD + pc * 8;
+        }
+        cp_async16(&cls[which * HD + pc * 8], ok ? src : a.q, ok);
+      }
+    }
+    const int k0 = kc * 64;
+    for (int idx = tid; idx < 64 * PIECES; idx += 160) {
+      const int row = idx / PIECES, pc = idx % PIECES;
+      const bool ok = k0 + row < a.nk_patch;
+      const size_t grow = (size_t)kvb * a.nk_patch + k0 + row;
+      cp_async16(&Ks[row * LD + pc * 8], ok ? a.k + grow * a.k_ld + hh * HD + pc * 8 : a.k, ok);
+      cp_async16(&Vs[row * LD + pc * 8], ok ? a.v + grow * a.v_ld + hh * HD + pc * 8 : a.v, ok);
+    }
+    cp_async_commit();
+  };
+
+  // ---- per-warp state (lives across the chunks of one item) ----
   uint32_t qf[HD / 16][4];
   float o_acc[HD / 8][4];
   float m_row[2], l_row[2];
-  // class-token query state (warp 4)
-  float mc = -INFINITY, lc = 0.f;
+  float mc = -INFINITY, lc = 0.f;   // class-token query (warp 4)
   float oc[HD / 32];
 
-  if (warp < 4) {
-#pragma unroll
-    for (int ks = 0; ks < HD / 16; ++ks) {
-      const int row = warp * 16 + (mi & 1) * 8 + ri;
-      const int col = ks * 16 + (mi >> 1) * 8;
-      ldsm_x4(smem_u32(&Qs[row * LD + col]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-    }
-    if (a.k_has_cls) {
-      // seed the online softmax with the class-token key
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < HD / 4; ++i) {
-        const int d = t * (HD / 4) + i;
-        const float kc = kcls[d];
-        s0 += __bfloat162float(Qs[(warp * 16 + g) * LD + d]) * kc;
-        s1 += __bfloat162float(Qs[(warp * 16 + g + 8) * LD + d]) * kc;
-      }
-      s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-      s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-      m_row[0] = s0 * sl2; m_row[1] = s1 * sl2;
-      l_row[0] = l_row[1] = (t == 0) ? 1.f : 0.f;   // thread-partial row sums; the quad is reduced at the end
-#pragma unroll
-      for (int nt = 0; nt < HD / 8; ++nt) {
-        o_acc[nt][0] = o_acc[nt][2] = vcls[nt * 8 + 2 * t];
-        o_acc[nt][1] = o_acc[nt][3] = vcls[nt * 8 + 2 * t + 1];
-      }
+  int item = blockIdx.x, kc = 0;
+  int stage = 0;
+  if (item < n_items) issue_loads(item, 0, smem);
+  while (item < n_items) {
+    // next step in this CTA's sequence
+    int n_item = item, n_kc = kc + 1;
+    if (n_kc == n_chunks) { n_kc = 0; n_item = item + gridDim.x; }
+    bf16* st = smem + stage * SM::STAGE;
+    if (n_item < n_items) {
+      issue_loads(n_item, n_kc, smem + (stage ^ 1) * SM::STAGE);
+      cp_async_wait<1>();
     } else {
-      m_row[0] = m_row[1] = -INFINITY;
-      l_row[0] = l_row[1] = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < HD / 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < HD / 32; ++i) oc[i] = 0.f;
-    if (do_cls_q && a.k_has_cls) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < HD / 32; ++i) s += qcls[lane + 32 * i] * kcls[lane + 32 * i];
-      s = warp_sum(s);
-      mc = s * sl2;
-      lc = 1.f;
-#pragma unroll
-      for (int i = 0; i < HD / 32; ++i) oc[i] = vcls[lane + 32 * i];
-    }
-  }
-
-  const int n_chunks = (a.nk_patch + 63) / 64;
-  for (int kc = 0; kc < n_chunks; ++kc) {
-    const int k0 = kc * 64;
-    if (kc > 0) __syncthreads();  // everyone is done with the previous chunk
-    for (int idx = tid; idx < 64 * PIECES; idx += 160) {
-      const int row = idx / PIECES, pc = idx % PIECES;
-      uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-      if (k0 + row < a.nk_patch) {
-        const size_t grow = (size_t)kvb * a.nk_patch + k0 + row;
-        kv = *reinterpret_cast<const uint4*>(a.k + grow * a.k_ld + h * HD + pc * 8);
-        vv = *reinterpret_cast<const uint4*>(a.v + grow * a.v_ld + h * HD + pc * 8);
-      }
-      *reinterpret_cast<uint4*>(&Ks[row * LD + pc * 8]) = kv;
-      *reinterpret_cast<uint4*>(&Vs[row * LD + pc * 8]) = vv;
+      cp_async_wait<0>();
     }
     __syncthreads();
+
+    const int qb = item % qblocks;
+    const int h = (item / qblocks) % a.n_heads;
+    const int b = item / (qblocks * a.n_heads);
+    const int q0 = qb * 64, k0 = kc * 64;
+    const bool do_cls_q = a.q_has_cls && qb == 0;
+    bf16* Qs = st;
+    bf16* Ks = st + SM::TILE;
+    bf16* Vs = st + 2 * SM::TILE;
+    bf16* cls = st + 3 * SM::TILE;
+
+    if (kc == 0) {
+      if (warp < 4) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const int row = warp * 16 + (mi & 1) * 8 + ri;
+          const int col = ks * 16 + (mi >> 1) * 8;
+          ldsm_x4(smem_u32(&Qs[row * LD + col]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        }
+        if (a.k_has_cls) {
+          // seed the online softmax with the class-token key
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < HD / 4; ++i) {
+            const int d = t * (HD / 4) + i;
+            const float kcv = __bfloat162float(cls[HD + d]);
+            s0 += __bfloat162float(Qs[(warp * 16 + g) * LD + d]) * kcv;
+            s1 += __bfloat162float(Qs[(warp * 16 + g + 8) * LD + d]) * kcv;
+          }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+          m_row[0] = s0 * sl2; m_row[1] = s1 * sl2;
+          l_row[0] = l_row[1] = (t == 0) ? 1.f : 0.f;   // thread-partial row sums; the quad is reduced at the end
+#pragma unroll
+          for (int nt = 0; nt < HD / 8; ++nt) {
+            o_acc[nt][0] = o_acc[nt][2] = __bfloat162float(cls[2 * HD + nt * 8 + 2 * t]);
+            o_acc[nt][1] = o_acc[nt][3] = __bfloat162float(cls[2 * HD + nt * 8 + 2 * t + 1]);
+          }
+        } else {
+          m_row[0] = m_row[1] = -INFINITY;
+          l_row[0] = l_row[1] = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < HD / 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
+        }
+      } else if (do_cls_q) {
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) qc[lane + 32 * i] = __bfloat162float(cls[lane + 32 * i]);
+        __syncwarp();
+        mc = -INFINITY; lc = 0.f;
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) oc[i] = 0.f;
+        if (a.k_has_cls) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < HD / 32; ++i)
+            s += __bfloat162float(cls[lane + 32 * i]) * __bfloat162float(cls[HD + lane + 32 * i]);
+          s = warp_sum(s);
+          mc = s * sl2;
+          lc = 1.f;
+#pragma unroll
+          for (int i = 0; i < HD / 32; ++i) oc[i] = __bfloat162float(cls[2 * HD + lane + 32 * i]);
+        }
+      }
+    }
 
     if (warp < 4) {
       // ---- S = Q K^T : 16 queries x 64 keys per warp ----
@@ -204,9 +262,8 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a) {
         for (int pc = 0; pc < PIECES; ++pc) {
           const uint4 kk = *reinterpret_cast<const uint4*>(&Ks[key * LD + pc * 8]);
           const float2 k01 = unpack_bf16(kk.x), k23 = unpack_bf16(kk.y), k45 = unpack_bf16(kk.z), k67 = unpack_bf16(kk.w);
-          acc += qcls[pc * 8 + 0] * k01.x + qcls[pc * 8 + 1] * k01.y + qcls[pc * 8 + 2] * k23.x +
-                 qcls[pc * 8 + 3] * k23.y + qcls[pc * 8 + 4] * k45.x + qcls[pc * 8 + 5] * k45.y +
-                 qcls[pc * 8 + 6] * k67.x + qcls[pc * 8 + 7] * k67.y;
+          acc += qc[pc * 8 + 0] * k01.x + qc[pc * 8 + 1] * k01.y + qc[pc * 8 + 2] * k23.x + qc[pc * 8 + 3] * k23.y +
+                 qc[pc * 8 + 4] * k45.x + qc[pc * 8 + 5] * k45.y + qc[pc * 8 + 6] * k67.x + qc[pc * 8 + 7] * k67.y;
         }
         sc[j] = (k0 + key < a.nk_patch) ? acc * sl2 : -INFINITY;
       }
@@ -224,36 +281,42 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a) {
         for (int i = 0; i < HD / 32; ++i) oc[i] += pk * __bfloat162float(Vs[key * LD + lane + 32 * i]);
       }
     }
-  }
 
-  // ---- finalize ----
-  if (warp < 4) {
-    float l0 = l_row[0], l1 = l_row[1];
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.f / l0, i1 = 1.f / l1;
-    // each warp only overwrites the Q rows it alone consumed
+    // ---- finalize the item after its last chunk ----
+    if (kc == n_chunks - 1) {
+      if (warp < 4) {
+        float l0 = l_row[0], l1 = l_row[1];
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.f / l0, i1 = 1.f / l1;
 #pragma unroll
-    for (int nt = 0; nt < HD / 8; ++nt) {
-      *reinterpret_cast<uint32_t*>(&Qs[(warp * 16 + g) * LD + nt * 8 + 2 * t]) =
-          pack_bf16(o_acc[nt][0] * i0, o_acc[nt][1] * i0);
-      *reinterpret_cast<uint32_t*>(&Qs[(warp * 16 + g + 8) * LD + nt * 8 + 2 * t]) =
-          pack_bf16(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
-    }
-  } else if (do_cls_q) {
-    const float inv = 1.f / lc;
-    const size_t orow = (size_t)a.n_seq * a.nq_patch + b;
+        for (int nt = 0; nt < HD / 8; ++nt) {
+          *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g) * LD + nt * 8 + 2 * t]) =
+              pack_bf16(o_acc[nt][0] * i0, o_acc[nt][1] * i0);
+          *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g + 8) * LD + nt * 8 + 2 * t]) =
+              pack_bf16(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
+        }
+        __syncwarp();
+        // each warp stores the 16 rows it produced (coalesced 16-byte pieces)
+        for (int idx = lane; idx < 16 * PIECES; idx += 32) {
+          const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
+          if (q0 + row < a.nq_patch) {
+            *reinterpret_cast<uint4*>(a.o + ((size_t)b * a.nq_patch + q0 + row) * a.o_ld + h * HD + pc * 8) =
+                *reinterpret_cast<const uint4*>(&sO[row * LD + pc * 8]);
+          }
+        }
+      } else if (do_cls_q) {
+        const float inv = 1.f / lc;
+        const size_t orow = (size_t)a.n_seq * a.nq_patch + b;
 #pragma unroll
-    for (int i = 0; i < HD / 32; ++i)
-      a.o[orow * a.o_ld + h * HD + lane + 32 * i] = __float2bfloat16_rn(oc[i] * inv);
-  }
-  __syncthreads();
-  for (int idx = tid; idx < 64 * PIECES; idx += 160) {
-    const int row = idx / PIECES, pc = idx % PIECES;
-    if (q0 + row < a.nq_patch) {
-      *reinterpret_cast<uint4*>(a.o + ((size_t)b * a.nq_patch + q0 + row) * a.o_ld + h * HD + pc * 8) =
-          *reinterpret_cast<const uint4*>(&Qs[row * LD + pc * 8]);
+        for (int i = 0; i < HD / 32; ++i)
+          a.o[orow * a.o_ld + h * HD + lane + 32 * i] = __float2bfloat16_rn(oc[i] * inv);
+      }
     }
+    __syncthreads();  // everyone is done with this stage before the next iteration refills it
+    item = n_item;
+    kc = n_kc;
+    stage ^= 1;
   }
 }
 
@@ -336,9 +399,32 @@ int attention(const AttnArgs& a, int impl, cudaStream_t stream) {
     if (a.head_dim == 32) attn_simt_kernel<32><<<grid, 128, 0, stream>>>(a);
     else attn_simt_kernel<64><<<grid, 128, 0, stream>>>(a);
   } else {
-    dim3 grid((unsigned)((size_t)a.n_seq * ((a.nq_patch + 63) / 64)), a.n_heads);
-    if (a.head_dim == 32) attn_mma_kernel<32><<<grid, 160, 0, stream>>>(a);
-    else attn_mma_kernel<64><<<grid, 160, 0, stream>>>(a);
+    const size_t items = (size_t)a.n_seq * a.n_heads * ((a.nq_patch + 63) / 64);
+    VITED_CHECK(items < (size_t)1 << 31, "attention: too many work items");
+    static int sms = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      int dev = 0;
+      VITED_CUDA_OK(cudaGetDevice(&dev));
+      VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnSmem<32>::BYTES));
+      VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnSmem<64>::BYTES));
+      attr_set = true;
+    }
+    static int per_sm32 = 0, per_sm64 = 0;        // resident CTAs per SM (registers / shared memory)
+    if (per_sm32 == 0) {
+      VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, attn_mma_kernel<32>, 160, AttnSmem<32>::BYTES));
+      VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm64, attn_mma_kernel<64>, 160, AttnSmem<64>::BYTES));
+      if (per_sm32 < 1) per_sm32 = 1;
+      if (per_sm64 < 1) per_sm64 = 1;
+    }
+    const int per_sm = a.head_dim == 32 ? per_sm32 : per_sm64;
+    size_t grid = (size_t)sms * per_sm;
+    if (grid > items) grid = items;
+    if (a.head_dim == 32) attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(a, (int)items);
+    else attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(a, (int)items);
   }
   VITED_CUDA_OK(cudaGetLastError());
   return 0;

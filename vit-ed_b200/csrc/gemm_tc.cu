@@ -5,9 +5,11 @@
 // :151-156 q/kv/proj, timm Mlp fc1/fc2, timm PatchEmbed conv-as-GEMM):  C = act(A * W^T + bias).
 //   A [M,K] bf16 row-major (activations), W [N,K] bf16 row-major (PyTorch Linear layout) -> both operands K-major.
 //
-// Warp roles (384 threads, 1 CTA / SM):
+// Warp roles (128 + 32*4*BN/64 threads, 1 CTA / SM):
 //   warp 0 lane 0 : TMA producer            warp 1 lane 0 : tcgen05.mma issuer
-//   warp 2        : TMEM allocator          warps 4..11   : epilogue (warp%4 = TMEM lane quarter, 2 column halves)
+//   warp 2        : TMEM allocator          warps 4..     : epilogue; warp (q, sl) owns TMEM lane quarter q = warp%4
+//                                             and the 64-column slab sl, stages its 32x64 bf16 sub-tile in a private
+//                                             4 KB swizzled buffer and TMA-stores it itself (no CTA-wide barrier).
 #include "kernels.h"
 #include <cudaTypedefs.h>
 #include <mutex>
@@ -59,26 +61,43 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t r
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kGemmThreads = 384;
-constexpr int kEpiWarps = 8;
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 128) ? 6 : 4;
+  static constexpr int kEpiWarps = 4 * (BN / 64);
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t C_BYTES = BM * BN * 2;
+  static constexpr uint32_t C_BYTES = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp
+  static constexpr int kStages = (232448 - 1024 - 256 - (int)C_BYTES) / (int)STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
   static constexpr uint32_t SMEM_BYTES = 1024 + kStages * STAGE_BYTES + C_BYTES + 256;
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 up to 256");
+  static_assert(kStages >= 3, "not enough shared memory for the pipeline");
 };
 
+// exact-erf GELU evaluated with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, far below the bf16 rounding of the
+// result): gelu(v) = max(v, 0) - 0.5*|v|*poly(t)*exp(-v^2/2), t = 1/(1 + p*|v|/sqrt(2)). Two MUFU ops + ~10 FMAs.
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float a = fabsf(v);
+  const float t = __frcp_rn(fmaf(a, 0.3275911f * 0.70710678118654752440f, 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  p *= t;
+  const float ex = exp2f(a * a * -0.72134752044448170368f);  // exp(-a^2 / 2)
+  return fmaf(-0.5f * a * p, ex, fmaxf(v, 0.0f));
+}
+
 template <int BN, int ACT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiWarps = Cfg::kEpiWarps;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sC = smem + kStages * Cfg::STAGE_BYTES;
@@ -168,27 +187,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue =====================
     const int ew = warp - 4;
     const int q = warp & 3;   // TMEM lane quarter this warp may read
-    const int hf = ew >> 2;   // column half
-    const int r = q * 32 + lane;
-    constexpr int NCHUNK = BN / 64;  // 32-column chunks per warp
+    const int sl = ew >> 2;   // 64-column slab of the tile
+    uint8_t* my_stage = sC + ew * 4096;          // 32 rows x 128 B, 128B-swizzled (what the TMA store box expects)
+    uint8_t* rowp = my_stage + lane * 128;
     uint32_t as = 0, aphase = 0;
+    bool store_pending = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_blks, n_blk = tile % n_blks;
-      const int n_base = n_blk * BN;
+      const int n0 = n_blk * BN + sl * 64;
       mbar_wait(&tfull[as], aphase, 30);
       tc_fence_after();
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + as * BN + sl * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      tmem_ld_32x32b_x32(taddr, v0);
+      tmem_ld_32x32b_x32(taddr + 32, v1);
+      tmem_ld_wait();
+      // accumulator values are in registers: hand the TMEM stage back to the MMA warp right away
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      // the previous tile's TMA store must have finished reading this warp's staging buffer
+      if (store_pending) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
 #pragma unroll
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        const int col = hf * (BN / 2) + ch * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + as * BN + col + (static_cast<uint32_t>(q * 32) << 16), v);
-        tmem_ld_wait();
-        const int n0 = n_base + col;
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t* v = ch == 0 ? v0 : v1;
+        const int nc = n0 + ch * 32;
         float f[32];
-        if (n0 + 32 <= N) {
+        if (nc + 32 <= N) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nc) + i);
             f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
             f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
             f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
@@ -197,17 +228,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float b = (n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+            const float b = (nc + i < N) ? __ldg(bias + nc + i) : 0.f;
             f[i] = __uint_as_float(v[i]) + b;
           }
         }
         if (ACT == ACT_GELU) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
+          for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
         }
-        // staging layout == what a 128B-swizzled TMA store box {64 cols, 128 rows} expects
-        uint8_t* rowp = sC + (col >> 6) * (BM * 128) + r * 128;
-        const int cc0 = (col & 63) >> 3;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 pk;
@@ -215,27 +243,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           pk.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
           pk.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
           pk.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-          *reinterpret_cast<uint4*>(rowp + (((cc0 + i) ^ (r & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(rowp + (((ch * 4 + i) ^ (lane & 7)) << 4)) = pk;
         }
       }
-      // this warp's part of the accumulator stage is drained
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      if (ew == 0 && lane == 0) {
-#pragma unroll
-        for (int sl = 0; sl < BN / 64; ++sl) {
-          if (n_base + sl * 64 < N) tma_store_2d(&tmC, sC + sl * (BM * 128), n_base + sl * 64, m_blk * BM);
-        }
+      __syncwarp();
+      if (lane == 0 && n0 < N) {
+        tma_store_2d(&tmC, my_stage, n0, m_blk * BM + q * 32);
         tma_store_commit();
-        tma_store_wait_read();
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      store_pending = true;
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (ew == 0 && lane == 0) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -258,7 +278,7 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN, ACT><<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
+  gemm_tc_kernel<BN, ACT><<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -266,7 +286,7 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
 int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act,
               cudaStream_t stream);
 
-static int g_block_n = 0;  // 0 = auto; VITED_GEMM_BN=128|192 overrides (tuning knob)
+static int g_block_n = 0;  // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic choice (tuning knob)
 
 int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream) {
@@ -284,15 +304,19 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
     g_block_n = e ? atoi(e) : -1;
   }
   int bn = 128;
-  if (g_block_n == 192 || (g_block_n < 0 && N % 192 == 0 && N % 128 != 0)) bn = 192;
-  if (g_block_n == 128) bn = 128;
+  if (g_block_n == 128 || g_block_n == 192 || g_block_n == 256) bn = g_block_n;
+  else if (N % 192 == 0) bn = 192;
   CUtensorMap tA, tB, tC;
   if (make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, BM)) return 1;
   if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)bn)) return 1;
-  if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, BM)) return 1;
+  if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
   if (bn == 128) {
     return act == ACT_GELU ? launch_tc<128, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
                            : launch_tc<128, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+  }
+  if (bn == 256) {
+    return act == ACT_GELU ? launch_tc<256, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                           : launch_tc<256, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
   }
   return act == ACT_GELU ? launch_tc<192, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
                          : launch_tc<192, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
