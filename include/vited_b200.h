@@ -60,7 +60,9 @@ enum {
   VITED_OPT_ATTN_IMPL = 1,      /* 0 = tensor-core flash kernel (default), 1 = SIMT debugging reference kernel   */
   VITED_OPT_CHUNK_ROWS = 2,     /* target token rows per decoder chunk (default 262144)                          */
   VITED_OPT_CACHE_LAYER0 = 3,   /* 1 (default) = run decoder layer 0's self-attention once per item, not per pair */
-  VITED_OPT_PROFILE = 4         /* 1 = record a CUDA event before every launch (see vited_profile_json); default 0   */
+  VITED_OPT_PROFILE = 4,        /* 1 = record a CUDA event before every launch (see vited_profile_json); default 0   */
+  VITED_OPT_PRUNE_TAIL = 5      /* 1 (default) = in the last decoder layer run everything after the K/V projection of
+                                   its self-attention on the class-token rows only (only row 0 reaches the head)   */
 };
 
 /* Library-wide last error message (thread-local). */

@@ -120,6 +120,11 @@ def test_grid_properties_puzzle_model():
     model.set_option(vited_b200.OPT_CACHE_LAYER0, 0)
     nocache = grid.score_puzzle(model, images)
     np.testing.assert_allclose(nocache.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=5e-3)
+    # (5) without last-layer pruning (all 65 rows carried to the end): same values up to bf16 noise
+    model.set_option(vited_b200.OPT_CACHE_LAYER0, 1)
+    model.set_option(vited_b200.OPT_PRUNE_TAIL, 0)
+    noprune = grid.score_puzzle(model, images)
+    np.testing.assert_allclose(noprune.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=5e-3)
 
 
 def test_argmax_agreement_puzzle_model():

@@ -38,6 +38,7 @@ OPT_ATTN_IMPL = 1
 OPT_CHUNK_ROWS = 2
 OPT_CACHE_LAYER0 = 3
 OPT_PROFILE = 4
+OPT_PRUNE_TAIL = 5
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -25,24 +25,28 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 template <int HD>
 struct AttnSmem {
-  static constexpr int LD = HD + 8;            // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B)
-  static constexpr int TILE = 64 * LD;         // one 64-row tile (elements)
-  static constexpr int STAGE = 3 * TILE + 3 * HD;  // Q, K, V tiles + class-token q/k/v vectors
-  static constexpr int BYTES = (2 * STAGE + TILE) * 2;  // two stages + output staging
+  static constexpr int LD = HD + 8;              // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B)
+  static constexpr int QROWS = 80;               // 64 patch queries + the class-token query in row 64 (+15 zero rows)
+  static constexpr int QT = QROWS * LD;          // elements
+  static constexpr int KT = 64 * LD;
+  static constexpr int STAGE = QT + 2 * KT + 2 * HD;   // Q tile, K chunk, V chunk, class-token k / v vectors
+  static constexpr int NST = HD == 32 ? 4 : 3;   // cp.async ring depth
+  static constexpr int BYTES = (NST * STAGE + QT) * 2;  // ring + output staging
 };
 
-// Persistent: every CTA walks a strided list of work items (sequence, head, 64-query block); the K/V chunk (and, on
-// an item's first chunk, the Q tile and class-token vectors) of step s+1 is fetched with cp.async while step s is
-// being computed, so global-load latency overlaps the MMAs instead of serialising with them.
+// Persistent, software-pipelined: every CTA walks a strided list of work items (sequence, head, 64-query block) and
+// their 64-key chunks; the loads of step s+NST-1 are in flight (cp.async ring) while step s is computed.
+// Five identical MMA warps: warps 0-3 own 16 patch queries each, warp 4 owns a 16-row tile whose row 0 is the
+// class-token query (rows 1-15 are zeros) so the class token rides the same tensor-core path.
 template <int HD>
 __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) {
   using SM = AttnSmem<HD>;
   constexpr int LD = SM::LD;
+  constexpr int NST = SM::NST;
   constexpr int PIECES = HD / 8;    // 16-byte pieces per head row
   extern __shared__ __align__(16) uint8_t attn_smem_raw[];
-  __shared__ float qc[HD];          // class-token query vector, fp32, lives across the chunks of one item
   bf16* smem = reinterpret_cast<bf16*>(attn_smem_raw);
-  bf16* sO = smem + 2 * SM::STAGE;
+  bf16* sO = smem + NST * SM::STAGE;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qblocks = (a.nq_patch + 63) / 64;
@@ -51,15 +55,19 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, ri = lane & 7;
 
+  // rows 65..79 of every stage's Q tile are never loaded: zero them once
+  for (int st = 0; st < NST; ++st)
+    for (int idx = tid; idx < 15 * LD; idx += 160) smem[st * SM::STAGE + 65 * LD + idx] = __float2bfloat16(0.f);
+
   auto issue_loads = [&](int item, int kc, bf16* st) {
     const int qb = item % qblocks;
     const int hh = (item / qblocks) % a.n_heads;
     const int bb = item / (qblocks * a.n_heads);
     const int kvb = a.kv_index ? __ldg(a.kv_index + bb) : bb;
     bf16* Qs = st;
-    bf16* Ks = st + SM::TILE;
-    bf16* Vs = st + 2 * SM::TILE;
-    bf16* cls = st + 3 * SM::TILE;
+    bf16* Ks = st + SM::QT;
+    bf16* Vs = Ks + SM::KT;
+    bf16* cls = Vs + SM::KT;
     if (kc == 0) {
       const int q0 = qb * 64;
       for (int idx = tid; idx < 64 * PIECES; idx += 160) {
@@ -70,19 +78,16 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
       }
       if (tid < 3 * PIECES) {
         const int which = tid / PIECES, pc = tid % PIECES;
-        bool ok;
-        const bf16* src;
-        if (which == 0) {
-          ok = a.q_has_cls && qb == 0;
-          src = a.q + ((size_t)a.n_seq * a.nq_patch + bb) * a.q_ld + hh * HD + pc * 8;
-        } else if (which == 1) {
-          ok = a.k_has_cls;
-          src = a.k + ((size_t)a.n_kv_seq * a.nk_patch + kvb) * a.k_ld + hh * HD + pc * 8;
-        } else {
-          ok = a.k_has_cls;
-          src = a.v + ((size_t)a.n_kv_seq * a.nk_patch + kvb) * a.v_ld + hh * HD + pc * 8;
+        if (which == 0) {   // class-token query -> row 64 of the Q tile
+          const bool ok = a.q_has_cls && qb == 0;
+          const bf16* src = a.q + ((size_t)a.n_seq * a.nq_patch + bb) * a.q_ld + hh * HD + pc * 8;
+          cp_async16(&Qs[64 * LD + pc * 8], ok ? src : a.q, ok);
+        } else {            // class-token key / value vectors
+          const bool ok = a.k_has_cls;
+          const size_t krow = (size_t)a.n_kv_seq * a.nk_patch + kvb;
+          const bf16* src = which == 1 ? a.k + krow * a.k_ld + hh * HD + pc * 8 : a.v + krow * a.v_ld + hh * HD + pc * 8;
+          cp_async16(&cls[(which - 1) * HD + pc * 8], ok ? src : a.q, ok);
         }
-        cp_async16(&cls[which * HD + pc * 8], ok ? src : a.q, ok);
       }
     }
     const int k0 = kc * 64;
@@ -93,44 +98,46 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
       cp_async16(&Ks[row * LD + pc * 8], ok ? a.k + grow * a.k_ld + hh * HD + pc * 8 : a.k, ok);
       cp_async16(&Vs[row * LD + pc * 8], ok ? a.v + grow * a.v_ld + hh * HD + pc * 8 : a.v, ok);
     }
-    cp_async_commit();
   };
 
   // ---- per-warp state (lives across the chunks of one item) ----
   uint32_t qf[HD / 16][4];
   float o_acc[HD / 8][4];
   float m_row[2], l_row[2];
-  float mc = -INFINITY, lc = 0.f;   // class-token query (warp 4)
-  float oc[HD / 32];
 
-  int item = blockIdx.x, kc = 0;
-  int stage = 0;
-  if (item < n_items) issue_loads(item, 0, smem);
-  while (item < n_items) {
-    // next step in this CTA's sequence
-    int n_item = item, n_kc = kc + 1;
-    if (n_kc == n_chunks) { n_kc = 0; n_item = item + gridDim.x; }
-    bf16* st = smem + stage * SM::STAGE;
-    if (n_item < n_items) {
-      issue_loads(n_item, n_kc, smem + (stage ^ 1) * SM::STAGE);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+  // fetch cursor runs NST-1 steps ahead of the compute cursor; exactly one commit group per step (possibly empty)
+  int f_item = blockIdx.x, f_kc = 0, f_stage = 0;
+  auto fetch_next = [&]() {
+    if (f_item < n_items) {
+      issue_loads(f_item, f_kc, smem + f_stage * SM::STAGE);
+      if (++f_kc == n_chunks) { f_kc = 0; f_item += gridDim.x; }
     }
+    cp_async_commit();
+    if (++f_stage == NST) f_stage = 0;
+  };
+  __syncthreads();  // zero rows visible before any ldmatrix
+#pragma unroll
+  for (int i = 0; i < NST - 1; ++i) fetch_next();
+
+  int item = blockIdx.x, kc = 0, stage = 0;
+  while (item < n_items) {
+    fetch_next();
+    cp_async_wait<NST - 1>();
     __syncthreads();
 
+    bf16* st = smem + stage * SM::STAGE;
     const int qb = item % qblocks;
     const int h = (item / qblocks) % a.n_heads;
     const int b = item / (qblocks * a.n_heads);
     const int q0 = qb * 64, k0 = kc * 64;
-    const bool do_cls_q = a.q_has_cls && qb == 0;
+    const bool active = warp < 4 || (a.q_has_cls && qb == 0);   // warp 4 only carries the class-token query
     bf16* Qs = st;
-    bf16* Ks = st + SM::TILE;
-    bf16* Vs = st + 2 * SM::TILE;
-    bf16* cls = st + 3 * SM::TILE;
+    bf16* Ks = st + SM::QT;
+    bf16* Vs = Ks + SM::KT;
+    bf16* cls = Vs + SM::KT;
 
-    if (kc == 0) {
-      if (warp < 4) {
+    if (active) {
+      if (kc == 0) {
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           const int row = warp * 16 + (mi & 1) * 8 + ri;
@@ -138,12 +145,12 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
           ldsm_x4(smem_u32(&Qs[row * LD + col]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
         }
         if (a.k_has_cls) {
-          // seed the online softmax with the class-token key
+          // seed the online softmax with the class-token key: m = q.k_cls, l = 1, O = v_cls
           float s0 = 0.f, s1 = 0.f;
 #pragma unroll
           for (int i = 0; i < HD / 4; ++i) {
             const int d = t * (HD / 4) + i;
-            const float kcv = __bfloat162float(cls[HD + d]);
+            const float kcv = __bfloat162float(cls[d]);
             s0 += __bfloat162float(Qs[(warp * 16 + g) * LD + d]) * kcv;
             s1 += __bfloat162float(Qs[(warp * 16 + g + 8) * LD + d]) * kcv;
           }
@@ -153,8 +160,8 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
           l_row[0] = l_row[1] = (t == 0) ? 1.f : 0.f;   // thread-partial row sums; the quad is reduced at the end
 #pragma unroll
           for (int nt = 0; nt < HD / 8; ++nt) {
-            o_acc[nt][0] = o_acc[nt][2] = __bfloat162float(cls[2 * HD + nt * 8 + 2 * t]);
-            o_acc[nt][1] = o_acc[nt][3] = __bfloat162float(cls[2 * HD + nt * 8 + 2 * t + 1]);
+            o_acc[nt][0] = o_acc[nt][2] = __bfloat162float(cls[HD + nt * 8 + 2 * t]);
+            o_acc[nt][1] = o_acc[nt][3] = __bfloat162float(cls[HD + nt * 8 + 2 * t + 1]);
           }
         } else {
           m_row[0] = m_row[1] = -INFINITY;
@@ -162,28 +169,8 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
 #pragma unroll
           for (int nt = 0; nt < HD / 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
         }
-      } else if (do_cls_q) {
-#pragma unroll
-        for (int i = 0; i < HD / 32; ++i) qc[lane + 32 * i] = __bfloat162float(cls[lane + 32 * i]);
-        __syncwarp();
-        mc = -INFINITY; lc = 0.f;
-#pragma unroll
-        for (int i = 0; i < HD / 32; ++i) oc[i] = 0.f;
-        if (a.k_has_cls) {
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < HD / 32; ++i)
-            s += __bfloat162float(cls[lane + 32 * i]) * __bfloat162float(cls[HD + lane + 32 * i]);
-          s = warp_sum(s);
-          mc = s * sl2;
-          lc = 1.f;
-#pragma unroll
-          for (int i = 0; i < HD / 32; ++i) oc[i] = __bfloat162float(cls[2 * HD + lane + 32 * i]);
-        }
       }
-    }
 
-    if (warp < 4) {
       // ---- S = Q K^T : 16 queries x 64 keys per warp ----
       float s[8][4];
 #pragma unroll
@@ -251,44 +238,15 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
           mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
         }
       }
-    } else if (do_cls_q) {
-      // ---- class-token query: lane owns keys (lane, lane+32) for the scores, head dims for the output ----
-      float sc[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int key = lane + 32 * j;
-        float acc = 0.f;
-#pragma unroll
-        for (int pc = 0; pc < PIECES; ++pc) {
-          const uint4 kk = *reinterpret_cast<const uint4*>(&Ks[key * LD + pc * 8]);
-          const float2 k01 = unpack_bf16(kk.x), k23 = unpack_bf16(kk.y), k45 = unpack_bf16(kk.z), k67 = unpack_bf16(kk.w);
-          acc += qc[pc * 8 + 0] * k01.x + qc[pc * 8 + 1] * k01.y + qc[pc * 8 + 2] * k23.x + qc[pc * 8 + 3] * k23.y +
-                 qc[pc * 8 + 4] * k45.x + qc[pc * 8 + 5] * k45.y + qc[pc * 8 + 6] * k67.x + qc[pc * 8 + 7] * k67.y;
-        }
-        sc[j] = (k0 + key < a.nk_patch) ? acc * sl2 : -INFINITY;
-      }
-      const float mx = warp_max(fmaxf(sc[0], sc[1]));
-      const float mn = fmaxf(mc, mx);
-      const float corr = exp2f(mc - mn);
-      const float p0 = exp2f(sc[0] - mn), p1 = exp2f(sc[1] - mn);
-      lc = lc * corr + warp_sum(p0 + p1);
-      mc = mn;
-#pragma unroll
-      for (int i = 0; i < HD / 32; ++i) oc[i] *= corr;
-      for (int key = 0; key < 64; ++key) {
-        const float pk = __shfl_sync(0xffffffffu, key < 32 ? p0 : p1, key & 31);
-#pragma unroll
-        for (int i = 0; i < HD / 32; ++i) oc[i] += pk * __bfloat162float(Vs[key * LD + lane + 32 * i]);
-      }
-    }
 
-    // ---- finalize the item after its last chunk ----
-    if (kc == n_chunks - 1) {
-      if (warp < 4) {
+      // ---- finalize the item after its last chunk ----
+      if (kc == n_chunks - 1) {
         float l0 = l_row[0], l1 = l_row[1];
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.f / l0, i1 = 1.f / l1;
+        // each warp stages and stores its own 16 rows; the previous item's rows were stored before the two
+        // __syncthreads of the steps in between, and only this warp touches these sO rows
 #pragma unroll
         for (int nt = 0; nt < HD / 8; ++nt) {
           *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g) * LD + nt * 8 + 2 * t]) =
@@ -297,27 +255,27 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
               pack_bf16(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
         }
         __syncwarp();
-        // each warp stores the 16 rows it produced (coalesced 16-byte pieces)
-        for (int idx = lane; idx < 16 * PIECES; idx += 32) {
-          const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
-          if (q0 + row < a.nq_patch) {
-            *reinterpret_cast<uint4*>(a.o + ((size_t)b * a.nq_patch + q0 + row) * a.o_ld + h * HD + pc * 8) =
-                *reinterpret_cast<const uint4*>(&sO[row * LD + pc * 8]);
+        if (warp < 4) {
+          for (int idx = lane; idx < 16 * PIECES; idx += 32) {
+            const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
+            if (q0 + row < a.nq_patch) {
+              *reinterpret_cast<uint4*>(a.o + ((size_t)b * a.nq_patch + q0 + row) * a.o_ld + h * HD + pc * 8) =
+                  *reinterpret_cast<const uint4*>(&sO[row * LD + pc * 8]);
+            }
           }
+        } else if (lane < PIECES) {
+          const size_t orow = (size_t)a.n_seq * a.nq_patch + b;   // class-token output row
+          *reinterpret_cast<uint4*>(a.o + orow * a.o_ld + h * HD + lane * 8) =
+              *reinterpret_cast<const uint4*>(&sO[64 * LD + lane * 8]);
         }
-      } else if (do_cls_q) {
-        const float inv = 1.f / lc;
-        const size_t orow = (size_t)a.n_seq * a.nq_patch + b;
-#pragma unroll
-        for (int i = 0; i < HD / 32; ++i)
-          a.o[orow * a.o_ld + h * HD + lane + 32 * i] = __float2bfloat16_rn(oc[i] * inv);
+        __syncwarp();
       }
     }
-    __syncthreads();  // everyone is done with this stage before the next iteration refills it
-    item = n_item;
-    kc = n_kc;
-    stage ^= 1;
+    __syncthreads();  // everyone is done with this stage before a later fetch refills it
+    if (++kc == n_chunks) { kc = 0; item += gridDim.x; }
+    if (++stage == NST) stage = 0;
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -385,6 +343,88 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(AttnArgs a) {
 #pragma unroll
     for (int d = 0; d < HD; ++d) a.o[row * a.o_ld + h * HD + d] = __float2bfloat16_rn(o[d] * inv);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// class-token-only attention: one warp per (sequence, head). Used by the LAST decoder layer, where only row 0 of every
+// sequence reaches the head (vision_transformer.py:400 + timm forward_head), so the patch queries are dead work.
+// q: [n_seq, q_ld] (one query row per sequence); keys/values in the split layout.
+// ------------------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(256) attn_cls_kernel(AttnArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int nk = a.nk_patch + a.k_has_cls;
+  const float sl2 = a.scale * kLog2e;
+  const size_t warps_total = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t items = (size_t)a.n_seq * a.n_heads;
+  for (size_t item = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < items; item += warps_total) {
+    const int h = (int)(item % a.n_heads);
+    const int b = (int)(item / a.n_heads);
+    const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;
+    float q[HD];
+    {
+      const uint4* qp = reinterpret_cast<const uint4*>(a.q + (size_t)b * a.q_ld + h * HD);
+#pragma unroll
+      for (int pc = 0; pc < HD / 8; ++pc) {
+        const uint4 v = __ldg(qp + pc);
+        const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
+        q[pc * 8 + 0] = f0.x; q[pc * 8 + 1] = f0.y; q[pc * 8 + 2] = f1.x; q[pc * 8 + 3] = f1.y;
+        q[pc * 8 + 4] = f2.x; q[pc * 8 + 5] = f2.y; q[pc * 8 + 6] = f3.x; q[pc * 8 + 7] = f3.y;
+      }
+    }
+    float m = -INFINITY, l = 0.f;
+    float acc[HD / 32];
+#pragma unroll
+    for (int i = 0; i < HD / 32; ++i) acc[i] = 0.f;
+    for (int j0 = 0; j0 < nk; j0 += 32) {
+      const int j = j0 + lane;
+      float s = -INFINITY;
+      if (j < nk) {
+        const size_t row = tok_row(a.n_kv_seq, a.nk_patch, a.k_has_cls, kvb, j);
+        const uint4* kp = reinterpret_cast<const uint4*>(a.k + row * a.k_ld + h * HD);
+        float d = 0.f;
+#pragma unroll
+        for (int pc = 0; pc < HD / 8; ++pc) {
+          const uint4 v = __ldg(kp + pc);
+          const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
+          d += q[pc * 8 + 0] * f0.x + q[pc * 8 + 1] * f0.y + q[pc * 8 + 2] * f1.x + q[pc * 8 + 3] * f1.y +
+               q[pc * 8 + 4] * f2.x + q[pc * 8 + 5] * f2.y + q[pc * 8 + 6] * f3.x + q[pc * 8 + 7] * f3.y;
+        }
+        s = d * sl2;
+      }
+      const float mn = fmaxf(m, warp_max(s));
+      const float corr = exp2f(m - mn);
+      const float p = exp2f(s - mn);
+      l = l * corr + warp_sum(p);
+      m = mn;
+#pragma unroll
+      for (int i = 0; i < HD / 32; ++i) acc[i] *= corr;
+      const int jn = min(32, nk - j0);
+      for (int jj = 0; jj < jn; ++jj) {
+        const float pj = __shfl_sync(0xffffffffu, p, jj);
+        const size_t row = tok_row(a.n_kv_seq, a.nk_patch, a.k_has_cls, kvb, j0 + jj);
+#pragma unroll
+        for (int i = 0; i < HD / 32; ++i) acc[i] += pj * __bfloat162float(a.v[row * a.v_ld + h * HD + lane + 32 * i]);
+      }
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int i = 0; i < HD / 32; ++i)
+      a.o[(size_t)b * a.o_ld + h * HD + lane + 32 * i] = __float2bfloat16_rn(acc[i] * inv);
+  }
+}
+
+int attention_cls(const AttnArgs& a, cudaStream_t stream) {
+  VITED_CHECK(a.head_dim == 32 || a.head_dim == 64, "attention_cls: head_dim %d not supported (32 or 64)", a.head_dim);
+  VITED_CHECK(a.q_ld % 8 == 0 && a.k_ld % 8 == 0 && a.v_ld % 8 == 0, "attention_cls: row strides must be multiples of 8");
+  if (a.n_seq == 0) return 0;
+  const size_t items = (size_t)a.n_seq * a.n_heads;
+  size_t blocks = (items + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (a.head_dim == 32) attn_cls_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(a);
+  else attn_cls_kernel<64><<<(unsigned)blocks, 256, 0, stream>>>(a);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int attention(const AttnArgs& a, int impl, cudaStream_t stream) {

@@ -92,6 +92,7 @@ struct vited_engine {
   int gemm_impl = IMPL_FAST, attn_impl = IMPL_FAST;
   int64_t chunk_rows = 262144;
   int cache_layer0 = 1;
+  int prune_tail = 1;   // last decoder layer: only the class-token row continues past self-attention
   int64_t launches = 0;
   // optional per-kernel timing (bench.py's roofline): one event before every launch, intervals summed per class
   int profile = 0;
@@ -284,6 +285,29 @@ static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o,
   return attention(a, e->attn_impl, s);
 }
 
+// class-token-only attention (last decoder layer). q_cls/o_cls: [n_seq, ld]; keys in the split layout.
+static int L_attn_cls(vited_engine* e, const bf16* q_cls, int q_ld, const bf16* k, const bf16* v, int kv_ld, bf16* o_cls,
+                      int n_seq, int k_has_cls, int n_kv_seq, const int* kv_index, cudaStream_t s) {
+  AttnArgs a;
+  a.q = q_cls; a.q_ld = q_ld; a.k = k; a.k_ld = kv_ld; a.v = v; a.v_ld = kv_ld; a.o = o_cls; a.o_ld = e->D;
+  a.n_seq = n_seq; a.n_heads = e->H; a.head_dim = e->hd;
+  a.nq_patch = 0; a.q_has_cls = 1; a.nk_patch = e->Ne; a.k_has_cls = k_has_cls;
+  a.n_kv_seq = n_kv_seq; a.kv_index = kv_index; a.scale = e->scale;
+  prof_mark(e, "attn_cls", 4.0 * n_seq * (double)(e->Ne + k_has_cls) * e->D,
+            (double)n_seq * (e->Ne + k_has_cls) * e->D * 2.0 * 2.0, s);
+  return attention_cls(a, s);
+}
+// resid_ln over a plain block of `rows` rows (no split-layout bookkeeping): used for the class-token rows alone
+static int L_resid_ln_rows(vited_engine* e, float* x, const bf16* delta, const float* gsrc_cls_rows, const int* gidx,
+                           const LNorm* ln, bf16* h, int rows, cudaStream_t s) {
+  ResidLnArgs a;
+  a.x = x; a.delta = delta; a.gather_src = gsrc_cls_rows; a.gather_idx = gidx; a.n_src_seq = 0;
+  a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
+  a.n_seq = rows; a.n_patch = 1; a.has_cls = 0; a.D = e->D; a.write_x = 1; a.eps = 1e-6f;
+  prof_mark(e, "resid_ln", 0.0, (double)rows * e->D * 12.0, s);
+  return resid_ln(a, s);
+}
+
 static int ensure_rows(vited_engine* e, size_t rows) {
   const size_t D = e->D;
   TRY(e->x.ensure(rows * D * 4));
@@ -407,32 +431,72 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
                         int n_kv_seq, HeadArgs head, cudaStream_t s) {
   const size_t rows = (size_t)P * e->Nd;
   TRY(ensure_rows(e, rows));
+  const size_t D = e->D;
+  const size_t cls_off = (size_t)P * e->Ne;      // first class-token row in every [rows, *] buffer
   float* x = e->x.as<float>();
   bf16* h = e->h.as<bf16>();
   bf16* delta = e->delta.as<bf16>();
-  const size_t kv_per_layer = (size_t)n_kv_seq * e->Ne * 2 * e->D;
-  for (size_t l = 0; l < e->dec.size(); ++l) {
+  bf16* qkv = e->qkv.as<bf16>();
+  bf16* o = e->o.as<bf16>();
+  bf16* q = e->q.as<bf16>();
+  bf16* hid = e->hid.as<bf16>();
+  const size_t kv_per_layer = (size_t)n_kv_seq * e->Ne * 2 * D;
+  const size_t L = e->dec.size();
+  for (size_t l = 0; l < L; ++l) {
     DecBlock& b = e->dec[l];
     const bool first = (l == 0);
-    if (first && e->cache_layer0) {
-      TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s));
+    // In the last layer only row 0 (the class token) of every sequence reaches the head, so after the keys/values of
+    // its self-attention are formed every kernel runs on the P class-token rows alone.
+    const bool tail = e->prune_tail && (l + 1 == L);
+    const bf16* kvl = e->kv.as<bf16>() + l * kv_per_layer;
+    if (!tail) {
+      if (first && e->cache_layer0) {
+        TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s));
+      } else {
+        if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
+        else TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
+        TRY(L_gemm(e, h, b.qkv, qkv, (int)rows, ACT_NONE, s));
+        TRY(L_attn_self(e, qkv, o, P, 1, s));
+        TRY(L_gemm(e, o, b.proj, delta, (int)rows, ACT_NONE, s));
+        TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm_cross, h, P, 1, 1, s));
+      }
+      TRY(L_gemm(e, h, b.q, q, (int)rows, ACT_NONE, s));
+      TRY(L_attn_cross(e, q, kvl, o, P, n_kv_seq, ci, s));
+      TRY(L_gemm(e, o, b.cproj, delta, (int)rows, ACT_NONE, s));
+      TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, P, 1, 1, s));
+      TRY(L_gemm(e, h, b.fc1, hid, (int)rows, ACT_GELU, s));
+      TRY(L_gemm(e, hid, b.fc2, delta, (int)rows, ACT_NONE, s));
     } else {
-      if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
-      else TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
-      TRY(L_gemm(e, h, b.qkv, e->qkv.as<bf16>(), (int)rows, ACT_NONE, s));
-      TRY(L_attn_self(e, e->qkv.as<bf16>(), e->o.as<bf16>(), P, 1, s));
-      TRY(L_gemm(e, e->o.as<bf16>(), b.proj, delta, (int)rows, ACT_NONE, s));
-      TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm_cross, h, P, 1, 1, s));
+      float* x_c = x + cls_off * D;
+      bf16* h_c = h + cls_off * D;
+      bf16* d_c = delta + cls_off * D;
+      bf16* q_c = q + cls_off * D;
+      bf16* o_c = o + cls_off * D;
+      if (first && e->cache_layer0) {
+        // single-layer decoder with the layer-0 cache: gather the class-token rows only
+        TRY(L_resid_ln_rows(e, x_c, nullptr, xsrc + (size_t)n_src * e->Ne * D, xj, &b.norm_cross, h_c, P, s));
+      } else {
+        if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
+        else TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
+        // keys/values for every token, the query for the class token only (qkv rows: [0,D) q, [D,3D) k|v)
+        Linear w_kv = b.qkv; w_kv.w = b.qkv.w + D * D; w_kv.b = b.qkv.b + D; w_kv.out = 2 * (int)D;
+        Linear w_q = b.qkv; w_q.out = (int)D;
+        TRY(L_gemm(e, h, w_kv, qkv, (int)rows, ACT_NONE, s));          // [rows, 2D]
+        TRY(L_gemm(e, h_c, w_q, q_c, P, ACT_NONE, s));                 // [P, D]
+        TRY(L_attn_cls(e, q_c, (int)D, qkv, qkv + D, 2 * (int)D, o_c, P, 1, P, nullptr, s));
+        TRY(L_gemm(e, o_c, b.proj, d_c, P, ACT_NONE, s));
+        TRY(L_resid_ln_rows(e, x_c, d_c, nullptr, nullptr, &b.norm_cross, h_c, P, s));
+      }
+      TRY(L_gemm(e, h_c, b.q, q_c, P, ACT_NONE, s));
+      TRY(L_attn_cls(e, q_c, (int)D, kvl, kvl + D, 2 * (int)D, o_c, P, 0, n_kv_seq, ci, s));
+      TRY(L_gemm(e, o_c, b.cproj, d_c, P, ACT_NONE, s));
+      TRY(L_resid_ln_rows(e, x_c, d_c, nullptr, nullptr, &b.norm2, h_c, P, s));
+      TRY(L_gemm(e, h_c, b.fc1, hid, P, ACT_GELU, s));
+      TRY(L_gemm(e, hid, b.fc2, d_c, P, ACT_NONE, s));
     }
-    TRY(L_gemm(e, h, b.q, e->q.as<bf16>(), (int)rows, ACT_NONE, s));
-    TRY(L_attn_cross(e, e->q.as<bf16>(), e->kv.as<bf16>() + l * kv_per_layer, e->o.as<bf16>(), P, n_kv_seq, ci, s));
-    TRY(L_gemm(e, e->o.as<bf16>(), b.cproj, delta, (int)rows, ACT_NONE, s));
-    TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, P, 1, 1, s));
-    TRY(L_gemm(e, h, b.fc1, e->hid.as<bf16>(), (int)rows, ACT_GELU, s));
-    TRY(L_gemm(e, e->hid.as<bf16>(), b.fc2, delta, (int)rows, ACT_NONE, s));
   }
-  head.x = x + (size_t)P * e->Ne * e->D;
-  head.delta = delta + (size_t)P * e->Ne * e->D;
+  head.x = x + cls_off * D;
+  head.delta = delta + cls_off * D;
   head.ln_w = e->norm.w; head.ln_b = e->norm.b; head.head_w = e->head_w; head.head_b = e->head_b;
   head.P = P; head.D = e->D; head.C = e->C; head.eps = 1e-6f;
   prof_mark(e, "head", 0.0, (double)P * e->D * 6.0, s);
@@ -503,6 +567,7 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
       e->chunk_rows = value;
       return 0;
     case VITED_OPT_CACHE_LAYER0: e->cache_layer0 = value ? 1 : 0; return 0;
+    case VITED_OPT_PRUNE_TAIL: e->prune_tail = value ? 1 : 0; return 0;
     case VITED_OPT_PROFILE:
       e->profile = value ? 1 : 0;
       e->recs.clear();

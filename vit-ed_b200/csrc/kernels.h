@@ -76,5 +76,7 @@ struct AttnArgs {
   float scale;
 };
 int attention(const AttnArgs& a, int impl, cudaStream_t stream);
+// class-token query only: q is [n_seq, q_ld] (one row per sequence), o likewise; nq_patch / q_has_cls are ignored.
+int attention_cls(const AttnArgs& a, cudaStream_t stream);
 
 }  // namespace vited
