@@ -37,6 +37,8 @@ GEMM_SHAPES = [
     (128, 128, 64), (256, 384, 384), (1000, 1152, 384), (4160, 384, 384), (777, 1536, 384), (640, 384, 1536),
     (65 * 37, 768, 384), (64 * 9, 384, 192), (300, 384, 768), (5, 32, 32), (130, 96, 3072), (1, 8, 8),
     (129, 1152, 384), (20000, 1152, 384),
+    # large-M, K<=384: the resident-weights variant of the tcgen05 kernel
+    (30000, 1536, 384), (26000, 384, 384), (26001, 384, 192), (19999, 768, 384),
 ]
 
 

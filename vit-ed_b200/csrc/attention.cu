@@ -26,77 +26,106 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int HD>
 struct AttnSmem {
   static constexpr int LD = HD + 8;              // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B)
-  static constexpr int QROWS = 80;               // 64 patch queries + the class-token query in row 64 (+15 zero rows)
-  static constexpr int QT = QROWS * LD;          // elements
-  static constexpr int KT = 64 * LD;
-  static constexpr int STAGE = QT + 2 * KT + 2 * HD;   // Q tile, K chunk, V chunk, class-token k / v vectors
-  static constexpr int NST = HD == 32 ? 4 : 3;   // cp.async ring depth
-  static constexpr int BYTES = (NST * STAGE + QT) * 2;  // ring + output staging
+  static constexpr int ROWS = 80;                // 64 patch rows + the class-token row (64) + 15 zero rows
+  static constexpr int T = ROWS * LD;            // one tile (elements)
+  static constexpr int STAGE = 3 * T;            // Q, K, V tiles
+  static constexpr int NST = HD == 32 ? 3 : 2;   // cp.async ring depth
+  static constexpr int BYTES = (NST * STAGE + T) * 2;  // ring + output staging
 };
 
-// Persistent, software-pipelined: every CTA walks a strided list of work items (sequence, head, 64-query block) and
-// their 64-key chunks; the loads of step s+NST-1 are in flight (cp.async ring) while step s is computed.
-// Five identical MMA warps: warps 0-3 own 16 patch queries each, warp 4 owns a 16-row tile whose row 0 is the
-// class-token query (rows 1-15 are zeros) so the class token rides the same tensor-core path.
+// Persistent, software-pipelined flash attention for one (sequence, head, 64-query block) per step and 64-key chunk:
+// the loads of step s+NST-1 are in flight (cp.async ring) while step s is computed.
+//  * Five identical MMA warps: warps 0-3 own 16 patch queries each; warp 4 owns a 16-row tile whose row 0 is the
+//    class-token query (rows 1-15 zero), so the class token rides the same tensor-core path.
+//  * The class-token KEY/VALUE sit in row 64 of the K/V tiles and are consumed as a ninth 8-key MMA tile (first
+//    chunk only), so 65-token sequences cost 9/8 of a 64-token one instead of 2x.
+//  * cls_only: only warp 4 computes (last decoder layer: only row 0 of each sequence reaches the head).
+// The kernel is instruction-issue bound (64x64x32 tiles), so per-step address arithmetic is hoisted out of the loop.
 template <int HD>
-__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) {
+__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, int cls_only) {
   using SM = AttnSmem<HD>;
   constexpr int LD = SM::LD;
   constexpr int NST = SM::NST;
-  constexpr int PIECES = HD / 8;    // 16-byte pieces per head row
+  constexpr int PIECES = HD / 8;                      // 16-byte pieces per head row
+  constexpr int NLD = (64 * PIECES + 159) / 160;      // tile pieces per thread
   extern __shared__ __align__(16) uint8_t attn_smem_raw[];
   bf16* smem = reinterpret_cast<bf16*>(attn_smem_raw);
   bf16* sO = smem + NST * SM::STAGE;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qblocks = (a.nq_patch + 63) / 64;
+  const int qblocks = cls_only ? 1 : (a.nq_patch + 63) / 64;
   const int n_chunks = (a.nk_patch + 63) / 64;
+  const bool ragged_k = (a.nk_patch & 63) != 0;
   const float sl2 = a.scale * kLog2e;
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, ri = lane & 7;
 
-  // rows 65..79 of every stage's Q tile are never loaded: zero them once
-  for (int st = 0; st < NST; ++st)
-    for (int idx = tid; idx < 15 * LD; idx += 160) smem[st * SM::STAGE + 65 * LD + idx] = __float2bfloat16(0.f);
+  // rows 65..79 of every tile are never loaded: zero them once (they multiply into the MMAs as exact zeros)
+  for (int i = tid; i < NST * 3 * 15 * LD; i += 160) {
+    const int tile = i / (15 * LD), r = i % (15 * LD);
+    smem[tile * SM::T + 65 * LD + r] = __float2bfloat16(0.f);
+  }
+
+  // per-thread load slots: (row, 16-byte piece) pairs are the same every step
+  int row_of[NLD], soff[NLD], qoff[NLD], koff[NLD], voff[NLD];
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    const int idx = tid + i * 160;
+    const int row = idx / PIECES, pc = idx % PIECES;
+    row_of[i] = idx < 64 * PIECES ? row : 1 << 20;    // out-of-range slots never pass the row test
+    soff[i] = row * LD + pc * 8;
+    qoff[i] = row * a.q_ld + pc * 8;
+    koff[i] = row * a.k_ld + pc * 8;
+    voff[i] = row * a.v_ld + pc * 8;
+  }
 
   auto issue_loads = [&](int item, int kc, bf16* st) {
-    const int qb = item % qblocks;
-    const int hh = (item / qblocks) % a.n_heads;
-    const int bb = item / (qblocks * a.n_heads);
+    const int qb = qblocks == 1 ? 0 : item % qblocks;
+    const int it2 = qblocks == 1 ? item : item / qblocks;
+    const int hh = it2 % a.n_heads;
+    const int bb = it2 / a.n_heads;
     const int kvb = a.kv_index ? __ldg(a.kv_index + bb) : bb;
     bf16* Qs = st;
-    bf16* Ks = st + SM::QT;
-    bf16* Vs = Ks + SM::KT;
-    bf16* cls = Vs + SM::KT;
+    bf16* Ks = st + SM::T;
+    bf16* Vs = st + 2 * SM::T;
     if (kc == 0) {
-      const int q0 = qb * 64;
-      for (int idx = tid; idx < 64 * PIECES; idx += 160) {
-        const int row = idx / PIECES, pc = idx % PIECES;
-        const bool ok = q0 + row < a.nq_patch;
-        const bf16* src = ok ? a.q + ((size_t)bb * a.nq_patch + q0 + row) * a.q_ld + hh * HD + pc * 8 : a.q;
-        cp_async16(&Qs[row * LD + pc * 8], src, ok);
+      if (!cls_only) {
+        const int q0 = qb * 64;
+        const int qrows = a.nq_patch - q0;
+        const bf16* qbase = a.q + ((size_t)bb * a.nq_patch + q0) * a.q_ld + hh * HD;
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) {
+          if (row_of[i] < 64) {
+            const bool ok = row_of[i] < qrows;
+            cp_async16(Qs + soff[i], ok ? qbase + qoff[i] : a.q, ok);
+          }
+        }
       }
       if (tid < 3 * PIECES) {
         const int which = tid / PIECES, pc = tid % PIECES;
         if (which == 0) {   // class-token query -> row 64 of the Q tile
           const bool ok = a.q_has_cls && qb == 0;
-          const bf16* src = a.q + ((size_t)a.n_seq * a.nq_patch + bb) * a.q_ld + hh * HD + pc * 8;
-          cp_async16(&Qs[64 * LD + pc * 8], ok ? src : a.q, ok);
-        } else {            // class-token key / value vectors
+          cp_async16(Qs + 64 * LD + pc * 8,
+                     ok ? a.q + ((size_t)a.n_seq * a.nq_patch + bb) * a.q_ld + hh * HD + pc * 8 : a.q, ok);
+        } else {            // class-token key / value -> row 64 of the K / V tiles
           const bool ok = a.k_has_cls;
           const size_t krow = (size_t)a.n_kv_seq * a.nk_patch + kvb;
           const bf16* src = which == 1 ? a.k + krow * a.k_ld + hh * HD + pc * 8 : a.v + krow * a.v_ld + hh * HD + pc * 8;
-          cp_async16(&cls[(which - 1) * HD + pc * 8], ok ? src : a.q, ok);
+          cp_async16((which == 1 ? Ks : Vs) + 64 * LD + pc * 8, ok ? src : a.q, ok);
         }
       }
     }
     const int k0 = kc * 64;
-    for (int idx = tid; idx < 64 * PIECES; idx += 160) {
-      const int row = idx / PIECES, pc = idx % PIECES;
-      const bool ok = k0 + row < a.nk_patch;
-      const size_t grow = (size_t)kvb * a.nk_patch + k0 + row;
-      cp_async16(&Ks[row * LD + pc * 8], ok ? a.k + grow * a.k_ld + hh * HD + pc * 8 : a.k, ok);
-      cp_async16(&Vs[row * LD + pc * 8], ok ? a.v + grow * a.v_ld + hh * HD + pc * 8 : a.v, ok);
+    const int krows = a.nk_patch - k0;
+    const bf16* kbase = a.k + ((size_t)kvb * a.nk_patch + k0) * a.k_ld + hh * HD;
+    const bf16* vbase = a.v + ((size_t)kvb * a.nk_patch + k0) * a.v_ld + hh * HD;
+#pragma unroll
+    for (int i = 0; i < NLD; ++i) {
+      if (row_of[i] < 64) {
+        const bool ok = row_of[i] < krows;
+        cp_async16(Ks + soff[i], ok ? kbase + koff[i] : a.k, ok);
+        cp_async16(Vs + soff[i], ok ? vbase + voff[i] : a.v, ok);
+      }
     }
   };
 
@@ -126,15 +155,11 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
     __syncthreads();
 
     bf16* st = smem + stage * SM::STAGE;
-    const int qb = item % qblocks;
-    const int h = (item / qblocks) % a.n_heads;
-    const int b = item / (qblocks * a.n_heads);
-    const int q0 = qb * 64, k0 = kc * 64;
-    const bool active = warp < 4 || (a.q_has_cls && qb == 0);   // warp 4 only carries the class-token query
-    bf16* Qs = st;
-    bf16* Ks = st + SM::QT;
-    bf16* Vs = Ks + SM::KT;
-    bf16* cls = Vs + SM::KT;
+    const int qb = qblocks == 1 ? 0 : item % qblocks;
+    const bool active = warp == 4 ? (a.q_has_cls && qb == 0) : !cls_only;
+    const bf16* Qs = st;
+    const bf16* Ks = st + SM::T;
+    const bf16* Vs = st + 2 * SM::T;
 
     if (active) {
       if (kc == 0) {
@@ -144,37 +169,17 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
           const int col = ks * 16 + (mi >> 1) * 8;
           ldsm_x4(smem_u32(&Qs[row * LD + col]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
         }
-        if (a.k_has_cls) {
-          // seed the online softmax with the class-token key: m = q.k_cls, l = 1, O = v_cls
-          float s0 = 0.f, s1 = 0.f;
+        m_row[0] = m_row[1] = -INFINITY;
+        l_row[0] = l_row[1] = 0.f;
 #pragma unroll
-          for (int i = 0; i < HD / 4; ++i) {
-            const int d = t * (HD / 4) + i;
-            const float kcv = __bfloat162float(cls[d]);
-            s0 += __bfloat162float(Qs[(warp * 16 + g) * LD + d]) * kcv;
-            s1 += __bfloat162float(Qs[(warp * 16 + g + 8) * LD + d]) * kcv;
-          }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-          m_row[0] = s0 * sl2; m_row[1] = s1 * sl2;
-          l_row[0] = l_row[1] = (t == 0) ? 1.f : 0.f;   // thread-partial row sums; the quad is reduced at the end
-#pragma unroll
-          for (int nt = 0; nt < HD / 8; ++nt) {
-            o_acc[nt][0] = o_acc[nt][2] = __bfloat162float(cls[HD + nt * 8 + 2 * t]);
-            o_acc[nt][1] = o_acc[nt][3] = __bfloat162float(cls[HD + nt * 8 + 2 * t + 1]);
-          }
-        } else {
-          m_row[0] = m_row[1] = -INFINITY;
-          l_row[0] = l_row[1] = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < HD / 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
-        }
+        for (int nt = 0; nt < HD / 8; ++nt) o_acc[nt][0] = o_acc[nt][1] = o_acc[nt][2] = o_acc[nt][3] = 0.f;
       }
+      const bool with_cls_key = a.k_has_cls && kc == 0;   // ninth key tile: row 64 = class-token key
 
-      // ---- S = Q K^T : 16 queries x 64 keys per warp ----
-      float s[8][4];
+      // ---- S = Q K^T : 16 queries x (64 [+8]) keys per warp, raw (unscaled) scores ----
+      float s[9][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      for (int nt = 0; nt < 9; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
 #pragma unroll
@@ -187,38 +192,58 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
           mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
         }
       }
+      if (with_cls_key) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ks += 2) {
+          // one ldmatrix.x4 = the (keys 64..71) B fragments of two k-steps
+          const int key = 64 + ri;
+          const int dim = ks * 16 + mi * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(smem_u32(&Ks[key * LD + dim]), b0, b1, b2, b3);
+          mma_bf16_16816(s[8], qf[ks], b0, b1);
+          mma_bf16_16816(s[8], qf[ks + 1], b2, b3);
+        }
+      }
       // ---- online softmax (rows g and g+8 of this warp's tile) ----
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (ragged_k) {
+        const int k0 = kc * 64;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int key = k0 + nt * 8 + 2 * t;
+          if (key >= a.nk_patch) s[nt][0] = s[nt][2] = -INFINITY;
+          if (key + 1 >= a.nk_patch) s[nt][1] = s[nt][3] = -INFINITY;
+        }
+      }
+      // only key 64 of the ninth tile exists (thread t == 0, first element)
+      if (!(with_cls_key && t == 0)) s[8][0] = s[8][2] = -INFINITY;
+      s[8][1] = s[8][3] = -INFINITY;
+      float mx0 = fmaxf(s[8][0], s[8][1]), mx1 = fmaxf(s[8][2], s[8][3]);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const int key = k0 + nt * 8 + 2 * t;
-        const bool v0 = key < a.nk_patch, v1 = key + 1 < a.nk_patch;
-        s[nt][0] = v0 ? s[nt][0] * sl2 : -INFINITY;
-        s[nt][1] = v1 ? s[nt][1] * sl2 : -INFINITY;
-        s[nt][2] = v0 ? s[nt][2] * sl2 : -INFINITY;
-        s[nt][3] = v1 ? s[nt][3] * sl2 : -INFINITY;
         mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
         mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m_row[0], mx0), mn1 = fmaxf(m_row[1], mx1);
+      const float mn0 = fmaxf(m_row[0], mx0 * sl2), mn1 = fmaxf(m_row[1], mx1 * sl2);   // scaled (log2) units
       const float c0 = exp2f(m_row[0] - mn0), c1 = exp2f(m_row[1] - mn1);
       m_row[0] = mn0; m_row[1] = mn1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f(s[nt][0] - mn0); s[nt][1] = exp2f(s[nt][1] - mn0);
-        s[nt][2] = exp2f(s[nt][2] - mn1); s[nt][3] = exp2f(s[nt][3] - mn1);
+      for (int nt = 0; nt < 9; ++nt) {
+        s[nt][0] = exp2f(fmaf(s[nt][0], sl2, -mn0)); s[nt][1] = exp2f(fmaf(s[nt][1], sl2, -mn0));
+        s[nt][2] = exp2f(fmaf(s[nt][2], sl2, -mn1)); s[nt][3] = exp2f(fmaf(s[nt][3], sl2, -mn1));
         rs0 += s[nt][0] + s[nt][1];
         rs1 += s[nt][2] + s[nt][3];
       }
-      l_row[0] = l_row[0] * c0 + rs0;
+      l_row[0] = l_row[0] * c0 + rs0;    // thread-partial row sums; the quad is reduced at the end
       l_row[1] = l_row[1] * c1 + rs1;
+      if (kc > 0) {
 #pragma unroll
-      for (int nt = 0; nt < HD / 8; ++nt) {
-        o_acc[nt][0] *= c0; o_acc[nt][1] *= c0;
-        o_acc[nt][2] *= c1; o_acc[nt][3] *= c1;
+        for (int nt = 0; nt < HD / 8; ++nt) {
+          o_acc[nt][0] *= c0; o_acc[nt][1] *= c0;
+          o_acc[nt][2] *= c1; o_acc[nt][3] *= c1;
+        }
       }
       // ---- O += P V ----
 #pragma unroll
@@ -238,15 +263,35 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
           mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
         }
       }
+      if (with_cls_key) {
+        // fifth k-step: keys 64..79 (64 = class token, 65..79 are zero rows with zero probabilities)
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[8][0], s[8][1]);
+        pa[1] = pack_bf16(s[8][2], s[8][3]);
+        pa[2] = 0u;
+        pa[3] = 0u;
+#pragma unroll
+        for (int dp = 0; dp < HD / 16; ++dp) {
+          const int key = 64 + (mi & 1) * 8 + ri;
+          const int dim = dp * 16 + (mi >> 1) * 8;
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(smem_u32(&Vs[key * LD + dim]), b0, b1, b2, b3);
+          mma_bf16_16816(o_acc[2 * dp], pa, b0, b1);
+          mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
+        }
+      }
 
       // ---- finalize the item after its last chunk ----
       if (kc == n_chunks - 1) {
+        const int it2 = qblocks == 1 ? item : item / qblocks;
+        const int h = it2 % a.n_heads;
+        const int b = it2 / a.n_heads;
+        const int q0 = qb * 64;
         float l0 = l_row[0], l1 = l_row[1];
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
         const float i0 = 1.f / l0, i1 = 1.f / l1;
-        // each warp stages and stores its own 16 rows; the previous item's rows were stored before the two
-        // __syncthreads of the steps in between, and only this warp touches these sO rows
+        // each warp stages and stores its own 16 rows (only this warp ever touches these sO rows)
 #pragma unroll
         for (int nt = 0; nt < HD / 8; ++nt) {
           *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g) * LD + nt * 8 + 2 * t]) =
@@ -256,12 +301,12 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items) 
         }
         __syncwarp();
         if (warp < 4) {
+          bf16* obase = a.o + ((size_t)b * a.nq_patch + q0) * a.o_ld + h * HD;
           for (int idx = lane; idx < 16 * PIECES; idx += 32) {
             const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
-            if (q0 + row < a.nq_patch) {
-              *reinterpret_cast<uint4*>(a.o + ((size_t)b * a.nq_patch + q0 + row) * a.o_ld + h * HD + pc * 8) =
+            if (q0 + row < a.nq_patch)
+              *reinterpret_cast<uint4*>(obase + (size_t)row * a.o_ld + pc * 8) =
                   *reinterpret_cast<const uint4*>(&sO[row * LD + pc * 8]);
-            }
           }
         } else if (lane < PIECES) {
           const size_t orow = (size_t)a.n_seq * a.nq_patch + b;   // class-token output row
@@ -345,86 +390,14 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(AttnArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// class-token-only attention: one warp per (sequence, head). Used by the LAST decoder layer, where only row 0 of every
-// sequence reaches the head (vision_transformer.py:400 + timm forward_head), so the patch queries are dead work.
-// q: [n_seq, q_ld] (one query row per sequence); keys/values in the split layout.
-// ------------------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void __launch_bounds__(256) attn_cls_kernel(AttnArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int nk = a.nk_patch + a.k_has_cls;
-  const float sl2 = a.scale * kLog2e;
-  const size_t warps_total = ((size_t)gridDim.x * blockDim.x) >> 5;
-  const size_t items = (size_t)a.n_seq * a.n_heads;
-  for (size_t item = (((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); item < items; item += warps_total) {
-    const int h = (int)(item % a.n_heads);
-    const int b = (int)(item / a.n_heads);
-    const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;
-    float q[HD];
-    {
-      const uint4* qp = reinterpret_cast<const uint4*>(a.q + (size_t)b * a.q_ld + h * HD);
-#pragma unroll
-      for (int pc = 0; pc < HD / 8; ++pc) {
-        const uint4 v = __ldg(qp + pc);
-        const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
-        q[pc * 8 + 0] = f0.x; q[pc * 8 + 1] = f0.y; q[pc * 8 + 2] = f1.x; q[pc * 8 + 3] = f1.y;
-        q[pc * 8 + 4] = f2.x; q[pc * 8 + 5] = f2.y; q[pc * 8 + 6] = f3.x; q[pc * 8 + 7] = f3.y;
-      }
-    }
-    float m = -INFINITY, l = 0.f;
-    float acc[HD / 32];
-#pragma unroll
-    for (int i = 0; i < HD / 32; ++i) acc[i] = 0.f;
-    for (int j0 = 0; j0 < nk; j0 += 32) {
-      const int j = j0 + lane;
-      float s = -INFINITY;
-      if (j < nk) {
-        const size_t row = tok_row(a.n_kv_seq, a.nk_patch, a.k_has_cls, kvb, j);
-        const uint4* kp = reinterpret_cast<const uint4*>(a.k + row * a.k_ld + h * HD);
-        float d = 0.f;
-#pragma unroll
-        for (int pc = 0; pc < HD / 8; ++pc) {
-          const uint4 v = __ldg(kp + pc);
-          const float2 f0 = unpack_bf16(v.x), f1 = unpack_bf16(v.y), f2 = unpack_bf16(v.z), f3 = unpack_bf16(v.w);
-          d += q[pc * 8 + 0] * f0.x + q[pc * 8 + 1] * f0.y + q[pc * 8 + 2] * f1.x + q[pc * 8 + 3] * f1.y +
-               q[pc * 8 + 4] * f2.x + q[pc * 8 + 5] * f2.y + q[pc * 8 + 6] * f3.x + q[pc * 8 + 7] * f3.y;
-        }
-        s = d * sl2;
-      }
-      const float mn = fmaxf(m, warp_max(s));
-      const float corr = exp2f(m - mn);
-      const float p = exp2f(s - mn);
-      l = l * corr + warp_sum(p);
-      m = mn;
-#pragma unroll
-      for (int i = 0; i < HD / 32; ++i) acc[i] *= corr;
-      const int jn = min(32, nk - j0);
-      for (int jj = 0; jj < jn; ++jj) {
-        const float pj = __shfl_sync(0xffffffffu, p, jj);
-        const size_t row = tok_row(a.n_kv_seq, a.nk_patch, a.k_has_cls, kvb, j0 + jj);
-#pragma unroll
-        for (int i = 0; i < HD / 32; ++i) acc[i] += pj * __bfloat162float(a.v[row * a.v_ld + h * HD + lane + 32 * i]);
-      }
-    }
-    const float inv = 1.f / l;
-#pragma unroll
-    for (int i = 0; i < HD / 32; ++i)
-      a.o[(size_t)b * a.o_ld + h * HD + lane + 32 * i] = __float2bfloat16_rn(acc[i] * inv);
-  }
-}
+static int attention_launch(const AttnArgs& a, int cls_only, cudaStream_t stream);
 
+// class-token query only (last decoder layer): same kernel, only the fifth warp computes.
 int attention_cls(const AttnArgs& a, cudaStream_t stream) {
   VITED_CHECK(a.head_dim == 32 || a.head_dim == 64, "attention_cls: head_dim %d not supported (32 or 64)", a.head_dim);
-  VITED_CHECK(a.q_ld % 8 == 0 && a.k_ld % 8 == 0 && a.v_ld % 8 == 0, "attention_cls: row strides must be multiples of 8");
+  VITED_CHECK(a.q_has_cls, "attention_cls: the query sequences have no class token");
   if (a.n_seq == 0) return 0;
-  const size_t items = (size_t)a.n_seq * a.n_heads;
-  size_t blocks = (items + 7) / 8;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (a.head_dim == 32) attn_cls_kernel<32><<<(unsigned)blocks, 256, 0, stream>>>(a);
-  else attn_cls_kernel<64><<<(unsigned)blocks, 256, 0, stream>>>(a);
-  VITED_CUDA_OK(cudaGetLastError());
-  return 0;
+  return attention_launch(a, 1, stream);
 }
 
 int attention(const AttnArgs& a, int impl, cudaStream_t stream) {
@@ -439,32 +412,39 @@ int attention(const AttnArgs& a, int impl, cudaStream_t stream) {
     if (a.head_dim == 32) attn_simt_kernel<32><<<grid, 128, 0, stream>>>(a);
     else attn_simt_kernel<64><<<grid, 128, 0, stream>>>(a);
   } else {
-    const size_t items = (size_t)a.n_seq * a.n_heads * ((a.nq_patch + 63) / 64);
-    VITED_CHECK(items < (size_t)1 << 31, "attention: too many work items");
-    static int sms = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-      int dev = 0;
-      VITED_CUDA_OK(cudaGetDevice(&dev));
-      VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         AttnSmem<32>::BYTES));
-      VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         AttnSmem<64>::BYTES));
-      attr_set = true;
-    }
-    static int per_sm32 = 0, per_sm64 = 0;        // resident CTAs per SM (registers / shared memory)
-    if (per_sm32 == 0) {
-      VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, attn_mma_kernel<32>, 160, AttnSmem<32>::BYTES));
-      VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm64, attn_mma_kernel<64>, 160, AttnSmem<64>::BYTES));
-      if (per_sm32 < 1) per_sm32 = 1;
-      if (per_sm64 < 1) per_sm64 = 1;
-    }
-    const int per_sm = a.head_dim == 32 ? per_sm32 : per_sm64;
-    size_t grid = (size_t)sms * per_sm;
-    if (grid > items) grid = items;
-    if (a.head_dim == 32) attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(a, (int)items);
-    else attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(a, (int)items);
+    return attention_launch(a, 0, stream);
+  }
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int attention_launch(const AttnArgs& a, int cls_only, cudaStream_t stream) {
+  const size_t items = (size_t)a.n_seq * a.n_heads * (cls_only ? 1 : (a.nq_patch + 63) / 64);
+  VITED_CHECK(items < (size_t)1 << 31, "attention: too many work items");
+  static int sms = 0, per_sm32 = 0, per_sm64 = 0;   // resident CTAs per SM (registers / shared memory)
+  if (sms == 0) {
+    int dev = 0;
+    VITED_CUDA_OK(cudaGetDevice(&dev));
+    VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<32>::BYTES));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::BYTES));
+    VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, attn_mma_kernel<32>, 160, AttnSmem<32>::BYTES));
+    VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm64, attn_mma_kernel<64>, 160, AttnSmem<64>::BYTES));
+    if (per_sm32 < 1) per_sm32 = 1;
+    if (per_sm64 < 1) per_sm64 = 1;
+  }
+  const int per_sm = a.head_dim == 32 ? per_sm32 : per_sm64;
+  size_t grid = (size_t)sms * per_sm;
+  if (grid > items) grid = items;
+  AttnArgs b = a;
+  if (cls_only) {
+    // with cls_only the 64-query blocks are not walked: one item per (sequence, head); the class-token query row is
+    // still addressed as row n_seq*nq_patch + b of the q buffer
+    if (a.head_dim == 32) attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(b, (int)items, 1);
+    else attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(b, (int)items, 1);
+  } else {
+    if (a.head_dim == 32) attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(b, (int)items, 0);
+    else attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(b, (int)items, 0);
   }
   VITED_CUDA_OK(cudaGetLastError());
   return 0;

@@ -285,13 +285,14 @@ static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o,
   return attention(a, e->attn_impl, s);
 }
 
-// class-token-only attention (last decoder layer). q_cls/o_cls: [n_seq, ld]; keys in the split layout.
-static int L_attn_cls(vited_engine* e, const bf16* q_cls, int q_ld, const bf16* k, const bf16* v, int kv_ld, bf16* o_cls,
+// class-token-only attention (last decoder layer). q/o are the full split-layout buffers: only their class-token rows
+// (row n_seq*Ne + b) are read / written.
+static int L_attn_cls(vited_engine* e, const bf16* q, int q_ld, const bf16* k, const bf16* v, int kv_ld, bf16* o,
                       int n_seq, int k_has_cls, int n_kv_seq, const int* kv_index, cudaStream_t s) {
   AttnArgs a;
-  a.q = q_cls; a.q_ld = q_ld; a.k = k; a.k_ld = kv_ld; a.v = v; a.v_ld = kv_ld; a.o = o_cls; a.o_ld = e->D;
+  a.q = q; a.q_ld = q_ld; a.k = k; a.k_ld = kv_ld; a.v = v; a.v_ld = kv_ld; a.o = o; a.o_ld = e->D;
   a.n_seq = n_seq; a.n_heads = e->H; a.head_dim = e->hd;
-  a.nq_patch = 0; a.q_has_cls = 1; a.nk_patch = e->Ne; a.k_has_cls = k_has_cls;
+  a.nq_patch = e->Ne; a.q_has_cls = 1; a.nk_patch = e->Ne; a.k_has_cls = k_has_cls;
   a.n_kv_seq = n_kv_seq; a.kv_index = kv_index; a.scale = e->scale;
   prof_mark(e, "attn_cls", 4.0 * n_seq * (double)(e->Ne + k_has_cls) * e->D,
             (double)n_seq * (e->Ne + k_has_cls) * e->D * 2.0 * 2.0, s);
@@ -483,12 +484,12 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
         Linear w_q = b.qkv; w_q.out = (int)D;
         TRY(L_gemm(e, h, w_kv, qkv, (int)rows, ACT_NONE, s));          // [rows, 2D]
         TRY(L_gemm(e, h_c, w_q, q_c, P, ACT_NONE, s));                 // [P, D]
-        TRY(L_attn_cls(e, q_c, (int)D, qkv, qkv + D, 2 * (int)D, o_c, P, 1, P, nullptr, s));
+        TRY(L_attn_cls(e, q, (int)D, qkv, qkv + D, 2 * (int)D, o, P, 1, P, nullptr, s));
         TRY(L_gemm(e, o_c, b.proj, d_c, P, ACT_NONE, s));
         TRY(L_resid_ln_rows(e, x_c, d_c, nullptr, nullptr, &b.norm_cross, h_c, P, s));
       }
       TRY(L_gemm(e, h_c, b.q, q_c, P, ACT_NONE, s));
-      TRY(L_attn_cls(e, q_c, (int)D, kvl, kvl + D, 2 * (int)D, o_c, P, 0, n_kv_seq, ci, s));
+      TRY(L_attn_cls(e, q, (int)D, kvl, kvl + D, 2 * (int)D, o, P, 0, n_kv_seq, ci, s));
       TRY(L_gemm(e, o_c, b.cproj, d_c, P, ACT_NONE, s));
       TRY(L_resid_ln_rows(e, x_c, d_c, nullptr, nullptr, &b.norm2, h_c, P, s));
       TRY(L_gemm(e, h_c, b.fc1, hid, P, ACT_GELU, s));

@@ -62,17 +62,23 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t r
 constexpr int BM = 128;
 constexpr int BK = 64;
 
-template <int BN>
+// KB_RES == 0: both operands stream through the ring (any K).
+// KB_RES  > 0: "resident weights": the CTA keeps its [BN x K] weight panel (K <= 64*KB_RES) in shared memory for its
+//              whole life and only the activation tiles stream; this halves the L2->SM traffic of the K=384 layers,
+//              which is what bounds them (a 128xBN tile with K=384 needs only 24 MMAs per 240 KB of operands).
+template <int BN, int KB_RES>
 struct GemmCfg {
   static constexpr int kEpiWarps = 4 * (BN / 64);
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
-  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t STAGE_BYTES = KB_RES > 0 ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr uint32_t PANEL_BYTES = KB_RES * B_BYTES;
   static constexpr uint32_t C_BYTES = kEpiWarps * 4096;  // one 32-row x 128-byte swizzled box per epilogue warp
-  static constexpr int kStages = (232448 - 1024 - 256 - (int)C_BYTES) / (int)STAGE_BYTES;
+  static constexpr int kStagesMax = (232448 - 1024 - 256 - (int)C_BYTES - (int)PANEL_BYTES) / (int)STAGE_BYTES;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
   static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
-  static constexpr uint32_t SMEM_BYTES = 1024 + kStages * STAGE_BYTES + C_BYTES + 256;
+  static constexpr uint32_t SMEM_BYTES = 1024 + PANEL_BYTES + kStages * STAGE_BYTES + C_BYTES + 256;
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 up to 256");
   static_assert(kStages >= 3, "not enough shared memory for the pipeline");
 };
@@ -93,30 +99,40 @@ __device__ __forceinline__ float gelu_fast(float v) {
   return fmaf(-0.5f * p, ex, fmaxf(v, 0.0f));
 }
 
-template <int BN, int ACT>
-__global__ void __launch_bounds__(GemmCfg<BN>::kThreads, 1)
+template <int BN, int ACT, int KB_RES>
+__global__ void __launch_bounds__(GemmCfg<BN, KB_RES>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, KB_RES>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kEpiWarps = Cfg::kEpiWarps;
+  constexpr bool kResident = KB_RES > 0;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sPanel = smem_base;                      // resident weight panel: KB_RES boxes of [BN x 64] (may be empty)
+  uint8_t* smem = smem_base + Cfg::PANEL_BYTES;     // operand ring
   uint8_t* sC = smem + kStages * Cfg::STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sC + Cfg::C_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
   uint64_t* tempty = bars + 2 * kStages + 2;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* pfull = bars + 2 * kStages + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
   const int m_blks = (M + BM - 1) / BM;
   const int n_blks = (N + BN - 1) / BN;
-  const int num_tiles = m_blks * n_blks;
   const int num_kb = (K + BK - 1) / BK;
+  // Tile schedule. Streaming: tile = blockIdx.x + i*gridDim.x, n fastest. Resident: the CTA owns ONE n-block
+  // (blockIdx.x % n_blks) and walks the m-blocks (blockIdx.x / n_blks) + i*(gridDim.x / n_blks); the host launches a
+  // grid that is a multiple of n_blks.
+  const int my_n = kResident ? (int)(blockIdx.x % n_blks) : 0;
+  const int tile0 = kResident ? (int)(blockIdx.x / n_blks) : (int)blockIdx.x;
+  const int tile_step = kResident ? (int)(gridDim.x / n_blks) : (int)gridDim.x;
+  const int num_tiles = kResident ? m_blks : m_blks * n_blks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -131,6 +147,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], kEpiWarps);
     }
+    mbar_init(pfull, 1);
     fence_mbar_init();
   } else if (warp == 2) {
     tmem_alloc(tmem_holder, Cfg::TMEM_COLS);
@@ -145,15 +162,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+      if (kResident && tile0 < num_tiles) {
+        mbar_arrive_expect_tx(pfull, (uint32_t)num_kb * Cfg::B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tmB, pfull, sPanel + kb * Cfg::B_BYTES, kb * BK, my_n * BN);
+      }
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int m_blk = kResident ? tile : tile / n_blks;
+        const int n_blk = kResident ? my_n : tile % n_blks;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 10);
           uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           tma_load_2d(&tmA, &full[stage], a_dst, kb * BK, m_blk * BM);
-          tma_load_2d(&tmB, &full[stage], b_dst, kb * BK, n_blk * BN);
+          if (!kResident) tma_load_2d(&tmB, &full[stage], a_dst + Cfg::A_BYTES, kb * BK, n_blk * BN);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -163,7 +184,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (kResident && tile0 < num_tiles) mbar_wait(pfull, 0, 22);
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tempty[as], aphase ^ 1, 20);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -172,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+          const uint64_t db = umma_desc_sw128(kResident ? smem_u32(sPanel + kb * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
@@ -194,8 +216,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* rowp = my_stage + lane * 128;
     uint32_t as = 0, aphase = 0;
     bool store_pending = false;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_blks, n_blk = tile % n_blks;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      const int m_blk = kResident ? tile : tile / n_blks;
+      const int n_blk = kResident ? my_n : tile % n_blks;
       const int n0 = n_blk * BN + sl * 64;
       mbar_wait(&tfull[as], aphase, 30);
       tc_fence_after();
@@ -268,27 +291,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BN, int ACT>
+template <int BN, int ACT, int KB_RES>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                      int N, int K, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, KB_RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT, KB_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_tc_kernel<BN, ACT><<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
+  const int m_blks = (M + BM - 1) / BM, n_blks = (N + BN - 1) / BN;
+  int grid;
+  if (KB_RES > 0) {
+    int per_n = g_num_sms / n_blks;   // CTAs per weight panel
+    if (per_n > m_blks) per_n = m_blks;
+    grid = per_n * n_blks;
+  } else {
+    const int tiles = m_blks * n_blks;
+    grid = tiles < g_num_sms ? tiles : g_num_sms;
+  }
+  gemm_tc_kernel<BN, ACT, KB_RES><<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+template <int BN, int KB_RES>
+static int launch_act(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
+                      int N, int K, int act, cudaStream_t stream) {
+  return act == ACT_GELU ? launch_tc<BN, ACT_GELU, KB_RES>(tA, tB, tC, bias, M, N, K, stream)
+                         : launch_tc<BN, ACT_NONE, KB_RES>(tA, tB, tC, bias, M, N, K, stream);
 }
 
 int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act,
               cudaStream_t stream);
 
-static int g_block_n = 0;  // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic choice (tuning knob)
+static int g_block_n = 0;   // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic tile width (tuning knob)
+static int g_resident = -1; // VITED_GEMM_RESIDENT=0 disables the resident-weights variant (tuning knob)
 
 int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream) {
@@ -304,25 +343,27 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
   if (g_block_n == 0) {
     const char* e = getenv("VITED_GEMM_BN");
     g_block_n = e ? atoi(e) : -1;
+    const char* r = getenv("VITED_GEMM_RESIDENT");
+    g_resident = r ? atoi(r) : 1;
   }
+  const int m_blks = (M + BM - 1) / BM;
+  // resident weights: K <= 384, 128-wide panels, and enough m-blocks per panel to amortise loading it
+  const bool resident = g_resident && g_block_n < 0 && K <= 384 && N % 128 == 0 && N / 128 <= 16 &&
+                        m_blks >= 4 * (g_num_sms / (N / 128));
   int bn = 128;
-  if (g_block_n == 128 || g_block_n == 192 || g_block_n == 256) bn = g_block_n;
-  else if (N % 256 == 0) bn = 256;
-  else if (N % 192 == 0) bn = 192;
+  if (!resident) {
+    if (g_block_n == 128 || g_block_n == 192 || g_block_n == 256) bn = g_block_n;
+    else if (N % 256 == 0) bn = 256;
+    else if (N % 192 == 0) bn = 192;
+  }
   CUtensorMap tA, tB, tC;
   if (make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, BM)) return 1;
   if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)bn)) return 1;
   if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
-  if (bn == 128) {
-    return act == ACT_GELU ? launch_tc<128, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
-                           : launch_tc<128, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
-  }
-  if (bn == 256) {
-    return act == ACT_GELU ? launch_tc<256, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
-                           : launch_tc<256, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
-  }
-  return act == ACT_GELU ? launch_tc<192, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
-                         : launch_tc<192, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+  if (resident) return launch_act<128, 6>(tA, tB, tC, bias, M, N, K, act, stream);
+  if (bn == 128) return launch_act<128, 0>(tA, tB, tC, bias, M, N, K, act, stream);
+  if (bn == 256) return launch_act<256, 0>(tA, tB, tC, bias, M, N, K, act, stream);
+  return launch_act<192, 0>(tA, tB, tC, bias, M, N, K, act, stream);
 }
 
 }  // namespace vited
