@@ -353,6 +353,47 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_hisfrag(args):
+    """Side measurement (not the driver's line): BASELINE.json configs[3] model (patch16/512, 12+12 layers) on a
+    small all-pairs grid of `--items` synthetic fragments on ONE GPU; reports pairs/s and the tensor-roofline
+    fraction with the Hisfrag FLOP model of SURVEY 8d (89.50 GFLOP / pair, 63.42 + 7.25 + 0.60 GFLOP / item)."""
+    import vited_b200
+    from vited_b200 import grid, synthetic
+    torch.cuda.set_device(0)
+    peaks = load_peaks()
+    model = vited_b200.build_model(vited_b200.get_config('hisfrag'))
+    model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0), strict=True)
+    model = model.cuda().eval()
+    n = args.items
+    images = synthetic.synthetic_images(n, 512, seed=1000).cuda()
+    n_pairs = n * (n + 1) // 2
+    for _ in range(max(args.warmup, 1)):
+        grid.score_fragments(model, images)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sim = grid.score_fragments(model, images)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    model.set_option(vited_b200.OPT_PROFILE, 1)
+    grid.score_fragments(model, images)
+    prof = model.profile_read()
+    model.set_option(vited_b200.OPT_PROFILE, 0)
+    total = sum(v['ms'] for v in prof.values()) or 1.0
+    flops = n_pairs * 89.50e9 + n * (63.42e9 + 7.248e9 + 0.604e9)
+    print(json.dumps({
+        'metric': METRIC, 'value': n_pairs / (ms / 1e3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': f'configs[3] model (Hisfrag20 patch16 512px), {n} synthetic fragments, {n_pairs} pairs (a<=b), 1 GPU'},
+        'step_tensor_frac': flops / (ms / 1e3) / 1e12 / peaks['tf_sustained'],
+        'classes': {k: {'ms': round(v['ms'], 3), 'share': round(v['ms'] / total, 4),
+                        'tflops': round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 1), 'launches': v['launches']}
+                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms'])},
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -360,6 +401,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--workload', default='puzzle', choices=['puzzle', 'hisfrag'],
+                    help="'hisfrag' = side measurement of the Hisfrag20 model on a small grid (1 GPU)")
+    ap.add_argument('--items', type=int, default=48, help='fragments for --workload hisfrag')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = max(args.warmup, 0)
@@ -368,7 +412,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit('bench.py: no CUDA device; the scoring path has no CPU fallback (use --impl reference)')
-        run_ours(args)
+        if args.workload == 'hisfrag':
+            run_hisfrag(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == '__main__':

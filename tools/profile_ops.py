@@ -1,0 +1,53 @@
+"""Runs each hot kernel of the path a few times at the bench chunk shape (for ncu captures; GPU box only)."""
+import ctypes
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vited_b200 import _lib as L  # noqa: E402
+
+M = 4032 * 65
+D = 384
+torch.manual_seed(0)
+reps = int(os.environ.get('REPS', '2'))
+
+
+def gemm(N, K, act):
+    A = torch.randn(M, K, device='cuda').bfloat16()
+    W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device='cuda')
+    C = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+    for _ in range(reps):
+        L.check(L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, act, 0, None), 'gemm')
+    torch.cuda.synchronize()
+
+
+gemm(1152, 384, 0)
+gemm(1536, 384, 1)
+gemm(384, 1536, 0)
+gemm(384, 384, 0)
+P, H, hd, Np = 4032, 12, 32, 64
+qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
+o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+for _ in range(reps):
+    L.check(L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D, 3 * D,
+                                     o.data_ptr(), D, P, H, hd, Np, 1, Np, 1, P, None, hd ** -0.5, 0, None), 'attn')
+kv = torch.randn(540 * Np, 2 * D, device='cuda').bfloat16()
+q = torch.randn(M, D, device='cuda').bfloat16()
+idx = (torch.arange(P, device='cuda') // 539).int()
+for _ in range(reps):
+    L.check(L.lib.vited_op_attention(q.data_ptr(), D, kv.data_ptr(), 2 * D, kv.data_ptr() + 2 * D, 2 * D, o.data_ptr(), D,
+                                     P, H, hd, Np, 1, Np, 0, 540, idx.data_ptr(), hd ** -0.5, 0, None), 'attn')
+x = torch.randn(M, D, device='cuda')
+delta = torch.randn(M, D, device='cuda').bfloat16()
+w = torch.ones(D, device='cuda'); bb = torch.zeros(D, device='cuda')
+h = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+for _ in range(reps):
+    L.check(L.lib.vited_op_resid_ln(x.data_ptr(), delta.data_ptr(), w.data_ptr(), bb.data_ptr(), h.data_ptr(), 4032, 64, 1, D,
+                                    1e-6, None), 'ln')
+torch.cuda.synchronize()
+print('ok')

@@ -23,6 +23,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 2^x on the MUFU unit, flush-to-zero (inputs are <= 0 or -inf here); plain exp2f() adds a denormal-range fix-up
+// (3-4 extra instructions per element) that this instruction-bound kernel cannot afford.
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int HD>
 struct AttnSmem {
   static constexpr int LD = HD + 8;              // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B)
@@ -78,53 +86,86 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
     koff[i] = row * a.k_ld + pc * 8;
     voff[i] = row * a.v_ld + pc * 8;
   }
+  const bool full_tiles = (a.nq_patch & 63) == 0 && !ragged_k;   // no partial query / key tile anywhere
 
-  auto issue_loads = [&](int item, int kc, bf16* st) {
-    const int qb = qblocks == 1 ? 0 : item % qblocks;
-    const int it2 = qblocks == 1 ? item : item / qblocks;
-    const int hh = it2 % a.n_heads;
-    const int bb = it2 / a.n_heads;
-    const int kvb = a.kv_index ? __ldg(a.kv_index + bb) : bb;
+  // work-item cursor in mixed radix (qb, h, b): stepping by gridDim.x needs no division
+  struct Cursor { int item, qb, h, b; };
+  const int H = a.n_heads;
+  const int step_qb = (int)(gridDim.x % qblocks);
+  const int step_h = (int)((gridDim.x / qblocks) % H);
+  const int step_b = (int)(gridDim.x / qblocks / H);
+  auto advance = [&](Cursor& c) {
+    c.item += gridDim.x;
+    c.qb += step_qb;
+    if (c.qb >= qblocks) { c.qb -= qblocks; c.h += 1; }
+    c.h += step_h;
+    if (c.h >= H) { c.h -= H; c.b += 1; }
+    c.b += step_b;
+  };
+  Cursor c0;
+  c0.item = blockIdx.x;
+  c0.qb = (int)(blockIdx.x % qblocks);
+  c0.h = (int)((blockIdx.x / qblocks) % H);
+  c0.b = (int)(blockIdx.x / qblocks / H);
+
+  auto issue_loads = [&](const Cursor& c, int kc, bf16* st) {
+    const int kvb = a.kv_index ? __ldg(a.kv_index + c.b) : c.b;
     bf16* Qs = st;
     bf16* Ks = st + SM::T;
     bf16* Vs = st + 2 * SM::T;
     if (kc == 0) {
       if (!cls_only) {
-        const int q0 = qb * 64;
-        const int qrows = a.nq_patch - q0;
-        const bf16* qbase = a.q + ((size_t)bb * a.nq_patch + q0) * a.q_ld + hh * HD;
+        const int q0 = c.qb * 64;
+        const bf16* qbase = a.q + ((size_t)c.b * a.nq_patch + q0) * a.q_ld + c.h * HD;
+        if (full_tiles) {
 #pragma unroll
-        for (int i = 0; i < NLD; ++i) {
-          if (row_of[i] < 64) {
-            const bool ok = row_of[i] < qrows;
-            cp_async16(Qs + soff[i], ok ? qbase + qoff[i] : a.q, ok);
+          for (int i = 0; i < NLD; ++i)
+            if (row_of[i] < 64) cp_async16(Qs + soff[i], qbase + qoff[i], true);
+        } else {
+          const int qrows = a.nq_patch - q0;
+#pragma unroll
+          for (int i = 0; i < NLD; ++i) {
+            if (row_of[i] < 64) {
+              const bool ok = row_of[i] < qrows;
+              cp_async16(Qs + soff[i], ok ? qbase + qoff[i] : a.q, ok);
+            }
           }
         }
       }
       if (tid < 3 * PIECES) {
         const int which = tid / PIECES, pc = tid % PIECES;
         if (which == 0) {   // class-token query -> row 64 of the Q tile
-          const bool ok = a.q_has_cls && qb == 0;
+          const bool ok = a.q_has_cls && c.qb == 0;
           cp_async16(Qs + 64 * LD + pc * 8,
-                     ok ? a.q + ((size_t)a.n_seq * a.nq_patch + bb) * a.q_ld + hh * HD + pc * 8 : a.q, ok);
+                     ok ? a.q + ((size_t)a.n_seq * a.nq_patch + c.b) * a.q_ld + c.h * HD + pc * 8 : a.q, ok);
         } else {            // class-token key / value -> row 64 of the K / V tiles
           const bool ok = a.k_has_cls;
           const size_t krow = (size_t)a.n_kv_seq * a.nk_patch + kvb;
-          const bf16* src = which == 1 ? a.k + krow * a.k_ld + hh * HD + pc * 8 : a.v + krow * a.v_ld + hh * HD + pc * 8;
+          const bf16* src = which == 1 ? a.k + krow * a.k_ld + c.h * HD + pc * 8 : a.v + krow * a.v_ld + c.h * HD + pc * 8;
           cp_async16((which == 1 ? Ks : Vs) + 64 * LD + pc * 8, ok ? src : a.q, ok);
         }
       }
     }
     const int k0 = kc * 64;
-    const int krows = a.nk_patch - k0;
-    const bf16* kbase = a.k + ((size_t)kvb * a.nk_patch + k0) * a.k_ld + hh * HD;
-    const bf16* vbase = a.v + ((size_t)kvb * a.nk_patch + k0) * a.v_ld + hh * HD;
+    const bf16* kbase = a.k + ((size_t)kvb * a.nk_patch + k0) * a.k_ld + c.h * HD;
+    const bf16* vbase = a.v + ((size_t)kvb * a.nk_patch + k0) * a.v_ld + c.h * HD;
+    if (full_tiles) {
 #pragma unroll
-    for (int i = 0; i < NLD; ++i) {
-      if (row_of[i] < 64) {
-        const bool ok = row_of[i] < krows;
-        cp_async16(Ks + soff[i], ok ? kbase + koff[i] : a.k, ok);
-        cp_async16(Vs + soff[i], ok ? vbase + voff[i] : a.v, ok);
+      for (int i = 0; i < NLD; ++i) {
+        if (row_of[i] < 64) {
+          cp_async16(Ks + soff[i], kbase + koff[i], true);
+          cp_async16(Vs + soff[i], vbase + voff[i], true);
+        }
+      }
+    } else {
+      const int krows = a.nk_patch - k0;
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        if (row_of[i] < 64) {
+          const bool ok = row_of[i] < krows;
+          cp_async16(Ks + soff[i], ok ? kbase + koff[i] : a.k, ok);
+          cp_async16(Vs + soff[i], ok ? vbase + voff[i] : a.v, ok);
+        }
       }
     }
   };
@@ -135,11 +176,12 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
   float m_row[2], l_row[2];
 
   // fetch cursor runs NST-1 steps ahead of the compute cursor; exactly one commit group per step (possibly empty)
-  int f_item = blockIdx.x, f_kc = 0, f_stage = 0;
+  Cursor fc = c0;
+  int f_kc = 0, f_stage = 0;
   auto fetch_next = [&]() {
-    if (f_item < n_items) {
-      issue_loads(f_item, f_kc, smem + f_stage * SM::STAGE);
-      if (++f_kc == n_chunks) { f_kc = 0; f_item += gridDim.x; }
+    if (fc.item < n_items) {
+      issue_loads(fc, f_kc, smem + f_stage * SM::STAGE);
+      if (++f_kc == n_chunks) { f_kc = 0; advance(fc); }
     }
     cp_async_commit();
     if (++f_stage == NST) f_stage = 0;
@@ -148,14 +190,15 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
 #pragma unroll
   for (int i = 0; i < NST - 1; ++i) fetch_next();
 
-  int item = blockIdx.x, kc = 0, stage = 0;
-  while (item < n_items) {
+  Cursor cc = c0;
+  int kc = 0, stage = 0;
+  while (cc.item < n_items) {
     fetch_next();
     cp_async_wait<NST - 1>();
     __syncthreads();
 
     bf16* st = smem + stage * SM::STAGE;
-    const int qb = qblocks == 1 ? 0 : item % qblocks;
+    const int qb = cc.qb;
     const bool active = warp == 4 ? (a.q_has_cls && qb == 0) : !cls_only;
     const bf16* Qs = st;
     const bf16* Ks = st + SM::T;
@@ -226,13 +269,13 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m_row[0], mx0 * sl2), mn1 = fmaxf(m_row[1], mx1 * sl2);   // scaled (log2) units
-      const float c0 = exp2f(m_row[0] - mn0), c1 = exp2f(m_row[1] - mn1);
+      const float c0 = ex2_ftz(m_row[0] - mn0), c1 = ex2_ftz(m_row[1] - mn1);
       m_row[0] = mn0; m_row[1] = mn1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < 9; ++nt) {
-        s[nt][0] = exp2f(fmaf(s[nt][0], sl2, -mn0)); s[nt][1] = exp2f(fmaf(s[nt][1], sl2, -mn0));
-        s[nt][2] = exp2f(fmaf(s[nt][2], sl2, -mn1)); s[nt][3] = exp2f(fmaf(s[nt][3], sl2, -mn1));
+        s[nt][0] = ex2_ftz(fmaf(s[nt][0], sl2, -mn0)); s[nt][1] = ex2_ftz(fmaf(s[nt][1], sl2, -mn0));
+        s[nt][2] = ex2_ftz(fmaf(s[nt][2], sl2, -mn1)); s[nt][3] = ex2_ftz(fmaf(s[nt][3], sl2, -mn1));
         rs0 += s[nt][0] + s[nt][1];
         rs1 += s[nt][2] + s[nt][3];
       }
@@ -283,9 +326,8 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
 
       // ---- finalize the item after its last chunk ----
       if (kc == n_chunks - 1) {
-        const int it2 = qblocks == 1 ? item : item / qblocks;
-        const int h = it2 % a.n_heads;
-        const int b = it2 / a.n_heads;
+        const int h = cc.h;
+        const int b = cc.b;
         const int q0 = qb * 64;
         float l0 = l_row[0], l1 = l_row[1];
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -317,7 +359,7 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
       }
     }
     __syncthreads();  // everyone is done with this stage before a later fetch refills it
-    if (++kc == n_chunks) { kc = 0; item += gridDim.x; }
+    if (++kc == n_chunks) { kc = 0; advance(cc); }
     if (++stage == NST) stage = 0;
   }
   cp_async_wait<0>();

@@ -102,7 +102,8 @@ __device__ __forceinline__ float gelu_fast(float v) {
 template <int BN, int ACT, int KB_RES>
 __global__ void __launch_bounds__(GemmCfg<BN, KB_RES>::kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
+               int order) {
   using Cfg = GemmCfg<BN, KB_RES>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kEpiWarps = Cfg::kEpiWarps;
@@ -129,10 +130,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Tile schedule. Streaming: tile = blockIdx.x + i*gridDim.x, n fastest. Resident: the CTA owns ONE n-block
   // (blockIdx.x % n_blks) and walks the m-blocks (blockIdx.x / n_blks) + i*(gridDim.x / n_blks); the host launches a
   // grid that is a multiple of n_blks.
+  //   order 1 (streaming, large M): the CTA owns an m-block and runs its n-blocks back to back, so the activation
+  //   tile comes from HBM once and from L2 (short latency) for the remaining n-blocks, and CTAs do not miss in step.
   const int my_n = kResident ? (int)(blockIdx.x % n_blks) : 0;
   const int tile0 = kResident ? (int)(blockIdx.x / n_blks) : (int)blockIdx.x;
   const int tile_step = kResident ? (int)(gridDim.x / n_blks) : (int)gridDim.x;
-  const int num_tiles = kResident ? m_blks : m_blks * n_blks;
+  auto coords = [&](int it, int& m_blk, int& n_blk) -> bool {
+    if (kResident) {
+      m_blk = tile0 + it * tile_step;
+      n_blk = my_n;
+      return m_blk < m_blks;
+    }
+    if (order == 1) {
+      m_blk = (int)blockIdx.x + (it / n_blks) * (int)gridDim.x;
+      n_blk = it % n_blks;
+      return m_blk < m_blks;
+    }
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    m_blk = tile / n_blks;
+    n_blk = tile % n_blks;
+    return tile < m_blks * n_blks;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -162,13 +180,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      if (kResident && tile0 < num_tiles) {
+      if (kResident && tile0 < m_blks) {
         mbar_arrive_expect_tx(pfull, (uint32_t)num_kb * Cfg::B_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(&tmB, pfull, sPanel + kb * Cfg::B_BYTES, kb * BK, my_n * BN);
       }
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = kResident ? tile : tile / n_blks;
-        const int n_blk = kResident ? my_n : tile % n_blks;
+      int m_blk, n_blk;
+      for (int it = 0; coords(it, m_blk, n_blk); ++it) {
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1, 10);
           uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
@@ -184,8 +201,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      if (kResident && tile0 < num_tiles) mbar_wait(pfull, 0, 22);
-      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      if (kResident && tile0 < m_blks) mbar_wait(pfull, 0, 22);
+      int m_blk, n_blk;
+      for (int it = 0; coords(it, m_blk, n_blk); ++it) {
         mbar_wait(&tempty[as], aphase ^ 1, 20);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -216,9 +234,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* rowp = my_stage + lane * 128;
     uint32_t as = 0, aphase = 0;
     bool store_pending = false;
-    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = kResident ? tile : tile / n_blks;
-      const int n_blk = kResident ? my_n : tile % n_blks;
+    int m_blk, n_blk;
+    for (int it = 0; coords(it, m_blk, n_blk); ++it) {
       const int n0 = n_blk * BN + sl * 64;
       mbar_wait(&tfull[as], aphase, 30);
       tc_fence_after();
@@ -291,6 +308,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+static int g_order = 1;     // VITED_GEMM_ORDER=0 forces the n-fastest strided tile order (tuning knob)
+
 template <int BN, int ACT, int KB_RES>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                      int N, int K, cudaStream_t stream) {
@@ -302,7 +321,7 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
     attr_set = true;
   }
   const int m_blks = (M + BM - 1) / BM, n_blks = (N + BN - 1) / BN;
-  int grid;
+  int grid, order = 0;
   if (KB_RES > 0) {
     int per_n = g_num_sms / n_blks;   // CTAs per weight panel
     if (per_n > m_blks) per_n = m_blks;
@@ -310,8 +329,9 @@ static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtenso
   } else {
     const int tiles = m_blks * n_blks;
     grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (g_order != 0 && n_blks > 1 && m_blks >= 4 * g_num_sms) order = 1;
   }
-  gemm_tc_kernel<BN, ACT, KB_RES><<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
+  gemm_tc_kernel<BN, ACT, KB_RES><<<grid, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K, order);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -327,7 +347,7 @@ int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
               cudaStream_t stream);
 
 static int g_block_n = 0;   // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic tile width (tuning knob)
-static int g_resident = -1; // VITED_GEMM_RESIDENT=0 disables the resident-weights variant (tuning knob)
+static int g_resident = -1; // VITED_GEMM_RESIDENT=1 enables the resident-weights variant (measured slower: off by default)
 
 int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream) {
@@ -344,7 +364,9 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
     const char* e = getenv("VITED_GEMM_BN");
     g_block_n = e ? atoi(e) : -1;
     const char* r = getenv("VITED_GEMM_RESIDENT");
-    g_resident = r ? atoi(r) : 1;
+    g_resident = r ? atoi(r) : 0;
+    const char* o = getenv("VITED_GEMM_ORDER");
+    g_order = o ? atoi(o) : 1;
   }
   const int m_blks = (M + BM - 1) / BM;
   // resident weights: K <= 384, 128-wide panels, and enough m-blocks per panel to amortise loading it

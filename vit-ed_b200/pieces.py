@@ -64,3 +64,15 @@ def piece_to_tensor(lab_piece, img_size):
 def pieces_to_batch(lab_pieces, img_size):
     """[N,3,S,S] fp32 (CPU); upload once with .cuda()."""
     return torch.stack([piece_to_tensor(p, img_size) for p in lab_pieces], dim=0)
+
+
+def fragment_to_tensor(pil_image, img_size=512):
+    """Hisfrag20 test-time prep: CenterCrop(img_size) -> ToTensor -> Normalize(.5, .5), the
+    transform of hisfrag.py:89-93 applied by HisFrag20Test.__getitem__ (hisfrag_dataset.py:181-191)."""
+    from torchvision import transforms
+    tf = transforms.Compose([
+        transforms.CenterCrop(img_size),
+        transforms.ToTensor(),
+        transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+    ])
+    return tf(pil_image)
