@@ -227,6 +227,10 @@ def workload_config(n_gpus):
 def run_ours(args):
     import vited_b200
     from vited_b200 import grid
+    # stdout carries exactly ONE JSON line: anything libraries print meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dist_setup(args.gpus)
     dev = torch.device('cuda', local if world > 1 else 0)
     peaks = load_peaks()
@@ -346,7 +350,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             rate, cores, sample, _ = cpu_reference_rate(budget_s=20.0, steps=1, warmup=0)
             line['cpu_baseline'] = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

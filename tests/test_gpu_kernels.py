@@ -88,6 +88,32 @@ def test_gemm_tile_shapes_agree(bn, monkeypatch):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+def test_gemm_cta_pair_variant():
+    """The cta_group::2 (CTA-pair) variant of the tcgen05 kernel against torch (subprocess: env knob read once)."""
+    import subprocess, sys, os
+    from tests.conftest import ROOT
+    code = (
+        "import torch, math, sys; sys.path.insert(0, %r)\n"
+        "from vited_b200 import _lib as L\n"
+        "g = torch.Generator(device='cuda').manual_seed(1)\n"
+        "for (M, N, K, act) in [(40000, 1536, 384, 1), (40001, 384, 1536, 0), (38001, 1152, 384, 0), (40000, 384, 384, 0), (39990, 768, 384, 0)]:\n"
+        "    A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
+        "    b = torch.randn(N, device='cuda', generator=g); C = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')\n"
+        "    st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, act, 0, None)\n"
+        "    torch.cuda.synchronize(); assert st == 0, L.last_error()\n"
+        "    ref = A.float() @ W.float().t() + b\n"
+        "    ref = torch.nn.functional.gelu(ref) if act else ref\n"
+        "    assert torch.isfinite(C.float()).all(), ('nan', M, N, K)\n"
+        "    err = (C.float() - ref).abs(); tol = 1e-2 * ref.abs() + 2e-2\n"
+        "    bad = err > tol\n"
+        "    assert not bad.any(), (M, N, K, int(bad.sum()), float(err.max()), bad.nonzero()[0].tolist())\n"
+        "    print('ok', M, N, K, float(err.max()))\n"
+    ) % ROOT
+    env = dict(os.environ, VITED_GEMM_PAIR='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize('D', [384, 768, 32, 96])
 @pytest.mark.parametrize('has_cls', [0, 1])
 def test_resid_ln(D, has_cls):

@@ -83,20 +83,62 @@ struct GemmCfg {
   static_assert(kStages >= 3, "not enough shared memory for the pipeline");
 };
 
-// exact-erf GELU evaluated with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7) on the MUFU approximations
-// rcp.approx / ex2.approx (2^-22 relative): the total error stays ~1e-6, far below the bf16 rounding of the result.
-//   gelu(v) = max(v, 0) - 0.5*|v|*poly(t)*exp(-v^2/2),  t = 1/(1 + p*|v|/sqrt(2)).   ~13 FP32 ops + 2 MUFU.
+// exact-erf GELU with ONE MUFU op: gelu(v) = max(v, 0) - 0.5*|v|*erfc(|v|/sqrt(2)), and erfc(a/sqrt(2)) = 2^(-Q(a)) with a
+// degree-5 polynomial Q fitted (minimax on [0, 9], monotone beyond) so that the GELU value is within 6e-7 of the erf
+// definition everywhere -- four orders of magnitude below the bf16 rounding of the result. 8 FP32 ops + ex2.approx.
+// (fit: tools/fit_gelu.py; the GELU epilogue is MUFU/issue bound, so the rcp of the classic A&S 7.1.26 form matters.)
 __device__ __forceinline__ float gelu_fast(float v) {
   const float a = fabsf(v);
-  float t, ex;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(a, 0.3275911f * 0.70710678118654752440f, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(a * a * -0.72134752044448170368f));  // exp(-a^2 / 2)
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  p *= t * a;
-  return fmaf(-0.5f * p, ex, fmaxf(v, 0.0f));
+  float q = fmaf(a, -0.000487278765f, 0.00719261523f);
+  q = fmaf(a, q, -0.0521311556f);
+  q = fmaf(a, q, -0.459611519f);
+  q = fmaf(a, q, -1.15099531f);
+  q *= a;                                   // -Q(|v|)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-0.5f * a, e, fmaxf(v, 0.0f));
+}
+
+// bias (+ GELU) on one thread's 64 accumulator columns, packed to bf16 and written into the warp's 32x128-byte staging
+// box in the 128B-swizzle pattern the TMA store expects (16-byte chunk c of row r lives at chunk c ^ (r & 7)).
+template <int ACT>
+__device__ __forceinline__ void epilogue_tile(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
+                                              const float* __restrict__ bias, int n0, int N, uint8_t* rowp, int lane) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const uint32_t* v = ch == 0 ? v0 : v1;
+    const int nc = n0 + ch * 32;
+    float f[32];
+    if (nc + 32 <= N) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nc) + i);
+        f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float b = (nc + i < N) ? __ldg(bias + nc + i) : 0.f;
+        f[i] = __uint_as_float(v[i]) + b;
+      }
+    }
+    if (ACT == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 pk;
+      pk.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
+      pk.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
+      pk.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
+      pk.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+      *reinterpret_cast<uint4*>(rowp + (((ch * 4 + i) ^ (lane & 7)) << 4)) = pk;
+    }
+  }
 }
 
 template <int BN, int ACT, int KB_RES>
@@ -253,41 +295,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
       }
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        const uint32_t* v = ch == 0 ? v0 : v1;
-        const int nc = n0 + ch * 32;
-        float f[32];
-        if (nc + 32 <= N) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nc) + i);
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float b = (nc + i < N) ? __ldg(bias + nc + i) : 0.f;
-            f[i] = __uint_as_float(v[i]) + b;
-          }
-        }
-        if (ACT == ACT_GELU) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = gelu_fast(f[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 pk;
-          pk.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-          pk.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-          pk.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-          pk.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-          *reinterpret_cast<uint4*>(rowp + (((ch * 4 + i) ^ (lane & 7)) << 4)) = pk;
-        }
-      }
+      epilogue_tile<ACT>(v0, v1, bias, n0, N, rowp, lane);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0 && n0 < N) {
@@ -308,7 +316,188 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-static int g_order = 1;     // VITED_GEMM_ORDER=0 forces the n-fastest strided tile order (tuning knob)
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster compute one 256 x BN tile. Each CTA streams its own 128
+// activation rows and HALF of the weight tile; tcgen05.mma.cta_group::2 (issued by the leader CTA) reads both halves,
+// so the weight bytes every SM has to pull through its TMA ring and shared memory are halved. With K = 384 the ring
+// (bytes in flight per SM) is what limits the single-CTA kernel (profiles/: tensor pipe ~60 %, nothing saturated).
+// =====================================================================================================================
+template <int BN>
+struct PairCfg {
+  static constexpr int kEpiWarps = 4 * (BN / 64);
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t BH_BYTES = (BN / 2) * BK * 2;     // this CTA's half of the weight tile
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + BH_BYTES;
+  static constexpr uint32_t C_BYTES = kEpiWarps * 4096;
+  static constexpr int kStagesMax = (232448 - 1024 - 256 - (int)C_BYTES) / (int)STAGE_BYTES;
+  static constexpr int kStages = kStagesMax > 8 ? 8 : kStagesMax;
+  static constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr uint32_t SMEM_BYTES = 1024 + kStages * STAGE_BYTES + C_BYTES + 256;
+  static_assert(BN % 64 == 0 && BN <= 256 && (BN / 2) % 8 == 0, "bad BN");
+  static_assert(kStages >= 3, "not enough shared memory for the pipeline");
+};
+
+template <int BN, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PairCfg<BN>::kThreads, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  using Cfg = PairCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiWarps = Cfg::kEpiWarps;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = smem + kStages * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + Cfg::C_BYTES);
+  uint64_t* full = bars;                     // used in the leader CTA only (both CTAs' TMA bytes land on it)
+  uint64_t* empty = bars + kStages;          // per CTA, released by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * kStages;      // per CTA, multicast commit
+  uint64_t* tempty = bars + 2 * kStages + 2; // leader CTA only: epilogue warps of BOTH CTAs arrive
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1);
+  const int num_pairs = (int)(gridDim.x >> 1);
+
+  const int m2_blks = (M + 2 * BM - 1) / (2 * BM);
+  const int n_blks = (N + BN - 1) / BN;
+  const int num_tiles = m2_blks * n_blks;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc_2cta(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m2 = tile / n_blks, n_blk = tile % n_blks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 10);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(&tmA, &full[stage], a_dst, kb * BK, m2 * 2 * BM + (int)rank * BM);
+          tma_load_2d_2cta(&tmB, &full[stage], a_dst + Cfg::A_BYTES, kb * BK, n_blk * BN + (int)rank * (BN / 2));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty[as], aphase ^ 1, 20);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 21);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty[stage]);   // frees this stage in BOTH CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tfull[as]);        // accumulators complete in BOTH CTAs
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int sl = ew >> 2;
+    uint8_t* my_stage = sC + ew * 4096;
+    uint8_t* rowp = my_stage + lane * 128;
+    uint32_t as = 0, aphase = 0;
+    bool store_pending = false;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m2 = tile / n_blks, n_blk = tile % n_blks;
+      const int n0 = n_blk * BN + sl * 64;
+      mbar_wait(&tfull[as], aphase, 30);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + as * BN + sl * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      tmem_ld_32x32b_x32(taddr, v0);
+      tmem_ld_32x32b_x32(taddr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[as]);
+      if (store_pending) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      epilogue_tile<ACT>(v0, v1, bias, n0, N, rowp, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && n0 < N) {
+        tma_store_2d(&tmC, my_stage, n0, m2 * 2 * BM + (int)rank * BM + q * 32);
+        tma_store_commit();
+      }
+      store_pending = true;
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA may leave (or free TMEM) while the other can still touch its barriers / smem
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int ACT>
+static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
+                       int N, int K, cudaStream_t stream) {
+  using Cfg = PairCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  int pairs = g_num_sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  gemm_tc_pair_kernel<BN, ACT><<<2 * pairs, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int g_order = 0;     // VITED_GEMM_ORDER=1: every CTA owns an m-block (measured ~4 % slower: off by default)
 
 template <int BN, int ACT, int KB_RES>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
@@ -347,6 +536,7 @@ int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
               cudaStream_t stream);
 
 static int g_block_n = 0;   // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic tile width (tuning knob)
+static int g_pair = -1;     // VITED_GEMM_PAIR=0 disables the CTA-pair (cta_group::2) kernel (used for large M by default)
 static int g_resident = -1; // VITED_GEMM_RESIDENT=1 enables the resident-weights variant (measured slower: off by default)
 
 int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
@@ -366,7 +556,9 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
     const char* r = getenv("VITED_GEMM_RESIDENT");
     g_resident = r ? atoi(r) : 0;
     const char* o = getenv("VITED_GEMM_ORDER");
-    g_order = o ? atoi(o) : 1;
+    g_order = o ? atoi(o) : 0;
+    const char* pr = getenv("VITED_GEMM_PAIR");
+    g_pair = pr ? atoi(pr) : 1;
   }
   const int m_blks = (M + BM - 1) / BM;
   // resident weights: K <= 384, 128-wide panels, and enough m-blocks per panel to amortise loading it
@@ -380,6 +572,16 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
   }
   CUtensorMap tA, tB, tC;
   if (make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, BM)) return 1;
+  if (g_pair && g_block_n != 128 && m_blks >= 2 * g_num_sms && (N % 256 == 0 || N % 192 == 0)) {
+    const int pbn = (g_block_n == 192 || g_block_n == 256) ? g_block_n : (N % 256 == 0 ? 256 : 192);
+    if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)pbn / 2)) return 1;
+    if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
+    if (pbn == 256)
+      return act == ACT_GELU ? launch_pair<256, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                             : launch_pair<256, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+    return act == ACT_GELU ? launch_pair<192, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                           : launch_pair<192, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+  }
   if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)bn)) return 1;
   if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
   if (resident) return launch_act<128, 6>(tA, tB, tC, bias, M, N, K, act, stream);
