@@ -84,6 +84,17 @@ def test_piece_preparation_bit_exact_with_reference():
         pieces.grid_geometry(10, 10, 64)
 
 
+def test_fragment_prep_matches_reference_transform():
+    """hisfrag.py:89-93 test transform = CenterCrop(512) -> ToTensor -> Normalize(.5,.5) on a PIL image."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    img = Image.fromarray(rng.integers(0, 256, size=(600, 700, 3), dtype=np.uint8))
+    t = pieces.fragment_to_tensor(img, 512)
+    arr = np.asarray(img)[44:556, 94:606].astype(np.float32) / 255.0          # centre crop offsets (600-512)/2, (700-512)/2
+    want = (torch.from_numpy(arr).permute(2, 0, 1) - 0.5) / 0.5
+    assert t.shape == (3, 512, 512) and torch.equal(t, want)
+
+
 def test_consumer_layouts():
     from oracle import vited_oracle as orc
 
