@@ -321,7 +321,9 @@ def run_ours(args):
         'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05/TMEM/TMA, all Linear layers)',
         'achieved': achieved, 'peak': peaks['tf_sustained'], 'unit': 'TFLOP/s', 'frac': achieved / peaks['tf_sustained'],
         'peak_source': peaks['source'] + ', sustained figure (kernel timed inside a long step)',
-        'traffic': None,
+        # dram__bytes_read+write per launch from the ncu --set full capture of the same kernels (profiles/
+        # r01_ncu_full_v6_raw.csv), launch-weighted over the four GEMM shapes of a layer; algorithmic bytes 0.671e9
+        'traffic': 0.629e9 if world == 1 else None,
         'launches_per_step': g_n, 'avg_launch_ms': g_ms / max(g_n, 1), 'flops_per_launch': g_fl / max(g_n, 1),
         'share_of_step': g_ms / total_ms,
         'classes': {k: {'ms': round(v['ms'], 3), 'share': round(v['ms'] / total_ms, 4),
@@ -334,6 +336,10 @@ def run_ours(args):
     n_ctx = sum(b - a for a, b in row_ranges)
     f_step = n_pairs_rank * F_DEC_PAIR + n_items_total * F_PREP_ITEM + n_ctx * (F_ENC_ITEM + F_KV_ITEM)
     step_frac = f_step / (ms_step / 1e3) / 1e12 / peaks['tf_sustained']
+    # FLOPs actually launched (layer-0 self-attention runs once per item, the last layer runs on class-token rows
+    # only): sum of the per-launch algorithmic flops the engine attached to the profiled step
+    f_exec = sum(v['flops'] for v in prof.values())
+    step_frac_exec = f_exec / (ms_step / 1e3) / 1e12 / peaks['tf_sustained']
 
     if rank == 0:
         line = {
@@ -346,6 +352,10 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'roofline': roofline,
             'step_tensor_frac': step_frac,
+            'step_tensor_frac_executed': step_frac_exec,
+            'flops_note': 'step_tensor_frac uses SURVEY 8d nominal work (2.250 GFLOP/pair, all 8 decoder layers on all 65 '
+                          'rows); _executed counts only launched flops (layer-0 self-attention cached per item, last '
+                          'layer pruned to the class-token row)',
         }
         if world == 1 and not args.no_cpu:
             rate, cores, sample, _ = cpu_reference_rate(budget_s=20.0, steps=1, warmup=0)
