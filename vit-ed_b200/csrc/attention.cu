@@ -1,11 +1,10 @@
 // Self- and cross-attention for the ViT-ED blocks (reference: models/vision_transformer.py:56-80 Attention.forward,
 // :174-200 CrossAttention.forward; SDPA default scale head_dim^-0.5, no mask, no dropout at eval).
 //
-// Flash-style: one CTA = 64 patch queries of one (sequence, head); K/V stream through shared memory in 64-key
-// chunks; softmax statistics stay in registers and are combined with warp shuffles. The class token is never
-// padded into a 16-row MMA tile: as a KEY it seeds the online-softmax state (m = q.k_cls, l = 1, O = v_cls),
-// as a QUERY it is handled by a fifth warp with plain FMAs. That keeps the 64-token puzzle sequences exactly
-// one MMA tile wide instead of two half-empty ones.
+// Flash-style: persistent CTAs, one work item = 64 patch queries of one (sequence, head); Q/K/V tiles arrive by TMA
+// (hardware-swizzled boxes, mbarrier ring), softmax statistics stay in registers and are combined with quad shuffles.
+// The class token never costs a second 64-row tile: as a query it is row 64 of the Q tile (fifth warp), as a key it
+// is a ninth 8-key MMA tile.
 //
 // Token rows live in the "split" layout: n_seq*n_patch patch rows, then n_seq cls rows.
 #include "kernels.h"
@@ -13,15 +12,6 @@
 namespace vited {
 
 constexpr float kLog2e = 1.4426950408889634f;
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
-  const int sz = valid ? 16 : 0;  // src-size 0 => 16 bytes of zeros, nothing read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 2^x on the MUFU unit, flush-to-zero (inputs are <= 0 or -inf here); plain exp2f() adds a denormal-range fix-up
 // (3-4 extra instructions per element) that this instruction-bound kernel cannot afford.
@@ -33,32 +23,43 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 
 template <int HD>
 struct AttnSmem {
-  static constexpr int LD = HD + 8;              // padded smem row (elements): conflict-free ldmatrix (80 B / 144 B)
+  static constexpr int RB = HD * 2;              // bytes per tile row (dense; TMA-swizzled 64B / 128B)
   static constexpr int ROWS = 80;                // 64 patch rows + the class-token row (64) + 15 zero rows
-  static constexpr int T = ROWS * LD;            // one tile (elements)
-  static constexpr int STAGE = 3 * T;            // Q, K, V tiles
-  static constexpr int NST = HD == 32 ? 3 : 2;   // cp.async ring depth
-  static constexpr int BYTES = (NST * STAGE + T) * 2;  // ring + output staging
+  static constexpr int TB = ROWS * RB;           // one tile in bytes (5120 / 10240: a multiple of 1024)
+  static constexpr int STAGE = 3 * TB;           // Q, K, V tiles
+  static constexpr int NST = 3;                  // TMA ring depth
+  static constexpr int OLD = HD + 8;             // padded row (elements) of the per-warp output staging
+  static constexpr int OB = ROWS * OLD * 2;
+  static constexpr int BYTES = 1024 + NST * STAGE + OB + 64;
 };
 
-// Persistent, software-pipelined flash attention for one (sequence, head, 64-query block) per step and 64-key chunk:
-// the loads of step s+NST-1 are in flight (cp.async ring) while step s is computed.
+struct AttnMaps {
+  CUtensorMap q_tile, q_row, k_tile, k_row, v_tile, v_row;   // boxes {HD, 64} and {HD, 1}
+};
+
+// Persistent flash attention for (sequence, head, 64-query block) work items and 64-key chunks, fed by TMA.
+//  * One thread (lane 0 of warp 4) keeps a 3-deep ring of TMA box loads in flight: the 64x{32|64} Q / K / V tiles of
+//    the step two ahead land in hardware-swizzled shared memory and complete on an mbarrier, so the five compute warps
+//    execute no address arithmetic or copy instructions at all (the cp.async version spent 40 % of its issue slots
+//    there; profiles/README.md).
 //  * Five identical MMA warps: warps 0-3 own 16 patch queries each; warp 4 owns a 16-row tile whose row 0 is the
-//    class-token query (rows 1-15 zero), so the class token rides the same tensor-core path.
+//    class-token query (row 64 of the Q tile, rows 65-79 are zeros).
 //  * The class-token KEY/VALUE sit in row 64 of the K/V tiles and are consumed as a ninth 8-key MMA tile (first
 //    chunk only), so 65-token sequences cost 9/8 of a 64-token one instead of 2x.
 //  * cls_only: only warp 4 computes (last decoder layer: only row 0 of each sequence reaches the head).
-// The kernel is instruction-issue bound (64x64x32 tiles), so per-step address arithmetic is hoisted out of the loop.
 template <int HD>
-__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, int cls_only) {
+__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, const __grid_constant__ AttnMaps maps, int n_items,
+                                                       int cls_only) {
   using SM = AttnSmem<HD>;
-  constexpr int LD = SM::LD;
+  constexpr int RB = SM::RB;
   constexpr int NST = SM::NST;
-  constexpr int PIECES = HD / 8;                      // 16-byte pieces per head row
-  constexpr int NLD = (64 * PIECES + 159) / 160;      // tile pieces per thread
-  extern __shared__ __align__(16) uint8_t attn_smem_raw[];
-  bf16* smem = reinterpret_cast<bf16*>(attn_smem_raw);
-  bf16* sO = smem + NST * SM::STAGE;
+  constexpr int OLD = SM::OLD;
+  constexpr int PIECES = HD / 8;
+  extern __shared__ uint8_t attn_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
+  bf16* sO = reinterpret_cast<bf16*>(smem + NST * SM::STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * SM::STAGE + SM::OB);
+  uint64_t* empty = full + NST;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qblocks = cls_only ? 1 : (a.nq_patch + 63) / 64;
@@ -67,26 +68,25 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
   const float sl2 = a.scale * kLog2e;
   const int g = lane >> 2, t = lane & 3;
   const int mi = lane >> 3, ri = lane & 7;
+  const int sw = HD == 32 ? ((ri >> 1) & 3) : ri;   // swizzle term of this lane's ldmatrix rows (row % 8 == ri)
 
-  // rows 65..79 of every tile are never loaded: zero them once (they multiply into the MMAs as exact zeros)
-  for (int i = tid; i < NST * 3 * 15 * LD; i += 160) {
-    const int tile = i / (15 * LD), r = i % (15 * LD);
-    smem[tile * SM::T + 65 * LD + r] = __float2bfloat16(0.f);
+  // rows 65..79 of every tile are never loaded: zero them once (they enter the MMAs as exact zeros)
+  for (int i = tid; i < NST * 3 * (15 * RB / 16); i += 160) {
+    const int tile = i / (15 * RB / 16), r = i % (15 * RB / 16);
+    *reinterpret_cast<uint4*>(smem + tile * SM::TB + 65 * RB + r * 16) = make_uint4(0, 0, 0, 0);
   }
-
-  // per-thread load slots: (row, 16-byte piece) pairs are the same every step
-  int row_of[NLD], soff[NLD], qoff[NLD], koff[NLD], voff[NLD];
-#pragma unroll
-  for (int i = 0; i < NLD; ++i) {
-    const int idx = tid + i * 160;
-    const int row = idx / PIECES, pc = idx % PIECES;
-    row_of[i] = idx < 64 * PIECES ? row : 1 << 20;    // out-of-range slots never pass the row test
-    soff[i] = row * LD + pc * 8;
-    qoff[i] = row * a.q_ld + pc * 8;
-    koff[i] = row * a.k_ld + pc * 8;
-    voff[i] = row * a.v_ld + pc * 8;
+  if (tid == 0) {
+    for (int s2 = 0; s2 < NST; ++s2) {
+      mbar_init(&full[s2], 1);
+      mbar_init(&empty[s2], 5);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.q_tile);
+    tma_prefetch_desc(&maps.k_tile);
+    tma_prefetch_desc(&maps.v_tile);
   }
-  const bool full_tiles = (a.nq_patch & 63) == 0 && !ragged_k;   // no partial query / key tile anywhere
+  fence_proxy_async_smem();   // the generic-proxy zero fill is ordered before later async-proxy (TMA) writes nearby
+  __syncthreads();
 
   // work-item cursor in mixed radix (qb, h, b): stepping by gridDim.x needs no division
   struct Cursor { int item, qb, h, b; };
@@ -102,115 +102,74 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
     if (c.h >= H) { c.h -= H; c.b += 1; }
     c.b += step_b;
   };
-  Cursor c0;
-  c0.item = blockIdx.x;
-  c0.qb = (int)(blockIdx.x % qblocks);
-  c0.h = (int)((blockIdx.x / qblocks) % H);
-  c0.b = (int)(blockIdx.x / qblocks / H);
+  Cursor cc;
+  cc.item = blockIdx.x;
+  cc.qb = (int)(blockIdx.x % qblocks);
+  cc.h = (int)((blockIdx.x / qblocks) % H);
+  cc.b = (int)(blockIdx.x / qblocks / H);
 
-  auto issue_loads = [&](const Cursor& c, int kc, bf16* st) {
-    const int kvb = a.kv_index ? __ldg(a.kv_index + c.b) : c.b;
-    bf16* Qs = st;
-    bf16* Ks = st + SM::T;
-    bf16* Vs = st + 2 * SM::T;
-    if (kc == 0) {
-      if (!cls_only) {
-        const int q0 = c.qb * 64;
-        const bf16* qbase = a.q + ((size_t)c.b * a.nq_patch + q0) * a.q_ld + c.h * HD;
-        if (full_tiles) {
-#pragma unroll
-          for (int i = 0; i < NLD; ++i)
-            if (row_of[i] < 64) cp_async16(Qs + soff[i], qbase + qoff[i], true);
-        } else {
-          const int qrows = a.nq_patch - q0;
-#pragma unroll
-          for (int i = 0; i < NLD; ++i) {
-            if (row_of[i] < 64) {
-              const bool ok = row_of[i] < qrows;
-              cp_async16(Qs + soff[i], ok ? qbase + qoff[i] : a.q, ok);
-            }
-          }
-        }
-      }
-      if (tid < 3 * PIECES) {
-        const int which = tid / PIECES, pc = tid % PIECES;
-        if (which == 0) {   // class-token query -> row 64 of the Q tile
-          const bool ok = a.q_has_cls && c.qb == 0;
-          cp_async16(Qs + 64 * LD + pc * 8,
-                     ok ? a.q + ((size_t)a.n_seq * a.nq_patch + c.b) * a.q_ld + c.h * HD + pc * 8 : a.q, ok);
-        } else {            // class-token key / value -> row 64 of the K / V tiles
-          const bool ok = a.k_has_cls;
-          const size_t krow = (size_t)a.n_kv_seq * a.nk_patch + kvb;
-          const bf16* src = which == 1 ? a.k + krow * a.k_ld + c.h * HD + pc * 8 : a.v + krow * a.v_ld + c.h * HD + pc * 8;
-          cp_async16((which == 1 ? Ks : Vs) + 64 * LD + pc * 8, ok ? src : a.q, ok);
-        }
+  // ---- producer state (used by lane 0 of warp 4 only) ----
+  Cursor fc = cc;
+  int f_kc = 0, f_stage = 0;
+  uint32_t f_phase = 0;
+  auto produce = [&]() {     // issue the TMA loads of the next not-yet-fetched step (if any)
+    if (fc.item >= n_items) return;
+    mbar_wait(&empty[f_stage], f_phase ^ 1, 40);
+    uint8_t* st = smem + f_stage * SM::STAGE;
+    const int kvb = a.kv_index ? __ldg(a.kv_index + fc.b) : fc.b;
+    const int col = fc.h * HD;
+    uint32_t bytes = 2 * 64 * RB;
+    if (f_kc == 0) {
+      if (!cls_only) bytes += 64 * RB;
+      if (a.q_has_cls && fc.qb == 0) bytes += RB;
+      if (a.k_has_cls) bytes += 2 * RB;
+    }
+    mbar_arrive_expect_tx(&full[f_stage], bytes);
+    if (f_kc == 0) {
+      if (!cls_only) tma_load_2d(&maps.q_tile, &full[f_stage], st, col, fc.b * a.nq_patch + fc.qb * 64);
+      if (a.q_has_cls && fc.qb == 0)
+        tma_load_2d(&maps.q_row, &full[f_stage], st + 64 * RB, col, a.n_seq * a.nq_patch + fc.b);
+      if (a.k_has_cls) {
+        tma_load_2d(&maps.k_row, &full[f_stage], st + SM::TB + 64 * RB, col, a.n_kv_seq * a.nk_patch + kvb);
+        tma_load_2d(&maps.v_row, &full[f_stage], st + 2 * SM::TB + 64 * RB, col, a.n_kv_seq * a.nk_patch + kvb);
       }
     }
-    const int k0 = kc * 64;
-    const bf16* kbase = a.k + ((size_t)kvb * a.nk_patch + k0) * a.k_ld + c.h * HD;
-    const bf16* vbase = a.v + ((size_t)kvb * a.nk_patch + k0) * a.v_ld + c.h * HD;
-    if (full_tiles) {
-#pragma unroll
-      for (int i = 0; i < NLD; ++i) {
-        if (row_of[i] < 64) {
-          cp_async16(Ks + soff[i], kbase + koff[i], true);
-          cp_async16(Vs + soff[i], vbase + voff[i], true);
-        }
-      }
-    } else {
-      const int krows = a.nk_patch - k0;
-#pragma unroll
-      for (int i = 0; i < NLD; ++i) {
-        if (row_of[i] < 64) {
-          const bool ok = row_of[i] < krows;
-          cp_async16(Ks + soff[i], ok ? kbase + koff[i] : a.k, ok);
-          cp_async16(Vs + soff[i], ok ? vbase + voff[i] : a.v, ok);
-        }
-      }
-    }
+    tma_load_2d(&maps.k_tile, &full[f_stage], st + SM::TB, col, kvb * a.nk_patch + f_kc * 64);
+    tma_load_2d(&maps.v_tile, &full[f_stage], st + 2 * SM::TB, col, kvb * a.nk_patch + f_kc * 64);
+    if (++f_kc == n_chunks) { f_kc = 0; advance(fc); }
+    if (++f_stage == NST) { f_stage = 0; f_phase ^= 1; }
   };
+  const bool is_producer = (warp == 4 && lane == 0);
+  if (is_producer) {
+#pragma unroll
+    for (int i = 0; i < NST - 1; ++i) produce();
+  }
 
   // ---- per-warp state (lives across the chunks of one item) ----
   uint32_t qf[HD / 16][4];
   float o_acc[HD / 8][4];
   float m_row[2], l_row[2];
 
-  // fetch cursor runs NST-1 steps ahead of the compute cursor; exactly one commit group per step (possibly empty)
-  Cursor fc = c0;
-  int f_kc = 0, f_stage = 0;
-  auto fetch_next = [&]() {
-    if (fc.item < n_items) {
-      issue_loads(fc, f_kc, smem + f_stage * SM::STAGE);
-      if (++f_kc == n_chunks) { f_kc = 0; advance(fc); }
-    }
-    cp_async_commit();
-    if (++f_stage == NST) f_stage = 0;
-  };
-  __syncthreads();  // zero rows visible before any ldmatrix
-#pragma unroll
-  for (int i = 0; i < NST - 1; ++i) fetch_next();
-
-  Cursor cc = c0;
   int kc = 0, stage = 0;
+  uint32_t phase = 0;
   while (cc.item < n_items) {
-    fetch_next();
-    cp_async_wait<NST - 1>();
-    __syncthreads();
+    if (is_producer) produce();
+    __syncwarp();
+    mbar_wait(&full[stage], phase, 41);
 
-    bf16* st = smem + stage * SM::STAGE;
+    const uint32_t sQ = smem_u32(smem + stage * SM::STAGE);
+    const uint32_t sK = sQ + SM::TB;
+    const uint32_t sV = sQ + 2 * SM::TB;
     const int qb = cc.qb;
     const bool active = warp == 4 ? (a.q_has_cls && qb == 0) : !cls_only;
-    const bf16* Qs = st;
-    const bf16* Ks = st + SM::T;
-    const bf16* Vs = st + 2 * SM::T;
 
     if (active) {
       if (kc == 0) {
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           const int row = warp * 16 + (mi & 1) * 8 + ri;
-          const int col = ks * 16 + (mi >> 1) * 8;
-          ldsm_x4(smem_u32(&Qs[row * LD + col]), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+          const int c16 = ks * 2 + (mi >> 1);
+          ldsm_x4(sQ + row * RB + ((c16 ^ sw) << 4), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
         }
         m_row[0] = m_row[1] = -INFINITY;
         l_row[0] = l_row[1] = 0.f;
@@ -228,9 +187,9 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           const int key = np * 16 + (mi >> 1) * 8 + ri;
-          const int dim = ks * 16 + (mi & 1) * 8;
+          const int c16 = ks * 2 + (mi & 1);
           uint32_t b0, b1, b2, b3;
-          ldsm_x4(smem_u32(&Ks[key * LD + dim]), b0, b1, b2, b3);
+          ldsm_x4(sK + key * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
           mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
           mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
         }
@@ -239,10 +198,9 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ks += 2) {
           // one ldmatrix.x4 = the (keys 64..71) B fragments of two k-steps
-          const int key = 64 + ri;
-          const int dim = ks * 16 + mi * 8;
+          const int c16 = ks * 2 + mi;
           uint32_t b0, b1, b2, b3;
-          ldsm_x4(smem_u32(&Ks[key * LD + dim]), b0, b1, b2, b3);
+          ldsm_x4(sK + (64 + ri) * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
           mma_bf16_16816(s[8], qf[ks], b0, b1);
           mma_bf16_16816(s[8], qf[ks + 1], b2, b3);
         }
@@ -299,9 +257,9 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
 #pragma unroll
         for (int dp = 0; dp < HD / 16; ++dp) {
           const int key = k2 * 16 + (mi & 1) * 8 + ri;
-          const int dim = dp * 16 + (mi >> 1) * 8;
+          const int c16 = dp * 2 + (mi >> 1);
           uint32_t b0, b1, b2, b3;
-          ldsm_x4_trans(smem_u32(&Vs[key * LD + dim]), b0, b1, b2, b3);
+          ldsm_x4_trans(sV + key * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
           mma_bf16_16816(o_acc[2 * dp], pa, b0, b1);
           mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
         }
@@ -316,53 +274,54 @@ __global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, int n_items, 
 #pragma unroll
         for (int dp = 0; dp < HD / 16; ++dp) {
           const int key = 64 + (mi & 1) * 8 + ri;
-          const int dim = dp * 16 + (mi >> 1) * 8;
+          const int c16 = dp * 2 + (mi >> 1);
           uint32_t b0, b1, b2, b3;
-          ldsm_x4_trans(smem_u32(&Vs[key * LD + dim]), b0, b1, b2, b3);
+          ldsm_x4_trans(sV + key * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
           mma_bf16_16816(o_acc[2 * dp], pa, b0, b1);
           mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
         }
       }
-
-      // ---- finalize the item after its last chunk ----
-      if (kc == n_chunks - 1) {
-        const int h = cc.h;
-        const int b = cc.b;
-        const int q0 = qb * 64;
-        float l0 = l_row[0], l1 = l_row[1];
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float i0 = 1.f / l0, i1 = 1.f / l1;
-        // each warp stages and stores its own 16 rows (only this warp ever touches these sO rows)
-#pragma unroll
-        for (int nt = 0; nt < HD / 8; ++nt) {
-          *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g) * LD + nt * 8 + 2 * t]) =
-              pack_bf16(o_acc[nt][0] * i0, o_acc[nt][1] * i0);
-          *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g + 8) * LD + nt * 8 + 2 * t]) =
-              pack_bf16(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
-        }
-        __syncwarp();
-        if (warp < 4) {
-          bf16* obase = a.o + ((size_t)b * a.nq_patch + q0) * a.o_ld + h * HD;
-          for (int idx = lane; idx < 16 * PIECES; idx += 32) {
-            const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
-            if (q0 + row < a.nq_patch)
-              *reinterpret_cast<uint4*>(obase + (size_t)row * a.o_ld + pc * 8) =
-                  *reinterpret_cast<const uint4*>(&sO[row * LD + pc * 8]);
-          }
-        } else if (lane < PIECES) {
-          const size_t orow = (size_t)a.n_seq * a.nq_patch + b;   // class-token output row
-          *reinterpret_cast<uint4*>(a.o + orow * a.o_ld + h * HD + lane * 8) =
-              *reinterpret_cast<const uint4*>(&sO[64 * LD + lane * 8]);
-        }
-        __syncwarp();
-      }
     }
-    __syncthreads();  // everyone is done with this stage before a later fetch refills it
+    // this warp is done reading the stage: hand it back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+
+    // ---- finalize the item after its last chunk ----
+    if (active && kc == n_chunks - 1) {
+      const int h = cc.h;
+      const int b = cc.b;
+      const int q0 = qb * 64;
+      float l0 = l_row[0], l1 = l_row[1];
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = 1.f / l0, i1 = 1.f / l1;
+      // each warp stages and stores its own 16 rows (only this warp ever touches these sO rows)
+#pragma unroll
+      for (int nt = 0; nt < HD / 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g) * OLD + nt * 8 + 2 * t]) =
+            pack_bf16(o_acc[nt][0] * i0, o_acc[nt][1] * i0);
+        *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g + 8) * OLD + nt * 8 + 2 * t]) =
+            pack_bf16(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
+      }
+      __syncwarp();
+      if (warp < 4) {
+        bf16* obase = a.o + ((size_t)b * a.nq_patch + q0) * a.o_ld + h * HD;
+        for (int idx = lane; idx < 16 * PIECES; idx += 32) {
+          const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
+          if (q0 + row < a.nq_patch)
+            *reinterpret_cast<uint4*>(obase + (size_t)row * a.o_ld + pc * 8) =
+                *reinterpret_cast<const uint4*>(&sO[row * OLD + pc * 8]);
+        }
+      } else if (lane < PIECES) {
+        const size_t orow = (size_t)a.n_seq * a.nq_patch + b;   // class-token output row
+        *reinterpret_cast<uint4*>(a.o + orow * a.o_ld + h * HD + lane * 8) =
+            *reinterpret_cast<const uint4*>(&sO[64 * OLD + lane * 8]);
+      }
+      __syncwarp();
+    }
     if (++kc == n_chunks) { kc = 0; advance(cc); }
-    if (++stage == NST) stage = 0;
+    if (++stage == NST) { stage = 0; phase ^= 1; }
   }
-  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -478,16 +437,22 @@ static int attention_launch(const AttnArgs& a, int cls_only, cudaStream_t stream
   const int per_sm = a.head_dim == 32 ? per_sm32 : per_sm64;
   size_t grid = (size_t)sms * per_sm;
   if (grid > items) grid = items;
-  AttnArgs b = a;
-  if (cls_only) {
-    // with cls_only the 64-query blocks are not walked: one item per (sequence, head); the class-token query row is
-    // still addressed as row n_seq*nq_patch + b of the q buffer
-    if (a.head_dim == 32) attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(b, (int)items, 1);
-    else attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(b, (int)items, 1);
-  } else {
-    if (a.head_dim == 32) attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(b, (int)items, 0);
-    else attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(b, (int)items, 0);
-  }
+  // TMA descriptors: 64-row tiles and single rows (class token) of the q / k / v buffers, hardware swizzle = row bytes
+  const int HD = a.head_dim, swz = HD * 2;
+  const uint64_t cols = (uint64_t)a.n_heads * HD;
+  const uint64_t q_rows = (uint64_t)a.n_seq * a.nq_patch + (a.q_has_cls ? a.n_seq : 0);
+  const uint64_t k_rows = (uint64_t)a.n_kv_seq * a.nk_patch + (a.k_has_cls ? a.n_kv_seq : 0);
+  AttnMaps maps;
+  if (make_tmap_bf16_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, HD, 64, swz)) return 1;
+  if (make_tmap_bf16_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, HD, 1, swz)) return 1;
+  if (make_tmap_bf16_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, HD, 64, swz)) return 1;
+  if (make_tmap_bf16_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, HD, 1, swz)) return 1;
+  if (make_tmap_bf16_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, HD, 64, swz)) return 1;
+  if (make_tmap_bf16_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, HD, 1, swz)) return 1;
+  if (a.head_dim == 32)
+    attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(a, maps, (int)items, cls_only);
+  else
+    attn_mma_kernel<64><<<(unsigned)grid, 160, AttnSmem<64>::BYTES, stream>>>(a, maps, (int)items, cls_only);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }

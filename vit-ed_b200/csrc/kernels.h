@@ -13,6 +13,9 @@ enum { IMPL_FAST = 0, IMPL_REF = 1 };  // IMPL_REF: plain SIMT kernels kept as o
 int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream);
 int gemm_num_sms();
+// 2-D bf16 TMA descriptor (driver entry point resolved in gemm_tc.cu); swizzle_bytes in {0, 64, 128}
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
 // ---- row-wise kernels (rowops.cu) ----
 // x[r,:] = (gather ? src[map(r),:] : x[r,:]) + delta[r,:]; optionally h[r,:] = LayerNorm(x[r,:]) * w + b (bf16).
