@@ -48,7 +48,7 @@ struct AttnMaps {
 //    chunk only), so 65-token sequences cost 9/8 of a 64-token one instead of 2x.
 //  * cls_only: only warp 4 computes (last decoder layer: only row 0 of each sequence reaches the head).
 template <int HD>
-__global__ void __launch_bounds__(160) attn_mma_kernel(AttnArgs a, const __grid_constant__ AttnMaps maps, int n_items,
+__global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArgs a, const __grid_constant__ AttnMaps maps, int n_items,
                                                        int cls_only) {
   using SM = AttnSmem<HD>;
   constexpr int RB = SM::RB;
