@@ -74,19 +74,20 @@ def main():
     P, H, hd, Np = 4032, 12, 32, 64
     qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
     o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
-    for impl in (0, 1):
+    for impl in (0, 2):
         ms = timeit(lambda: L.check(L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D,
                                                               3 * D, o.data_ptr(), D, P, H, hd, Np, 1, Np, 1, P, None, hd ** -0.5, impl, st),
-                                    'attn'), flush=flush, iters=5 if impl else 20)
+                                    'attn'), flush=flush)
         fl = 4.0 * P * H * 65 * 65 * hd
         by = M * D * 2 * 4
         out.append(dict(op=f'attn_self_impl{impl}', ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
     kv = torch.randn(540 * Np, 2 * D, device='cuda').bfloat16()
     q = torch.randn(M, D, device='cuda').bfloat16()
     idx = (torch.arange(P, device='cuda') // 539).int()
-    ms = timeit(lambda: L.check(L.lib.vited_op_attention(q.data_ptr(), D, kv.data_ptr(), 2 * D, kv.data_ptr() + 2 * D, 2 * D, o.data_ptr(), D,
-                                                          P, H, hd, Np, 1, Np, 0, 540, idx.data_ptr(), hd ** -0.5, 0, st), 'attn'), flush=flush)
-    out.append(dict(op='attn_cross_impl0', ms=ms, tflops=4.0 * P * H * 65 * 64 * hd / ms / 1e9, gbs=M * D * 2 * 2 / ms / 1e6))
+    for impl in (0, 2):
+        ms = timeit(lambda: L.check(L.lib.vited_op_attention(q.data_ptr(), D, kv.data_ptr(), 2 * D, kv.data_ptr() + 2 * D, 2 * D, o.data_ptr(), D,
+                                                              P, H, hd, Np, 1, Np, 0, 540, idx.data_ptr(), hd ** -0.5, impl, st), 'attn'), flush=flush)
+        out.append(dict(op=f'attn_cross_impl{impl}', ms=ms, tflops=4.0 * P * H * 65 * 64 * hd / ms / 1e9, gbs=M * D * 2 * 2 / ms / 1e6))
     for r in out:
         r['peaks'] = src
         print(json.dumps(r))

@@ -8,6 +8,7 @@
 //
 // Token rows live in the "split" layout: n_seq*n_patch patch rows, then n_seq cls rows.
 #include "kernels.h"
+#include <cstdlib>
 
 namespace vited {
 
@@ -413,6 +414,12 @@ int attention(const AttnArgs& a, int impl, cudaStream_t stream) {
     if (a.head_dim == 32) attn_simt_kernel<32><<<grid, 128, 0, stream>>>(a);
     else attn_simt_kernel<64><<<grid, 128, 0, stream>>>(a);
   } else {
+    static int use_tc = -1;   // VITED_ATTN_TC=0 keeps everything on the mma.sync kernel (A/B measurements)
+    if (use_tc < 0) {
+      const char* e = getenv("VITED_ATTN_TC");
+      use_tc = e ? atoi(e) : 1;
+    }
+    if (impl == IMPL_FAST && use_tc && attention_tc_supported(a)) return attention_tc(a, stream);
     return attention_launch(a, 0, stream);
   }
   VITED_CUDA_OK(cudaGetLastError());

@@ -562,7 +562,7 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
   VITED_CHECK(e != nullptr, "null engine");
   switch (option) {
     case VITED_OPT_GEMM_IMPL: e->gemm_impl = value ? IMPL_REF : IMPL_FAST; return 0;
-    case VITED_OPT_ATTN_IMPL: e->attn_impl = value ? IMPL_REF : IMPL_FAST; return 0;
+    case VITED_OPT_ATTN_IMPL: e->attn_impl = value == 1 ? IMPL_REF : value == 2 ? IMPL_MMA_SYNC : IMPL_FAST; return 0;
     case VITED_OPT_CHUNK_ROWS:
       VITED_CHECK(value >= 1, "chunk_rows must be positive");
       e->chunk_rows = value;

@@ -6,7 +6,8 @@
 namespace vited {
 
 enum { ACT_NONE = 0, ACT_GELU = 1 };
-enum { IMPL_FAST = 0, IMPL_REF = 1 };  // IMPL_REF: plain SIMT kernels kept as on-device debugging references
+enum { IMPL_FAST = 0, IMPL_REF = 1, IMPL_MMA_SYNC = 2 };  // IMPL_REF: plain SIMT debugging kernels; IMPL_MMA_SYNC (attention
+                                                        // only): force the general mma.sync kernel even where a tcgen05 one exists
 
 // ---- GEMM: C[M,N] (bf16) = act(A[M,K] (bf16, row-major) * W[N,K]^T (bf16, row-major) + bias[N] (f32)) ----
 // IMPL_FAST: persistent warp-specialised tcgen05/TMEM kernel fed by TMA (gemm_tc.cu).
@@ -79,6 +80,9 @@ struct AttnArgs {
   float scale;
 };
 int attention(const AttnArgs& a, int impl, cudaStream_t stream);
+// tcgen05/TMEM kernels for the hot decoder shapes (attention_tc.cu); attention() dispatches to them by itself
+bool attention_tc_supported(const AttnArgs& a);
+int attention_tc(const AttnArgs& a, cudaStream_t stream);
 // class-token query only: q is [n_seq, q_ld] (one row per sequence), o likewise; nq_patch / q_has_cls are ignored.
 int attention_cls(const AttnArgs& a, cudaStream_t stream);
 
