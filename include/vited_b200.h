@@ -62,8 +62,10 @@ enum {
   VITED_OPT_CHUNK_ROWS = 2,     /* target token rows per decoder chunk (default 262144)                          */
   VITED_OPT_CACHE_LAYER0 = 3,   /* 1 (default) = run decoder layer 0's self-attention once per item, not per pair */
   VITED_OPT_PROFILE = 4,        /* 1 = record a CUDA event before every launch (see vited_profile_json); default 0   */
-  VITED_OPT_PRUNE_TAIL = 5      /* 1 (default) = in the last decoder layer run everything after the K/V projection of
+  VITED_OPT_PRUNE_TAIL = 5,     /* 1 (default) = in the last decoder layer run everything after the K/V projection of
                                    its self-attention on the class-token rows only (only row 0 reaches the head)   */
+  VITED_OPT_FUSE_LN = 6         /* 1 (default) = residual add + LayerNorm run in the epilogue of the producing GEMM
+                                   (embed_dim 384, large row counts); 0 = separate resid_ln kernel                  */
 };
 
 /* Library-wide last error message (thread-local). */
@@ -119,6 +121,10 @@ VITED_API int64_t vited_workspace_bytes(vited_engine* e);
 /* C[M,N] bf16 = act(A[M,K] bf16 * W[N,K]^T bf16 + bias[N] f32); act: 0 none, 1 exact-erf GELU; impl as GEMM_IMPL */
 VITED_API int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,
                   void* stream);
+/* fused Linear + residual + LayerNorm (N must be 384): x[M,384] f32 += A[M,K] bf16 * W[384,K]^T bf16 + bias;
+ * h[M,384] bf16 = LayerNorm(x) * ln_w + ln_b */
+VITED_API int vited_op_gemm_resid_ln(const void* A, const void* W, const float* bias, float* x, const float* ln_w,
+                           const float* ln_b, void* h, int M, int N, int K, float eps, void* stream);
 /* x += delta (bf16, may be NULL); h = LayerNorm(x) * w + b as bf16 (w NULL => skipped). Split token layout. */
 VITED_API int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
                       int n_patch, int has_cls, int D, float eps, void* stream);

@@ -136,6 +136,34 @@ def test_resid_ln(D, has_cls):
     assert (h.float() - h_ref).abs().max().item() <= 1e-2 * h_ref.abs().max().item() + 1e-3
 
 
+@pytest.mark.parametrize('shape', [(256, 384), (70000, 384), (33333, 1536), (1, 384), (300, 64), (40000, 192)],
+                         ids=lambda s: 'x'.join(map(str, s)))
+def test_gemm_resid_ln_fused(shape):
+    """x += A W^T + b; h = LayerNorm(x): the fused tcgen05 epilogue against fp32 torch on the same bf16 operands."""
+    L = _lib()
+    M, K = shape
+    N = 384
+    g = torch.Generator(device='cuda').manual_seed(M + K)
+    A = torch.randn(M, K, device='cuda', generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    bias = torch.randn(N, device='cuda', generator=g)
+    # rows with a large common offset exercise the shifted variance
+    x = torch.randn(M, N, device='cuda', generator=g) * 2 + torch.randn(M, 1, device='cuda', generator=g) * 5
+    lw = 1 + 0.1 * torch.randn(N, device='cuda', generator=g)
+    lb = 0.1 * torch.randn(N, device='cuda', generator=g)
+    x_ref = x + A.float() @ W.float().t() + bias
+    h_ref = torch.nn.functional.layer_norm(x_ref, (N,), lw, lb, 1e-6)
+    h = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')
+    L.check(L.lib.vited_op_gemm_resid_ln(_ptr(A), _ptr(W), _ptr(bias), _ptr(x), _ptr(lw), _ptr(lb), _ptr(h), M, N, K,
+                                         1e-6, _stream()), 'op_gemm_resid_ln')
+    torch.cuda.synchronize()
+    assert torch.isfinite(h.float()).all() and torch.isfinite(x).all()
+    # fp32 accumulation-order noise only (the accumulator is never rounded to bf16 on this path)
+    assert (x - x_ref).abs().max().item() < 1e-3 * max(1.0, x_ref.abs().max().item())
+    # bf16 rounding of the normalised row: 2^-9 relative
+    assert (h.float() - h_ref).abs().max().item() <= 1e-2 * h_ref.abs().max().item() + 2e-3
+
+
 def _attn_reference(q, k, v, scale):
     # q [B,H,Nq,hd] etc, fp32 math on bf16-rounded inputs
     s = (q.float() @ k.float().transpose(-1, -2)) * scale

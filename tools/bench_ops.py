@@ -60,6 +60,20 @@ def main():
                             gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm, bn=os.environ.get('VITED_GEMM_BN', 'auto')))
         ms = timeit(lambda: torch.matmul(A, W.t(), out=C), flush=flush)
         out.append(dict(op=f'cublas_{name}', M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9))
+    # fused GEMM + residual + LayerNorm (N = 384)
+    for name, K in (('proj', 384), ('fc2', 1536)):
+        A = torch.randn(M, K, device='cuda').bfloat16()
+        W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).bfloat16()
+        b = torch.randn(384, device='cuda')
+        xx = torch.randn(M, 384, device='cuda')
+        lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
+        hh = torch.empty(M, 384, dtype=torch.bfloat16, device='cuda')
+        ms = timeit(lambda: L.check(L.lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), xx.data_ptr(), lw.data_ptr(),
+                                                                  lb.data_ptr(), hh.data_ptr(), M, 384, K, 1e-6, st), 'gemm_ln'), flush=flush)
+        fl = 2.0 * M * 384 * K
+        by = M * K * 2 + 384 * K * 2 + M * 384 * (4 + 4 + 2)
+        out.append(dict(op=f'gemm_ln_{name}', M=M, N=384, K=K, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+        del A, W, xx, hh
     # resid + LN
     D = 384
     x = torch.randn(M, D, device='cuda')

@@ -39,6 +39,7 @@ OPT_CHUNK_ROWS = 2
 OPT_CACHE_LAYER0 = 3
 OPT_PROFILE = 4
 OPT_PRUNE_TAIL = 5
+OPT_FUSE_LN = 6
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -63,6 +64,7 @@ SIGNATURES = {
     "vited_launch_count": (_i64, [_vp]),
     "vited_workspace_bytes": (_i64, [_vp]),
     "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "vited_op_gemm_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "vited_op_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "vited_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i, _vp]),
     "vited_op_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

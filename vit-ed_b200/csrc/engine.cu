@@ -93,6 +93,7 @@ struct vited_engine {
   int64_t chunk_rows = 262144;
   int cache_layer0 = 1;
   int prune_tail = 1;   // last decoder layer: only the class-token row continues past self-attention
+  int fuse_ln = 1;      // residual + LayerNorm in the epilogue of the N = 384 GEMMs (gemm_ln.cu)
   int64_t launches = 0;
   // optional per-kernel timing (bench.py's roofline): one event before every launch, intervals summed per class
   int profile = 0;
@@ -246,6 +247,22 @@ static int L_gemm(vited_engine* e, const bf16* A, const Linear& l, bf16* Cout, i
     e->launches++;
   }
   return gemm_bf16(A, l.w, l.b, Cout, M, l.out, l.in, act, e->gemm_impl, s);
+}
+// fused x += A W^T + b; h = LN(x)  (gemm_ln.cu). Caller has checked use_fused_ln().
+static bool use_fused_ln(vited_engine* e, size_t rows, const Linear& l) {
+  return e->fuse_ln && e->gemm_impl == IMPL_FAST && rows >= 8192 && gemm_resid_ln_supported((int)rows, l.out, l.in);
+}
+static int L_gemm_ln(vited_engine* e, const bf16* A, const Linear& l, float* x, const LNorm& ln, bf16* h, int M,
+                     cudaStream_t s) {
+  if (e->profile) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "gemm_ln_n%d_k%d", l.out, l.in);
+    prof_mark(e, nm, 2.0 * M * (double)l.out * l.in,
+              2.0 * ((double)M * l.in + (double)l.out * l.in) + (double)M * l.out * (4.0 + 4.0 + 2.0), s);
+  } else {
+    e->launches++;
+  }
+  return gemm_resid_ln(A, l.w, l.b, x, ln.w, ln.b, h, M, l.out, l.in, 1e-6f, s);
 }
 static int L_resid_ln(vited_engine* e, float* x, const bf16* delta, const float* gsrc, const int* gidx, int n_src,
                       const LNorm* ln, bf16* h, int n_seq, int has_cls, int write_x, cudaStream_t s) {
@@ -443,6 +460,11 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
   bf16* hid = e->hid.as<bf16>();
   const size_t kv_per_layer = (size_t)n_kv_seq * e->Ne * 2 * D;
   const size_t L = e->dec.size();
+  // With FUSE_LN the residual add + LayerNorm of a sub-block boundary runs in the epilogue of the GEMM that produces
+  // the sub-block output (proj -> norm_cross, cross proj -> norm2, fc2 -> the NEXT layer's norm1), so `delta` is never
+  // written and the separate resid_ln pass disappears.
+  const bool fuse = use_fused_ln(e, rows, e->dec[0].proj);
+  bool h_is_norm1 = false;   // h already holds norm1(x) of the current layer (fc2 of the previous layer was fused)
   for (size_t l = 0; l < L; ++l) {
     DecBlock& b = e->dec[l];
     const bool first = (l == 0);
@@ -455,18 +477,32 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
         TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s));
       } else {
         if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
-        else TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
+        else if (!h_is_norm1) TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
         TRY(L_gemm(e, h, b.qkv, qkv, (int)rows, ACT_NONE, s));
         TRY(L_attn_self(e, qkv, o, P, 1, s));
-        TRY(L_gemm(e, o, b.proj, delta, (int)rows, ACT_NONE, s));
-        TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm_cross, h, P, 1, 1, s));
+        if (fuse) {
+          TRY(L_gemm_ln(e, o, b.proj, x, b.norm_cross, h, (int)rows, s));
+        } else {
+          TRY(L_gemm(e, o, b.proj, delta, (int)rows, ACT_NONE, s));
+          TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm_cross, h, P, 1, 1, s));
+        }
       }
       TRY(L_gemm(e, h, b.q, q, (int)rows, ACT_NONE, s));
       TRY(L_attn_cross(e, q, kvl, o, P, n_kv_seq, ci, s));
-      TRY(L_gemm(e, o, b.cproj, delta, (int)rows, ACT_NONE, s));
-      TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, P, 1, 1, s));
+      if (fuse) {
+        TRY(L_gemm_ln(e, o, b.cproj, x, b.norm2, h, (int)rows, s));
+      } else {
+        TRY(L_gemm(e, o, b.cproj, delta, (int)rows, ACT_NONE, s));
+        TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, P, 1, 1, s));
+      }
       TRY(L_gemm(e, h, b.fc1, hid, (int)rows, ACT_GELU, s));
-      TRY(L_gemm(e, hid, b.fc2, delta, (int)rows, ACT_NONE, s));
+      h_is_norm1 = false;
+      if (fuse && l + 1 < L) {
+        TRY(L_gemm_ln(e, hid, b.fc2, x, e->dec[l + 1].norm1, h, (int)rows, s));
+        h_is_norm1 = true;
+      } else {
+        TRY(L_gemm(e, hid, b.fc2, delta, (int)rows, ACT_NONE, s));
+      }
     } else {
       float* x_c = x + cls_off * D;
       bf16* h_c = h + cls_off * D;
@@ -478,7 +514,7 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
         TRY(L_resid_ln_rows(e, x_c, nullptr, xsrc + (size_t)n_src * e->Ne * D, xj, &b.norm_cross, h_c, P, s));
       } else {
         if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
-        else TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
+        else if (!h_is_norm1) TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
         // keys/values for every token, the query for the class token only (qkv rows: [0,D) q, [D,3D) k|v)
         Linear w_kv = b.qkv; w_kv.w = b.qkv.w + D * D; w_kv.b = b.qkv.b + D; w_kv.out = 2 * (int)D;
         Linear w_q = b.qkv; w_q.out = (int)D;
@@ -494,6 +530,7 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
       TRY(L_resid_ln_rows(e, x_c, d_c, nullptr, nullptr, &b.norm2, h_c, P, s));
       TRY(L_gemm(e, h_c, b.fc1, hid, P, ACT_GELU, s));
       TRY(L_gemm(e, hid, b.fc2, d_c, P, ACT_NONE, s));
+      h_is_norm1 = false;
     }
   }
   head.x = x + cls_off * D;
@@ -569,6 +606,7 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
       return 0;
     case VITED_OPT_CACHE_LAYER0: e->cache_layer0 = value ? 1 : 0; return 0;
     case VITED_OPT_PRUNE_TAIL: e->prune_tail = value ? 1 : 0; return 0;
+    case VITED_OPT_FUSE_LN: e->fuse_ln = value ? 1 : 0; return 0;
     case VITED_OPT_PROFILE:
       e->profile = value ? 1 : 0;
       e->recs.clear();
@@ -779,6 +817,11 @@ int64_t vited_workspace_bytes(vited_engine* e) { return e ? e->workspace_bytes()
 int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,
                   void* stream) {
   return gemm_bf16((const bf16*)A, (const bf16*)W, bias, (bf16*)C, M, N, K, act, impl, (cudaStream_t)stream);
+}
+
+int vited_op_gemm_resid_ln(const void* A, const void* W, const float* bias, float* x, const float* ln_w,
+                           const float* ln_b, void* h, int M, int N, int K, float eps, void* stream) {
+  return gemm_resid_ln((const bf16*)A, (const bf16*)W, bias, x, ln_w, ln_b, (bf16*)h, M, N, K, eps, (cudaStream_t)stream);
 }
 
 int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,

@@ -1,0 +1,309 @@
+// Fused Linear + residual add + LayerNorm for the N = embed_dim = 384 projections of the ViT-ED blocks:
+//     x += A * W^T + bias          (attn.proj / cross_attn.proj / mlp.fc2; vision_transformer.py:125-126, :269-271)
+//     h  = LayerNorm(x) * g + b    (the NEXT sub-block's norm: norm_cross / norm2 / next layer's norm1; eps 1e-6)
+// The unfused path writes the GEMM result as a bf16 `delta`, and a second kernel (resid_ln, 98 % of HBM peak, 23 % of the
+// step) re-reads it together with x. Here a CTA pair owns complete 256 x 384 output rows: the accumulator row stays in
+// TMEM (384 fp32 columns), the residual tile streams through small TMA boxes, the updated row is parked back in TMEM
+// (tcgen05.st) while the row statistics are combined, and the normalised bf16 row leaves through TMA stores.
+//
+// Structure = gemm_tc_pair_kernel (cta_group::2, TMA ring, one MMA thread) with N = 384 issued as two N = 192 MMAs per
+// k-step and a full-row epilogue: 8 epilogue warps per CTA, warp (q, c) owns TMEM lane quarter q (32 rows) and the
+// 192-column half c; one thread = one row half. Row statistics use the shifted one-pass form (pivot = first element of
+// the half row) and Chan's pairwise combination across the two halves.
+#include "kernels.h"
+
+namespace vited {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int LN_N = 384;
+constexpr int NH = 192;        // columns per MMA / per epilogue half
+constexpr int CHUNKS = NH / 32;
+
+struct LnCfg {
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t BH_BYTES = (NH / 2) * BK * 2;          // this CTA's 96 rows of one 192-row weight half
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
+  static constexpr int kStages = 3;
+  static constexpr uint32_t XBOX = 32 * 32 * 4;                    // 32 rows x 32 fp32, 128B-swizzled
+  static constexpr uint32_t X_BYTES = kEpiWarps * 2 * XBOX;
+  static constexpr uint32_t H_BYTES = kEpiWarps * 4096;            // 32 rows x 64 bf16 per warp
+  static constexpr uint32_t PARAM_BYTES = 3 * LN_N * 4;
+  static constexpr uint32_t PART_BYTES = 2 * BM * 16;
+  static constexpr uint32_t BAR_BYTES = 512;
+  static constexpr uint32_t SMEM_BYTES = 1024 + kStages * STAGE_BYTES + X_BYTES + H_BYTES + PARAM_BYTES + PART_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LnCfg::kThreads, 1)
+gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                    const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    int M, int K, float eps) {
+  using Cfg = LnCfg;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem + kStages * Cfg::STAGE_BYTES;
+  uint8_t* sH = sX + Cfg::X_BYTES;
+  float* sBias = reinterpret_cast<float*>(sH + Cfg::H_BYTES);
+  float* sG = sBias + LN_N;
+  float* sBt = sG + LN_N;
+  float4* sPart = reinterpret_cast<float4*>(sBt + LN_N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPart) + Cfg::PART_BYTES);
+  uint64_t* full = bars;                       // leader CTA: both CTAs' TMA bytes land here
+  uint64_t* empty = bars + kStages;            // per CTA, released by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * kStages;        // per CTA, multicast commit
+  uint64_t* tempty = tfull + 1;                // leader CTA: epilogue warps of BOTH CTAs arrive
+  uint64_t* xfull = tempty + 1;                // [8 warps][2 boxes]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfull + 2 * Cfg::kEpiWarps);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1);
+  const int num_pairs = (int)(gridDim.x >> 1);
+  const int num_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int num_kb = (K + BK - 1) / BK;
+  const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+
+  for (int i = threadIdx.x; i < LN_N; i += Cfg::kThreads) {
+    sBias[i] = bias[i];
+    sG[i] = ln_w[i];
+    sBt[i] = ln_b[i];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmH);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 2 * Cfg::kEpiWarps);
+    for (int i = 0; i < 2 * Cfg::kEpiWarps; ++i) mbar_init(&xfull[i], 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc_2cta(tmem_holder, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own 128 activation rows + 2 x 96 weight rows per k-block ========
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 10);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(&tmA, &full[stage], a_dst, kb * BK, tile * 2 * BM + (int)rank * BM);
+          tma_load_2d_2cta(&tmB, &full[stage], a_dst + Cfg::A_BYTES, kb * BK, (int)rank * (NH / 2));
+          tma_load_2d_2cta(&tmB, &full[stage], a_dst + Cfg::A_BYTES + Cfg::BH_BYTES, kb * BK, NH + (int)rank * (NH / 2));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only): two N = 192 MMAs per k-step =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, NH);
+      uint32_t stage = 0, phase = 0, aphase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(tempty, aphase ^ 1, 20);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 21);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db0 = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+          const uint64_t db1 = umma_desc_sw128(a_addr + Cfg::A_BYTES + Cfg::BH_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_bf16_2cta(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_2cta(tmem_base + NH, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(tfull);
+        aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== full-row epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;       // TMEM lane quarter: rows q*32 .. q*32+31 of this CTA's 128
+    const int c = ew >> 2;        // column half
+    uint8_t* xbox = sX + ew * 2 * Cfg::XBOX;
+    uint8_t* hbox = sH + ew * 4096;
+    uint64_t* my_xfull = xfull + ew * 2;
+    const int total_chunks = my_tiles * CHUNKS;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * NH;
+    const int sw = lane & 7;
+    // residual boxes are prefetched two chunks ahead, across tile boundaries (so the next tile's first boxes are in
+    // flight while the tensor core works on it)
+    auto issue_x = [&](int g) {   // lane 0 only
+      if (g >= total_chunks) return;
+      const int t = g / CHUNKS, j = g - t * CHUNKS;
+      const int tile = pair + t * num_pairs;
+      mbar_arrive_expect_tx(&my_xfull[g & 1], Cfg::XBOX);
+      tma_load_2d(&tmX, &my_xfull[g & 1], xbox + (g & 1) * Cfg::XBOX, c * NH + j * 32, tile * 2 * BM + (int)rank * BM + q * 32);
+    };
+    if (lane == 0) { issue_x(0); issue_x(1); }
+    uint32_t aphase = 0;
+    int g = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = pair + t * num_pairs;
+      const int row0 = tile * 2 * BM + (int)rank * BM + q * 32;
+      mbar_wait(tfull, aphase, 30);
+      tc_fence_after();
+      // ---- pass 1: v = acc + bias + x; park v in TMEM, write it back to the residual stream, shifted statistics ----
+      float s = 0.f, ss = 0.f, c0 = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < CHUNKS; ++j, ++g) {
+        const int col0 = c * NH + j * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tlane + j * 32, acc);
+        tmem_ld_wait();
+        mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
+        uint8_t* rowp = xbox + (g & 1) * Cfg::XBOX + lane * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4* px = reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4));
+          const float4 xv = *px;
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + col0 + 4 * i);
+          float4 v;
+          v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
+          v.y = __uint_as_float(acc[4 * i + 1]) + b4.y + xv.y;
+          v.z = __uint_as_float(acc[4 * i + 2]) + b4.z + xv.z;
+          v.w = __uint_as_float(acc[4 * i + 3]) + b4.w + xv.w;
+          if (j == 0 && i == 0) c0 = v.x;
+          const float d0 = v.x - c0, d1 = v.y - c0, d2 = v.z - c0, d3 = v.w - c0;
+          s += (d0 + d1) + (d2 + d3);
+          ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+          *px = v;
+          acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
+          acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
+        }
+        tmem_st_32x32b_x32(tlane + j * 32, acc);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmX, xbox + (g & 1) * Cfg::XBOX, col0, row0);
+          tma_store_commit();
+          tma_store_wait_read();      // the box is free again once the store has read it
+          issue_x(g + 2);
+        }
+      }
+      tmem_st_wait();
+      // ---- combine the two column halves of every row (Chan): n = 192 each ----
+      sPart[c * BM + q * 32 + lane] = make_float4(s, ss, c0, 0.f);
+      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+      const float4 o4 = sPart[(c ^ 1) * BM + q * 32 + lane];
+      const float inv_n = 1.f / NH;
+      const float mean_a = c0 + s * inv_n, m2_a = ss - s * s * inv_n;
+      const float mean_b = o4.z + o4.x * inv_n, m2_b = o4.y - o4.x * o4.x * inv_n;
+      const float dm = mean_b - mean_a;
+      const float mean = 0.5f * (mean_a + mean_b);
+      const float var = (m2_a + m2_b + dm * dm * (0.5f * NH)) * (1.f / LN_N);
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+      // ---- pass 2: normalise out of TMEM, bf16, 64-column slabs through the warp's staging box ----
+#pragma unroll 1
+      for (int jj = 0; jj < CHUNKS / 2; ++jj) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int j = jj * 2 + hh;
+          const int col0 = c * NH + j * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tlane + j * 32, v);
+          tmem_ld_wait();
+          if (j == CHUNKS - 1) {
+            // last read of this tile's accumulator: hand TMEM back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float ga = sG[col0 + 8 * i + e] * rstd;
+              y[e] = fmaf(__uint_as_float(v[8 * i + e]) - mean, ga, sBt[col0 + 8 * i + e]);
+            }
+            uint4 pk;
+            pk.x = pack_bf16(y[0], y[1]);
+            pk.y = pack_bf16(y[2], y[3]);
+            pk.z = pack_bf16(y[4], y[5]);
+            pk.w = pack_bf16(y[6], y[7]);
+            *reinterpret_cast<uint4*>(hbox + lane * 128 + (((hh * 4 + i) ^ sw) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmH, hbox, c * NH + jj * 64, row0);
+          tma_store_commit();
+        }
+      }
+      aphase ^= 1;
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool gemm_resid_ln_supported(int M, int N, int K) { return N == LN_N && K % 8 == 0 && K >= 8 && M >= 1; }
+
+int gemm_resid_ln(const bf16* A, const bf16* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
+                  bf16* h, int M, int N, int K, float eps, cudaStream_t stream) {
+  VITED_CHECK(gemm_resid_ln_supported(M, N, K), "gemm_resid_ln: unsupported shape M=%d N=%d K=%d (N must be 384)", M, N, K);
+  VITED_CHECK(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x) |
+                reinterpret_cast<uintptr_t>(h)) & 15) == 0, "gemm_resid_ln: operands must be 16-byte aligned");
+  const int sms = gemm_num_sms();
+  VITED_CHECK(sms >= 2, "gemm_resid_ln: no device");
+  static bool attr_set = false;
+  if (!attr_set) {
+    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)LnCfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  CUtensorMap tA, tB, tX, tH;
+  if (make_tmap_bf16_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, BM, 128)) return 1;
+  if (make_tmap_bf16_2d(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, NH / 2, 128)) return 1;
+  if (make_tmap_f32_2d(&tX, x, (uint64_t)N, (uint64_t)M, (uint64_t)N * 4, 32, 32, 128)) return 1;
+  if (make_tmap_bf16_2d(&tH, h, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 64, 32, 128)) return 1;
+  const int tiles = (M + 2 * BM - 1) / (2 * BM);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  gemm_ln_pair_kernel<<<2 * pairs, LnCfg::kThreads, LnCfg::SMEM_BYTES, stream>>>(tA, tB, tX, tH, bias, ln_w, ln_b, M, K, eps);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vited

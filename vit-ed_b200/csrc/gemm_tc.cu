@@ -82,6 +82,29 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t 
   return 0;
 }
 
+// 2-D fp32 tensor map (residual stream tiles of the fused GEMM + residual + LayerNorm kernel, gemm_ln.cu)
+int make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                     uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+  std::call_once(g_once, init_driver_once);
+  if (g_init_status) return 1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32) failed (%d): ptr=%p cols=%llu rows=%llu stride=%llu box=%ux%u swizzle=%d", (int)r,
+              ptr, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_cols,
+              box_rows, swizzle_bytes);
+    return 1;
+  }
+  return 0;
+}
+
 constexpr int BM = 128;
 constexpr int BK = 64;
 

@@ -18,6 +18,17 @@ int gemm_num_sms();
 int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
+int make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                     uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
+
+// ---- fused GEMM + residual + LayerNorm (gemm_ln.cu) ----
+//   x[M,384] (f32, in place) += A[M,K] (bf16) * W[384,K]^T (bf16) + bias;  h[M,384] (bf16) = LayerNorm(x) * ln_w + ln_b
+// i.e. `x = x + proj(...)` followed by the next `normX(x)` (vision_transformer.py:124-127, :268-272) in ONE kernel: the
+// accumulator row never leaves the SM before it is normalised. Only N = 384 (the models' embed_dim) and large M.
+bool gemm_resid_ln_supported(int M, int N, int K);
+int gemm_resid_ln(const bf16* A, const bf16* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
+                  bf16* h, int M, int N, int K, float eps, cudaStream_t stream);
+
 // ---- row-wise kernels (rowops.cu) ----
 // x[r,:] = (gather ? src[map(r),:] : x[r,:]) + delta[r,:]; optionally h[r,:] = LayerNorm(x[r,:]) * w + b (bf16).
 // Row space is the "split" layout: n_seq*n_patch patch rows followed by n_cls cls rows (n_cls = n_seq or 0).
