@@ -173,7 +173,8 @@ def _attn_reference(q, k, v, scale):
 @pytest.mark.parametrize('impl', [0, 1, 2], ids=['fast', 'simt', 'mma_sync'])
 @pytest.mark.parametrize('cfg', [
     # (n_seq, H, hd, n_patch, has_cls)  -- self-attention
-    (7, 12, 32, 64, 1), (1, 1, 32, 64, 1), (333, 12, 32, 64, 1), (150, 5, 32, 64, 0), (3, 6, 64, 1024, 1), (5, 12, 32, 64, 0), (2, 6, 64, 1024, 0), (4, 1, 32, 4, 1),
+    (7, 12, 32, 64, 1), (1, 1, 32, 64, 1), (333, 12, 32, 64, 1), (150, 5, 32, 64, 0),
+    (40, 6, 64, 1024, 1), (1, 1, 64, 256, 1), (9, 3, 64, 512, 0), (30, 2, 64, 256, 1), (3, 6, 64, 1024, 1), (5, 12, 32, 64, 0), (2, 6, 64, 1024, 0), (4, 1, 32, 4, 1),
     (3, 3, 32, 16, 1), (2, 2, 64, 100, 1), (1, 2, 32, 130, 0),
 ], ids=lambda c: 'x'.join(map(str, c)))
 def test_self_attention(cfg, impl):
@@ -205,7 +206,7 @@ def test_self_attention(cfg, impl):
 @pytest.mark.parametrize('impl', [0, 1, 2], ids=['fast', 'simt', 'mma_sync'])
 @pytest.mark.parametrize('cfg', [
     # (n_pairs, n_ctx, H, hd, n_patch)
-    (9, 4, 12, 32, 64), (1, 1, 12, 32, 64), (401, 7, 12, 32, 64), (5, 3, 6, 64, 1024), (6, 2, 1, 32, 4), (4, 4, 2, 64, 16),
+    (9, 4, 12, 32, 64), (1, 1, 12, 32, 64), (401, 7, 12, 32, 64), (37, 5, 6, 64, 1024), (3, 2, 1, 64, 256), (5, 3, 6, 64, 1024), (6, 2, 1, 32, 4), (4, 4, 2, 64, 16),
 ], ids=lambda c: 'x'.join(map(str, c)))
 def test_cross_attention(cfg, impl):
     L = _lib()

@@ -237,15 +237,452 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
   }
 }
 
+
+// =====================================================================================================================
+// attn_l64_kernel -- Hisfrag model: long sequences (patch tokens a multiple of 256 queries / 128 keys), head_dim 64.
+//   Work item = (sequence, head, 256 patch queries): two softmax groups (128 query rows, 8 warps: two threads per row)
+//   share one ring of 128-key K/V tiles. Per group and key tile: S = Q K^T (128x128, fp32 in TMEM) -> the row's two
+//   threads take the row max, exponentiates (ex2), writes P back to TMEM as packed bf16 over S -> O += P V with P read from TMEM and V
+//   consumed in place as an MN-major operand. The group's leader thread issues PV(t) and then QK^T(t+1) back to back,
+//   so while one group runs its softmax the tensor core works for the other (ping-pong).
+//   Online softmax with a LAZY rescale: the running max only moves when a tile exceeds it by more than 2^8; then the
+//   group waits for its previous PV, multiplies its O rows in TMEM (tcgen05.ld / st) and carries on. Probabilities are
+//   therefore <= 256, exact after the final division by the row sum.
+//   The class-token KEY is a last 16-key tile (row 0 real, the others masked); the class-token QUERY is one extra item
+//   per (sequence, head) whose tile has a single live row (group 0 only).
+// =====================================================================================================================
+struct L64 {
+  static constexpr int HD = 64;
+  static constexpr int RB = 128;               // bytes per tile row
+  static constexpr int QB = 128 * RB;          // one Q tile
+  static constexpr int KVB = 128 * RB;         // one K or V tile
+  static constexpr int STAGE = 2 * KVB;        // K, V
+  static constexpr int NS = 5;                 // K/V ring depth
+  static constexpr int THREADS = 576;          // warps 0-7 group 0, 8-15 group 1, 16 TMA producer, 17 TMEM allocator + MMA issuer
+  static constexpr int GCOLS = 256;            // TMEM columns per group: S/P at +0 (128), O at +128 (64)
+  static constexpr int OCOL = 128;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // [max | sum][group][half][row] exchange slots
+  static constexpr int BYTES = 1024 + 2 * QB + NS * STAGE + XCH_BYTES + BAR_BYTES;
+};
+
+#ifdef VITED_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[2 * 64 * 12];   // [group][tile][event] clock64 of block 0's leader threads
+#define TRACE(ev) do { if (blockIdx.x == 0 && leader && trace_tile < 64) g_attn_trace[(g * 64 + trace_tile) * 12 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(ev) do { } while (0)
+#endif
+
+struct L64Maps {
+  CUtensorMap q_tile, q_row, k_tile, k_row, v_tile, v_row;   // boxes {64, 128} and {64, 1}, 128B swizzle
+};
+
+__device__ __forceinline__ uint32_t group_any256(uint32_t pred, int bar_id) {   // OR-reduce a flag over a 256-thread group
+  uint32_t r;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "barrier.cta.red.or.pred q, %2, 256, p;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"(pred), "r"(bar_id)
+      : "memory");
+  return r;
+}
+
+__global__ void __launch_bounds__(L64::THREADS, 1)
+attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
+  using C = L64;
+  extern __shared__ uint8_t attn_tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                          // [2 groups][128 x 128 B]
+  uint8_t* sKV = smem + 2 * C::QB;             // [NS][K tile | V tile]
+  float* sXch = reinterpret_cast<float*>(sKV + C::NS * C::STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::NS * C::STAGE + C::XCH_BYTES);
+  uint64_t* kv_full = bars;                    // [NS] TMA bytes landed
+  uint64_t* kv_empty = bars + C::NS;           // [NS] both groups' PVs have read the stage (one commit after the last)
+  uint64_t* q_full = bars + 2 * C::NS;         // [2]
+  uint64_t* q_empty = q_full + 2;              // [2] the item's last QK^T has read the Q tile
+  uint64_t* s_full = q_empty + 2;              // [2] S ready in TMEM
+  uint64_t* o_done = s_full + 2;               // [2] PV finished (O consistent)
+  uint64_t* exp_done = o_done + 2;             // [2] the group has finished the exp phase of a tile (ping-pong order; 8 warps)
+  uint64_t* p_ready = exp_done + 2;            // [2] the group's probabilities are in TMEM (8 warps)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(p_ready + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = a.n_heads;
+  const int n_qp = a.nq_patch / 256;                         // 256-query blocks per (sequence, head)
+  const int per_bh = n_qp + (a.q_has_cls ? 1 : 0);           // + the class-token item
+  const int n_kt = a.nk_patch / 128;
+  const int T = n_kt + (a.k_has_cls ? 1 : 0);                // key tiles per item (last one = class-token key)
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  // stale rows of the ring enter masked score columns / multiply zero probabilities: they only have to be finite
+  for (int i = tid; i < (2 * C::QB + C::NS * C::STAGE) / 16; i += C::THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < C::NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&q_full[g], 1); mbar_init(&q_empty[g], 1); mbar_init(&s_full[g], 1); mbar_init(&o_done[g], 1);
+      mbar_init(&exp_done[g], 8); mbar_init(&p_ready[g], 8);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.q_tile);
+    tma_prefetch_desc(&maps.k_tile);
+    tma_prefetch_desc(&maps.v_tile);
+  }
+  if (warp == 17) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  if (warp == 16) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0, qph = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int item = (int)blockIdx.x + i * (int)gridDim.x;
+        const int bh = item / per_bh, qp = item - bh * per_bh;
+        const int b = bh / H, h = bh - b * H;
+        const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;
+        const int col = h * C::HD;
+        const bool cls_item = qp == n_qp;
+        // Q tiles (group 1 has none in the class-token item)
+        for (int g = 0; g < (cls_item ? 1 : 2); ++g) {
+          mbar_wait(&q_empty[g], qph ^ 1, 60);
+          if (cls_item) {
+            mbar_arrive_expect_tx(&q_full[g], C::RB);
+            tma_load_2d(&maps.q_row, &q_full[g], sQ + g * C::QB, col, a.n_seq * a.nq_patch + b);
+          } else {
+            mbar_arrive_expect_tx(&q_full[g], C::QB);
+            tma_load_2d(&maps.q_tile, &q_full[g], sQ + g * C::QB, col, b * a.nq_patch + qp * 256 + g * 128);
+          }
+        }
+        if (cls_item) {
+          // keep group 1's Q barriers in step: nothing to load, nothing will be consumed
+          mbar_wait(&q_empty[1], qph ^ 1, 61);
+          mbar_arrive(&q_full[1]);
+        }
+        qph ^= 1;
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(&kv_empty[stage], ph ^ 1, 62);
+          uint8_t* st = sKV + stage * C::STAGE;
+          if (t < n_kt) {
+            mbar_arrive_expect_tx(&kv_full[stage], 2 * C::KVB);
+            tma_load_2d(&maps.k_tile, &kv_full[stage], st, col, kvb * a.nk_patch + t * 128);
+            tma_load_2d(&maps.v_tile, &kv_full[stage], st + C::KVB, col, kvb * a.nk_patch + t * 128);
+          } else {
+            mbar_arrive_expect_tx(&kv_full[stage], 2 * C::RB);
+            tma_load_2d(&maps.k_row, &kv_full[stage], st, col, a.n_kv_seq * a.nk_patch + kvb);
+            tma_load_2d(&maps.v_row, &kv_full[stage], st + C::KVB, col, a.n_kv_seq * a.nk_patch + kvb);
+          }
+          if (++stage == C::NS) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ===================== MMA issuer for both groups (warp-uniform; tcgen05 ops on one elected lane) ==========
+    // The ping-pong order makes the events arrive as A(t) B(t) A(t+1) ...: per group and key tile PV(t) as soon as the
+    // group's probabilities are in TMEM, then QK^T(t+1) right behind it (the tensor pipe runs in issue order, so
+    // S(t+1) may overwrite P(t)).
+    const uint32_t idesc_qk128 = umma_idesc_bf16(128, 128), idesc_qk16 = umma_idesc_bf16(128, 16);
+    const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
+    int stage = 0;
+    uint32_t kv_ph = 0, q_ph = 0, p_ph0 = 0, p_ph1 = 0;   // (group 1 skips the class-token items: own phase)
+    auto issue_qk = [&](int g, uint32_t k_addr, bool cls_tile, bool last) {
+      const uint64_t dq = umma_desc_sw128(smem_u32(sQ + g * C::QB));
+      const uint64_t dk = umma_desc_sw128(k_addr);
+      const uint32_t t_col = tmem_base + g * C::GCOLS;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < C::HD / 16; ++k)
+          umma_bf16(t_col, dq + 2 * k, dk + 2 * k, cls_tile ? idesc_qk16 : idesc_qk128, k);
+        umma_commit(&s_full[g]);
+        if (last) umma_commit(&q_empty[g]);
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < n_my; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const bool cls_item = (item % per_bh) == n_qp;
+      const int nact = cls_item ? 1 : 2;          // group 1 has no queries in the class-token item
+      mbar_wait(&q_full[0], q_ph, 66);
+      mbar_wait(&q_full[1], q_ph, 66);
+      q_ph ^= 1;
+      if (cls_item) {
+        if (elect_one_sync()) mbar_arrive(&q_empty[1]);
+        __syncwarp();
+      }
+      mbar_wait(&kv_full[stage], kv_ph, 63);
+      tc_fence_after();
+      for (int g = 0; g < nact; ++g) issue_qk(g, smem_u32(sKV + stage * C::STAGE), n_kt == 0, T == 1);
+      for (int t = 0; t < T; ++t) {
+        const bool cls_tile = t >= n_kt;
+        const uint32_t k_addr = smem_u32(sKV + stage * C::STAGE);
+        int nstage = stage + 1;
+        uint32_t nph = kv_ph;
+        if (nstage == C::NS) { nstage = 0; nph ^= 1; }
+        for (int g = 0; g < nact; ++g) {
+          const uint32_t t_col = tmem_base + g * C::GCOLS;
+          mbar_wait(&p_ready[g], g == 0 ? p_ph0 : p_ph1, 64);
+          if (g == 0) p_ph0 ^= 1; else p_ph1 ^= 1;
+          tc_fence_after();
+          const uint64_t dv = umma_desc_sw(k_addr + C::KVB, 128);
+          if (elect_one_sync()) {
+            if (cls_tile) {
+              umma_bf16_ts(t_col + C::OCOL, t_col, dv, idesc_pv, t != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)   // 16 keys per step = two 8-key groups of 1024 B = +128 in the (addr >> 4) field
+                umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&o_done[g]);
+            if (g == nact - 1) umma_commit(&kv_empty[stage]);   // both groups' PVs have been issued by this thread
+          }
+          __syncwarp();
+          if (t + 1 < T) {
+            if (g == 0) {
+              mbar_wait(&kv_full[nstage], nph, 65);
+              tc_fence_after();
+            }
+            issue_qk(g, smem_u32(sKV + nstage * C::STAGE), t + 1 >= n_kt, t + 2 == T);
+          }
+        }
+        stage = nstage;
+        kv_ph = nph;
+      }
+    }
+  } else if (warp < 16) {
+    // ===================== softmax group g: 128 query rows x 2 column halves (8 warps) =====================
+    // thread (row, half) owns score columns [64*half, 64*half+64) of its row, the matching 32 packed P columns and 32
+    // of the 64 output columns; the two halves of a row exchange their partial max / sum through shared memory.
+    const int g = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool leader = half == 0 && quarter == 0 && lane == 0; (void)leader;
+    const float sl2 = a.scale * kLog2e;
+    const uint32_t t_col = tmem_base + g * C::GCOLS;
+    const uint32_t t_row = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* my_x = sXch + (g * 2 + half) * 128 + row;          // this thread's exchange slot
+    float* peer_x = sXch + (g * 2 + (half ^ 1)) * 128 + row;  // the other half of the same row
+    uint32_t s_ph = 0;
+    uint32_t pv_count = 0;      // PVs issued for this group so far (o_done phase bookkeeping)
+    // Ping-pong: the exp phases of the two groups strictly alternate (A0 B0 A1 B1 ...), so while one group keeps the
+    // MUFU pipe busy the tensor pipe runs the other group's PV / QK^T. Without the order both groups fall into lock
+    // step (exponentiate together, then wait for the tensor pipe together).
+    uint32_t n_exp = 0;         // exp phases (tiles) this group has been through
+    int trace_tile = 0; (void)trace_tile;
+    auto wait_turn = [&]() {
+      if (g == 0) { if (n_exp > 0) mbar_wait(&exp_done[1], (n_exp - 1) & 1u, 72); }
+      else mbar_wait(&exp_done[0], n_exp & 1u, 73);
+    };
+    // running max moved by more than the threshold somewhere in the group: wait for the previous PV, rescale own O columns
+    auto rescale = [&](bool need, float mt, float& m, float& l) {
+      mbar_wait(&o_done[g], (pv_count - 1) & 1u, 68);
+      tc_fence_after();
+      if (need) {
+        const float f = ex2_ftz(m - mt);
+        l *= f;
+        m = mt;
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(t_row + C::OCOL + 32 * half, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * f);
+        tmem_st_32x32b_x32(t_row + C::OCOL + 32 * half, ov);
+      }
+    };
+
+    for (int i = 0; i < n_my; ++i) {
+      const int item = (int)blockIdx.x + i * (int)gridDim.x;
+      const int bh = item / per_bh, qp = item - bh * per_bh;
+      const int b = bh / H, h = bh - b * H;
+      const bool cls_item = qp == n_qp;
+      if (cls_item && g == 1) {
+        // no queries for this group: T empty exp phases keep the ping-pong order in step
+        for (int t = 0; t < T; ++t) {
+          wait_turn();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&exp_done[1]);
+          ++n_exp;
+        }
+        continue;
+      }
+      float m = -INFINITY, l = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const bool cls_tile = t >= n_kt;
+        mbar_wait(&s_full[g], s_ph, 67);
+        s_ph ^= 1;
+        tc_fence_after();
+        TRACE(0);
+        if (!cls_tile) {
+          uint32_t v0[32], v1[32];   // (two plain arrays: taking the address of one 64-entry array forces it into local memory)
+          tmem_ld_32x32b_x32(t_row + 64 * half, v0);
+          tmem_ld_32x32b_x32(t_row + 64 * half + 32, v1);
+          tmem_ld_wait();
+          TRACE(1);
+          float mx[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mx[j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
+#pragma unroll
+          for (int j = 4; j < 32; j += 4)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v0[j + e]), __uint_as_float(v1[j + e])));
+          float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
+          *my_x = mt;
+          // lazy rescale: the running max only moves when a tile exceeds it by more than 8 (log2 units). The vote on
+          // the half-row maxima is exact (the row max exceeds the bound iff one of its halves does) and doubles as the
+          // barrier that publishes the partial maxima.
+          const uint32_t any = group_any256((t > 0 && mt > m + 8.f) ? 1u : 0u, 3 + g);
+          mt = fmaxf(mt, *peer_x);
+          if (t == 0) m = mt;
+          else if (any) rescale(mt > m + 8.f, mt, m, l);
+          TRACE(2);
+          wait_turn();
+          TRACE(3);
+          const float mneg = -m;
+          float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float p0 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j]), sl2, mneg));
+              const float p1 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j + 1]), sl2, mneg));
+              sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
+              pk[j] = pack_bf16(p0, p1);
+            }
+            tmem_st_32x32b_x16(t_row + 32 * half, pk);
+          }
+          {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float p0 = ex2_ftz(fmaf(__uint_as_float(v1[2 * j]), sl2, mneg));
+              const float p1 = ex2_ftz(fmaf(__uint_as_float(v1[2 * j + 1]), sl2, mneg));
+              sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
+              pk[j] = pack_bf16(p0, p1);
+            }
+            tmem_st_32x32b_x16(t_row + 32 * half + 16, pk);
+          }
+          l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+          TRACE(4);
+        } else {
+          // class-token key tile: column 0 is the only real key; both halves see it, half 0 owns it
+          uint32_t vc[8];
+          tmem_ld_32x32b_x8(t_row, vc);
+          tmem_ld_wait();
+          const float mt = __uint_as_float(vc[0]) * sl2;
+          const uint32_t any = group_any256((t > 0 && mt > m + 8.f) ? 1u : 0u, 3 + g);
+          if (t == 0) m = mt;
+          else if (any) rescale(mt > m + 8.f, mt, m, l);
+          wait_turn();
+          if (half == 0) {
+            const float pc = ex2_ftz(mt - m);
+            l += pc;
+            uint32_t pc8[8] = {pack_bf16(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st_32x32b_x8(t_row, pc8);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        TRACE(5);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_ready[g]);      // 8 warps: all of P (and any rescaled O) is in TMEM -> the MMA warp issues PV
+          mbar_arrive(&exp_done[g]);     // 8 warps: this group's exp phase is over -> the other group's turn
+        }
+        ++n_exp;
+        ++pv_count;
+        TRACE(6);
+        TRACE(7);
+        ++trace_tile;
+      }
+      // ---- item epilogue: O / l -> bf16 -> global (each thread writes its 32 of the row's 64 columns) ----
+      my_x[512] = l;        // separate slots: a fast thread may already publish the next item's first max
+      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+      l += peer_x[512];
+      mbar_wait(&o_done[g], (pv_count - 1) & 1u, 71);
+      tc_fence_after();
+      {
+        const float inv = 1.f / l;
+        size_t orow = 0;
+        bool valid;
+        if (cls_item) { valid = row == 0; orow = (size_t)a.n_seq * a.nq_patch + b; }
+        else { valid = true; orow = (size_t)b * a.nq_patch + qp * 256 + g * 128 + row; }
+        uint4* dst = reinterpret_cast<uint4*>(a.o + orow * a.o_ld + h * C::HD + 32 * half);
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(t_row + C::OCOL + 32 * half, ov);
+        tmem_ld_wait();
+        tc_fence_before();   // (the next item's first PV overwrites O only after every warp has published its next P)
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(ov[8 * j + 0]) * inv, __uint_as_float(ov[8 * j + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv);
+            dst[j] = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 
 // true when the tcgen05 kernel covers this problem (the mma.sync kernel in attention.cu covers everything else)
-bool attention_tc_supported(const AttnArgs& a) {
-  return a.head_dim == 32 && a.nq_patch == 64 && a.nk_patch == 64 && a.n_heads >= 1;
+static bool p64_shape(const AttnArgs& a) { return a.head_dim == 32 && a.nq_patch == 64 && a.nk_patch == 64; }
+static bool l64_shape(const AttnArgs& a) {
+  return a.head_dim == 64 && a.nq_patch >= 256 && a.nq_patch % 256 == 0 && a.nk_patch >= 128 && a.nk_patch % 128 == 0;
+}
+bool attention_tc_supported(const AttnArgs& a) { return a.n_heads >= 1 && (p64_shape(a) || l64_shape(a)); }
+
+static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
+  const size_t items = (size_t)a.n_seq * a.n_heads * (a.nq_patch / 256 + (a.q_has_cls ? 1 : 0));
+  VITED_CHECK(items < ((size_t)1 << 31), "attention_tc: too many work items");
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    VITED_CUDA_OK(cudaGetDevice(&dev));
+    VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_l64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L64::BYTES));
+  }
+  const uint64_t cols = (uint64_t)a.n_heads * 64;
+  const uint64_t q_rows = (uint64_t)a.n_seq * a.nq_patch + (a.q_has_cls ? a.n_seq : 0);
+  const uint64_t k_rows = (uint64_t)a.n_kv_seq * a.nk_patch + (a.k_has_cls ? a.n_kv_seq : 0);
+  L64Maps maps;
+  if (make_tmap_bf16_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 64, 128, 128)) return 1;
+  if (make_tmap_bf16_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 64, 1, 128)) return 1;
+  if (make_tmap_bf16_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 64, 128, 128)) return 1;
+  if (make_tmap_bf16_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 64, 1, 128)) return 1;
+  if (make_tmap_bf16_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 128, 128)) return 1;
+  if (make_tmap_bf16_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 1, 128)) return 1;
+  const unsigned grid = (unsigned)(items < (size_t)sms ? items : (size_t)sms);
+  attn_l64_kernel<<<grid, L64::THREADS, L64::BYTES, stream>>>(a, maps, (int)items);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int attention_tc(const AttnArgs& a, cudaStream_t stream) {
   VITED_CHECK(attention_tc_supported(a), "attention_tc: unsupported shape");
+  if (l64_shape(a)) return attention_tc_l64(a, stream);
   const size_t units = (size_t)a.n_seq * a.n_heads;
   VITED_CHECK(units < ((size_t)1 << 31), "attention_tc: too many work units");
   static int sms = 0;
@@ -272,3 +709,9 @@ int attention_tc(const AttnArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace vited
+
+#ifdef VITED_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int vited_debug_attn_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, vited::g_attn_trace, sizeof(unsigned long long) * 2 * 64 * 12);
+}
+#endif

@@ -118,7 +118,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only): two N = 192 MMAs per k-step =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {   // warp-uniform loop, tcgen05 instructions predicated on one elected lane
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, NH);
       uint32_t stage = 0, phase = 0, aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -131,15 +131,19 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db0 = umma_desc_sw128(a_addr + Cfg::A_BYTES);
           const uint64_t db1 = umma_desc_sw128(a_addr + Cfg::A_BYTES + Cfg::BH_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_bf16_2cta(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_bf16_2cta(tmem_base + NH, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              umma_bf16_2cta(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_2cta(tmem_base + NH, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty[stage]);
           }
-          umma_commit_2cta(&empty[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(tfull);
+        if (elect_one_sync()) umma_commit_2cta(tfull);
+        __syncwarp();
         aphase ^= 1;
       }
     }

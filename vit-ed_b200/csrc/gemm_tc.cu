@@ -286,7 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // warp-uniform loop, tcgen05 instructions predicated on one elected lane (see elect_one_sync)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       if (kResident && tile0 < m_blks) mbar_wait(pfull, 0, 22);
@@ -301,15 +302,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(kResident ? smem_u32(sPanel + kb * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
           }
-          umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        if (elect_one_sync()) umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -454,7 +459,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop (warp-uniform control flow and descriptors); only the tcgen05 instructions are
+    // predicated on one elected lane.
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -467,13 +474,17 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = umma_desc_sw128(a_addr);
           const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2cta(&empty[stage]);   // frees this stage in BOTH CTAs
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty[stage]);   // frees this stage in BOTH CTAs
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(&tfull[as]);        // accumulators complete in BOTH CTAs
+        if (elect_one_sync()) umma_commit_2cta(&tfull[as]);        // accumulators complete in BOTH CTAs
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
