@@ -56,7 +56,8 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
   uint64_t* o_full = s_full + C::NT;           // O ready in TMEM (commit)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_full + C::NT);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (keeps MMA operands in uniform registers)
   const int quarter = warp & 3, group = warp >> 2;
   const int H = a.n_heads;
   const int n_my = (n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -121,24 +122,25 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
     const float sl2 = a.scale * kLog2e;
     const int row = quarter * 32 + lane;                  // query row of the unit's tile
     const bool warp_active = quarter < 2 || a.q_has_cls;  // quarter 2 only carries the class-token query (row 64)
-    const bool leader = quarter == 0 && lane == 0;
     const uint32_t t_col = tmem_base + group * C::TCOLS;
     const uint32_t t_stage = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t idesc_qk = umma_idesc_bf16(128, NK);
     const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
-    const int pv_steps = NK / 16;
-    auto issue_qk = [&](int i) {      // leader only: S(stage) = Q K^T of local unit i
+    auto issue_qk = [&](int i) {      // first warp of the group, warp-uniform: S(stage) = Q K^T of local unit i
       const int s = i % C::NS;
       mbar_wait(&full[s], (uint32_t)(i / C::NS) & 1u, 51);
       tc_fence_after();
       const uint32_t q_addr = smem_u32(smem + s * C::STAGE);
       const uint64_t dq = umma_desc_sw(q_addr, 64);
       const uint64_t dk = umma_desc_sw(q_addr + C::TB, 64);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int k = 0; k < C::HD / 16; ++k) umma_bf16(t_col, dq + 2 * k, dk + 2 * k, idesc_qk, k);
-      umma_commit(&s_full[group]);
+        for (int k = 0; k < C::HD / 16; ++k) umma_bf16(t_col, dq + 2 * k, dk + 2 * k, idesc_qk, k);
+        umma_commit(&s_full[group]);
+      }
+      __syncwarp();
     };
-    if (leader && group < n_my) issue_qk(group);
+    if (quarter == 0 && group < n_my) issue_qk(group);
     uint32_t ph = 0;
     for (int i = group; i < n_my; i += C::NT) {
       const int u = (int)blockIdx.x + i * (int)gridDim.x;
@@ -189,14 +191,24 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
       }
       tc_fence_before();
       asm volatile("bar.sync %0, 96;" ::"r"(group + 1) : "memory");   // the group's three warps: all of P is in TMEM
-      if (leader) {
+      if (quarter == 0) {     // the group's first warp issues (warp-uniform code, one elected lane)
         tc_fence_after();
         const int s = i % C::NS;
-        const uint32_t v_addr = smem_u32(smem + s * C::STAGE + 2 * C::TB);
-        for (int k = 0; k < pv_steps; ++k)   // 16 keys per step = two 8-key groups of 512 B
-          umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, umma_desc_sw(v_addr + k * 1024, 64), idesc_pv, k);
-        umma_commit(&empty[s]);
-        umma_commit(&o_full[group]);
+        const uint64_t dv = umma_desc_sw(smem_u32(smem + s * C::STAGE + 2 * C::TB), 64);
+        if (elect_one_sync()) {
+          if (NK == 80) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k)   // 16 keys per step = two 8-key groups of 512 B = +64 in the (addr >> 4) field
+              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&o_full[group]);
+        }
+        __syncwarp();
         if (i + C::NT < n_my) issue_qk(i + C::NT);
       }
       __syncwarp();
