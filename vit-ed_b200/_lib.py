@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvited_b200.so")
+# VITED_LIB: path override used by tools/ to A/B differently built libraries (still the same C-ABI, still no fallback)
+LIB_PATH = os.environ.get("VITED_LIB") or os.path.join(_HERE, "lib", "libvited_b200.so")
 
 
 class VitedError(RuntimeError):

@@ -252,100 +252,87 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
 
 // =====================================================================================================================
 // attn_l64_kernel -- Hisfrag model: long sequences (patch tokens a multiple of 256 queries / 128 keys), head_dim 64.
-//   Work item = (sequence, head, 256 patch queries): two softmax groups (128 query rows, 8 warps: two threads per row)
-//   share one ring of 128-key K/V tiles. Per group and key tile: S = Q K^T (128x128, fp32 in TMEM) -> the row's two
-//   threads take the row max, exponentiates (ex2), writes P back to TMEM as packed bf16 over S -> O += P V with P read from TMEM and V
-//   consumed in place as an MN-major operand. The group's leader thread issues PV(t) and then QK^T(t+1) back to back,
-//   so while one group runs its softmax the tensor core works for the other (ping-pong).
-//   Online softmax with a LAZY rescale: the running max only moves when a tile exceeds it by more than 2^8; then the
-//   group waits for its previous PV, multiplies its O rows in TMEM (tcgen05.ld / st) and carries on. Probabilities are
-//   therefore <= 256, exact after the final division by the row sum.
-//   The class-token KEY is a last 16-key tile (row 0 real, the others masked); the class-token QUERY is one extra item
-//   per (sequence, head) whose tile has a single live row (group 0 only).
+//   Work item = (sequence, head, 256 patch queries): two softmax groups (128 query rows = 4 warps, one thread per row)
+//   share one ring of 128-key K/V stages. A group consumes a stage as two 64-key HALF TILES with two score buffers in
+//   TMEM: while its threads run the softmax of half tile u (tcgen05.ld -> row max -> ex2 -> packed bf16 P written back
+//   over S with tcgen05.st), the tensor pipe executes PV(u-1) and QK^T(u+1), issued earlier by the MMA warp -- the MMA
+//   round trip is hidden behind the other buffer's softmax and the group never idles. P feeds the second MMA straight
+//   from TMEM (A operand), V is consumed in place as an MN-major operand.
+//   Online softmax with a LAZY, per-thread rescale: the running max only moves when a half tile exceeds it by more than
+//   2^8; then the thread waits for its group's previous PV, multiplies its own O row in TMEM and carries on.
+//   Probabilities are therefore <= 256, exact after the final division by the row sum.
+//   The class-token KEY is a last 16-key half tile (row 0 real, the others masked); the class-token QUERY is one extra
+//   item per (sequence, head) whose tile has a single live row (group 0 only).
+//   Warps: 0-3 group 0, 4-7 group 1, 8 TMA producer, 9 / 10 MMA issuers of group 0 / 1 (warp-uniform code, elected
+//   lane; warp 9 also owns the TMEM allocation).
 // =====================================================================================================================
 struct L64 {
   static constexpr int HD = 64;
   static constexpr int RB = 128;               // bytes per tile row
   static constexpr int QB = 128 * RB;          // one Q tile
-  static constexpr int KVB = 128 * RB;         // one K or V tile
+  static constexpr int KVB = 128 * RB;         // K (or V) part of a stage: 128 keys
   static constexpr int STAGE = 2 * KVB;        // K, V
-  static constexpr int NS = 5;                 // K/V ring depth
-  static constexpr int THREADS = 576;          // warps 0-7 group 0, 8-15 group 1, 16 TMA producer, 17 TMEM allocator + MMA issuer
-  static constexpr int GCOLS = 256;            // TMEM columns per group: S/P at +0 (128), O at +128 (64)
+  static constexpr int NS = 4;                 // K/V ring depth (stages of 128 keys)
+  static constexpr int THREADS = 352;
+  static constexpr int GCOLS = 256;            // TMEM columns per group: S/P buffers at +0 and +64, O at +128
   static constexpr int OCOL = 128;
-  static constexpr int BAR_BYTES = 256;
-  static constexpr int XCH_BYTES = 2 * 2 * 2 * 128 * 4;   // [max | sum][group][half][row] exchange slots
-  static constexpr int BYTES = 1024 + 2 * QB + NS * STAGE + XCH_BYTES + BAR_BYTES;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int BYTES = 1024 + 4 * QB + NS * STAGE + BAR_BYTES;   // Q double-buffered per group
 };
 
 #ifdef VITED_ATTN_TRACE
-__device__ unsigned long long g_attn_trace[2 * 64 * 12];   // [group][tile][event] clock64 of block 0's leader threads
-#define TRACE(ev) do { if (blockIdx.x == 0 && leader && trace_tile < 64) g_attn_trace[(g * 64 + trace_tile) * 12 + (ev)] = clock64(); } while (0)
+__device__ unsigned long long g_attn_trace[4 * 128 * 4];   // [who][event index][4 timestamps]; who: 0/1 = MMA warp for group 0/1, 2/3 = softmax warp 0 of group 0/1
+#define TR(who, idx, k) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 128) g_attn_trace[((who) * 128 + (idx)) * 4 + (k)] = clock64(); } while (0)
 #else
-#define TRACE(ev) do { } while (0)
+#define TR(who, idx, k) do { } while (0)
 #endif
 
 struct L64Maps {
   CUtensorMap q_tile, q_row, k_tile, k_row, v_tile, v_row;   // boxes {64, 128} and {64, 1}, 128B swizzle
 };
 
-__device__ __forceinline__ uint32_t group_any256(uint32_t pred, int bar_id) {   // OR-reduce a flag over a 256-thread group
-  uint32_t r;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.u32 p, %1, 0;\n\t"
-      "barrier.cta.red.or.pred q, %2, 256, p;\n\t"
-      "selp.u32 %0, 1, 0, q;\n\t"
-      "}\n"
-      : "=r"(r)
-      : "r"(pred), "r"(bar_id)
-      : "memory");
-  return r;
-}
-
 __global__ void __launch_bounds__(L64::THREADS, 1)
 attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   using C = L64;
   extern __shared__ uint8_t attn_tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_tc_smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                          // [2 groups][128 x 128 B]
-  uint8_t* sKV = smem + 2 * C::QB;             // [NS][K tile | V tile]
-  float* sXch = reinterpret_cast<float*>(sKV + C::NS * C::STAGE);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::NS * C::STAGE + C::XCH_BYTES);
+  uint8_t* sQ = smem;                          // [group][buffer][128 x 128 B]
+  uint8_t* sKV = smem + 4 * C::QB;             // [NS][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + C::NS * C::STAGE);
   uint64_t* kv_full = bars;                    // [NS] TMA bytes landed
-  uint64_t* kv_empty = bars + C::NS;           // [NS] both groups' PVs have read the stage (one commit after the last)
-  uint64_t* q_full = bars + 2 * C::NS;         // [2]
-  uint64_t* q_empty = q_full + 2;              // [2] the item's last QK^T has read the Q tile
-  uint64_t* s_full = q_empty + 2;              // [2] S ready in TMEM
-  uint64_t* o_done = s_full + 2;               // [2] PV finished (O consistent)
-  uint64_t* exp_done = o_done + 2;             // [2] the group has finished the exp phase of a tile (ping-pong order; 8 warps)
-  uint64_t* p_ready = exp_done + 2;            // [2] the group's probabilities are in TMEM (8 warps)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(p_ready + 2);
+  uint64_t* kv_empty = kv_full + C::NS;        // [NS] both groups' PVs on the stage have finished (2 commits / arrivals)
+  uint64_t* q_full = kv_empty + C::NS;         // [group*2 + buffer]
+  uint64_t* q_empty = q_full + 4;              // [group*2 + buffer] the item's last QK^T has read the Q tile (commit)
+  uint64_t* s_full = q_empty + 4;              // [group*2 + buffer] scores of a half tile are in TMEM (commit)
+  uint64_t* p_ready = s_full + 4;              // [group*2 + buffer] probabilities are in TMEM (4 warps)
+  uint64_t* o_done = p_ready + 4;              // [group] a PV has finished (commit)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int H = a.n_heads;
   const int n_qp = a.nq_patch / 256;                         // 256-query blocks per (sequence, head)
   const int per_bh = n_qp + (a.q_has_cls ? 1 : 0);           // + the class-token item
-  const int n_kt = a.nk_patch / 128;
-  const int T = n_kt + (a.k_has_cls ? 1 : 0);                // key tiles per item (last one = class-token key)
+  const int n_kt = a.nk_patch / 128;                         // full 128-key stages per item
+  const int n_st = n_kt + (a.k_has_cls ? 1 : 0);             // stages per item (the last one = class-token key)
+  const int U = 2 * n_kt + (a.k_has_cls ? 1 : 0);            // half tiles per item
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // stale rows of the ring enter masked score columns / multiply zero probabilities: they only have to be finite
-  for (int i = tid; i < (2 * C::QB + C::NS * C::STAGE) / 16; i += C::THREADS)
+  for (int i = tid; i < (4 * C::QB + C::NS * C::STAGE) / 16; i += C::THREADS)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int s = 0; s < C::NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&q_full[g], 1); mbar_init(&q_empty[g], 1); mbar_init(&s_full[g], 1); mbar_init(&o_done[g], 1);
-      mbar_init(&exp_done[g], 8); mbar_init(&p_ready[g], 8);
+    for (int s = 0; s < C::NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+    for (int j = 0; j < 4; ++j) {
+      mbar_init(&q_full[j], 1); mbar_init(&q_empty[j], 1); mbar_init(&s_full[j], 1); mbar_init(&p_ready[j], 4);
     }
+    mbar_init(&o_done[0], 1); mbar_init(&o_done[1], 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.q_tile);
     tma_prefetch_desc(&maps.k_tile);
     tma_prefetch_desc(&maps.v_tile);
   }
-  if (warp == 17) {
+  if (warp == 9) {
     tmem_alloc(tmem_holder, 512);
     tmem_relinquish();
   }
@@ -354,11 +341,14 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
-  if (warp == 16) {
+  auto is_cls_item = [&](int i) { return (((int)blockIdx.x + i * (int)gridDim.x) % per_bh) == n_qp; };
+
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
-      uint32_t ph = 0, qph = 0;
+      uint32_t ph = 0;
+      uint32_t qn[2] = {0, 0};      // Q tiles loaded so far per group (buffer = n & 1, phase = (n >> 1) & 1)
       for (int i = 0; i < n_my; ++i) {
         const int item = (int)blockIdx.x + i * (int)gridDim.x;
         const int bh = item / per_bh, qp = item - bh * per_bh;
@@ -366,24 +356,19 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;
         const int col = h * C::HD;
         const bool cls_item = qp == n_qp;
-        // Q tiles (group 1 has none in the class-token item)
-        for (int g = 0; g < (cls_item ? 1 : 2); ++g) {
-          mbar_wait(&q_empty[g], qph ^ 1, 60);
+        for (int g = 0; g < (cls_item ? 1 : 2); ++g) {     // group 1 has no queries in the class-token item
+          const int qb = g * 2 + (int)(qn[g] & 1);
+          mbar_wait(&q_empty[qb], ((qn[g] >> 1) & 1) ^ 1, 60);
           if (cls_item) {
-            mbar_arrive_expect_tx(&q_full[g], C::RB);
-            tma_load_2d(&maps.q_row, &q_full[g], sQ + g * C::QB, col, a.n_seq * a.nq_patch + b);
+            mbar_arrive_expect_tx(&q_full[qb], C::RB);
+            tma_load_2d(&maps.q_row, &q_full[qb], sQ + qb * C::QB, col, a.n_seq * a.nq_patch + b);
           } else {
-            mbar_arrive_expect_tx(&q_full[g], C::QB);
-            tma_load_2d(&maps.q_tile, &q_full[g], sQ + g * C::QB, col, b * a.nq_patch + qp * 256 + g * 128);
+            mbar_arrive_expect_tx(&q_full[qb], C::QB);
+            tma_load_2d(&maps.q_tile, &q_full[qb], sQ + qb * C::QB, col, b * a.nq_patch + qp * 256 + g * 128);
           }
+          ++qn[g];
         }
-        if (cls_item) {
-          // keep group 1's Q barriers in step: nothing to load, nothing will be consumed
-          mbar_wait(&q_empty[1], qph ^ 1, 61);
-          mbar_arrive(&q_full[1]);
-        }
-        qph ^= 1;
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t < n_st; ++t) {
           mbar_wait(&kv_empty[stage], ph ^ 1, 62);
           uint8_t* st = sKV + stage * C::STAGE;
           if (t < n_kt) {
@@ -399,229 +384,185 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         }
       }
     }
-  } else if (warp == 17) {
-    // ===================== MMA issuer for both groups (warp-uniform; tcgen05 ops on one elected lane) ==========
-    // The ping-pong order makes the events arrive as A(t) B(t) A(t+1) ...: per group and key tile PV(t) as soon as the
-    // group's probabilities are in TMEM, then QK^T(t+1) right behind it (the tensor pipe runs in issue order, so
-    // S(t+1) may overwrite P(t)).
-    const uint32_t idesc_qk128 = umma_idesc_bf16(128, 128), idesc_qk16 = umma_idesc_bf16(128, 16);
+  } else if (warp >= 9) {
+    // ===================== MMA issuer of group g = warp - 9 (warp-uniform; tcgen05 ops on one elected lane) ==========
+    // A lean linear program per item: QK^T(0), QK^T(1), then for every half tile u: PV(u) as soon as P(u) is in TMEM
+    // and QK^T(u+2) right behind it into the same score buffer (the tensor pipe runs in issue order). This warp is on
+    // the critical path of its group (a single warp executes ~1 dependent instruction per 5 cycles), so it carries
+    // no bookkeeping beyond a few counters: an earlier version with one generic cursor-driven warp for both groups
+    // spent ~1300 cycles per PV + QK^T pair and starved the softmax warps (tools/trace_attn_l64.py).
+    const int g = warp - 9;
+    const uint32_t idesc_qk64 = umma_idesc_bf16(128, 64), idesc_qk16 = umma_idesc_bf16(128, 16);
     const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
-    int stage = 0;
-    uint32_t kv_ph = 0, q_ph = 0, p_ph0 = 0, p_ph1 = 0;   // (group 1 skips the class-token items: own phase)
-    auto issue_qk = [&](int g, uint32_t k_addr, bool cls_tile, bool last) {
-      const uint64_t dq = umma_desc_sw128(smem_u32(sQ + g * C::QB));
-      const uint64_t dk = umma_desc_sw128(k_addr);
-      const uint32_t t_col = tmem_base + g * C::GCOLS;
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int k = 0; k < C::HD / 16; ++k)
-          umma_bf16(t_col, dq + 2 * k, dk + 2 * k, cls_tile ? idesc_qk16 : idesc_qk128, k);
-        umma_commit(&s_full[g]);
-        if (last) umma_commit(&q_empty[g]);
-      }
-      __syncwarp();
-    };
+    const uint32_t t_col = tmem_base + g * C::GCOLS;
+    const uint32_t kv_base = smem_u32(sKV);
+    int stage = 0, qs = 0;          // K/V stage of the next PV / of the next QK^T
+    uint32_t kv_ph = 0, qph = 0;
+    uint32_t qn = 0, j = 0, pj = 0; // Q tiles consumed, QK^T issued, PV issued
     for (int i = 0; i < n_my; ++i) {
-      const int item = (int)blockIdx.x + i * (int)gridDim.x;
-      const bool cls_item = (item % per_bh) == n_qp;
-      const int nact = cls_item ? 1 : 2;          // group 1 has no queries in the class-token item
-      mbar_wait(&q_full[0], q_ph, 66);
-      mbar_wait(&q_full[1], q_ph, 66);
-      q_ph ^= 1;
-      if (cls_item) {
-        if (elect_one_sync()) mbar_arrive(&q_empty[1]);
-        __syncwarp();
-      }
-      mbar_wait(&kv_full[stage], kv_ph, 63);
-      tc_fence_after();
-      for (int g = 0; g < nact; ++g) issue_qk(g, smem_u32(sKV + stage * C::STAGE), n_kt == 0, T == 1);
-      for (int t = 0; t < T; ++t) {
-        const bool cls_tile = t >= n_kt;
-        const uint32_t k_addr = smem_u32(sKV + stage * C::STAGE);
-        int nstage = stage + 1;
-        uint32_t nph = kv_ph;
-        if (nstage == C::NS) { nstage = 0; nph ^= 1; }
-        for (int g = 0; g < nact; ++g) {
-          const uint32_t t_col = tmem_base + g * C::GCOLS;
-          mbar_wait(&p_ready[g], g == 0 ? p_ph0 : p_ph1, 64);
-          if (g == 0) p_ph0 ^= 1; else p_ph1 ^= 1;
-          tc_fence_after();
-          const uint64_t dv = umma_desc_sw(k_addr + C::KVB, 128);
-          if (elect_one_sync()) {
-            if (cls_tile) {
-              umma_bf16_ts(t_col + C::OCOL, t_col, dv, idesc_pv, t != 0 ? 1u : 0u);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)   // 16 keys per step = two 8-key groups of 1024 B = +128 in the (addr >> 4) field
-                umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 128 * k, idesc_pv, (t | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(&o_done[g]);
-            if (g == nact - 1) umma_commit(&kv_empty[stage]);   // both groups' PVs have been issued by this thread
-          }
+      if (g == 1 && is_cls_item(i)) {
+        // no queries for this group in the class-token item: release its K/V stages as they land
+        for (int t = 0; t < n_st; ++t) {
+          mbar_wait(&kv_full[stage], kv_ph, 65);
+          if (elect_one_sync()) mbar_arrive(&kv_empty[stage]);
           __syncwarp();
-          if (t + 1 < T) {
-            if (g == 0) {
-              mbar_wait(&kv_full[nstage], nph, 65);
-              tc_fence_after();
-            }
-            issue_qk(g, smem_u32(sKV + nstage * C::STAGE), t + 1 >= n_kt, t + 2 == T);
-          }
+          if (++stage == C::NS) { stage = 0; kv_ph ^= 1; }
         }
-        stage = nstage;
-        kv_ph = nph;
+        qs = stage; qph = kv_ph;
+        continue;
       }
+      const int qb = g * 2 + (int)(qn & 1);
+      mbar_wait(&q_full[qb], (qn >> 1) & 1, 66);
+      const uint64_t dq = umma_desc_sw128(smem_u32(sQ + qb * C::QB));
+      auto issue_qk = [&](int u) {
+        if ((u & 1) == 0) mbar_wait(&kv_full[qs], qph, 63);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_sw128(kv_base + qs * C::STAGE + (u & 1) * (64 * C::RB));
+        const uint32_t t_s = t_col + (j & 1) * 64;
+        const bool cls_tile = u >= 2 * n_kt, last = u + 1 == U;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < C::HD / 16; ++k)
+            umma_bf16(t_s, dq + 2 * k, dk + 2 * k, cls_tile ? idesc_qk16 : idesc_qk64, k);
+          umma_commit(&s_full[g * 2 + (j & 1)]);
+          if (last) umma_commit(&q_empty[qb]);
+        }
+        __syncwarp();
+        ++j;
+        if ((u & 1) == 1 || last) { if (++qs == C::NS) { qs = 0; qph ^= 1; } }
+      };
+      issue_qk(0);
+      if (U > 1) issue_qk(1);
+      for (int u = 0; u < U; ++u) {
+        const bool cls_tile = u >= 2 * n_kt;
+        const bool stage_done = (u & 1) == 1 || u + 1 == U;
+        const uint32_t t_p = t_col + (pj & 1) * 64;
+        mbar_wait(&p_ready[g * 2 + (pj & 1)], (pj >> 1) & 1, 64);
+        tc_fence_after();
+        const uint64_t dv = umma_desc_sw(kv_base + stage * C::STAGE + C::KVB + (u & 1) * (64 * C::RB), 128);
+        if (elect_one_sync()) {
+          if (cls_tile) {
+            umma_bf16_ts(t_col + C::OCOL, t_p, dv, idesc_pv, u != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 16 keys per step = two 8-key groups of 1024 B = +128 in the (addr >> 4) field
+              umma_bf16_ts(t_col + C::OCOL, t_p + 8 * k, dv + 128 * k, idesc_pv, (u | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&o_done[g]);
+          if (stage_done) umma_commit(&kv_empty[stage]);
+        }
+        __syncwarp();
+        ++pj;
+        if (stage_done) { if (++stage == C::NS) { stage = 0; kv_ph ^= 1; } }
+        if (u + 2 < U) issue_qk(u + 2);
+      }
+      ++qn;
     }
-  } else if (warp < 16) {
-    // ===================== softmax group g: 128 query rows x 2 column halves (8 warps) =====================
-    // thread (row, half) owns score columns [64*half, 64*half+64) of its row, the matching 32 packed P columns and 32
-    // of the 64 output columns; the two halves of a row exchange their partial max / sum through shared memory.
-    const int g = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+  } else {
+    // ===================== softmax group g = warp / 4: one thread per query row =====================
+    const int g = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const bool leader = half == 0 && quarter == 0 && lane == 0; (void)leader;
     const float sl2 = a.scale * kLog2e;
     const uint32_t t_col = tmem_base + g * C::GCOLS;
     const uint32_t t_row = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
-    float* my_x = sXch + (g * 2 + half) * 128 + row;          // this thread's exchange slot
-    float* peer_x = sXch + (g * 2 + (half ^ 1)) * 128 + row;  // the other half of the same row
-    uint32_t s_ph = 0;
-    uint32_t pv_count = 0;      // PVs issued for this group so far (o_done phase bookkeeping)
-    // Ping-pong: the exp phases of the two groups strictly alternate (A0 B0 A1 B1 ...), so while one group keeps the
-    // MUFU pipe busy the tensor pipe runs the other group's PV / QK^T. Without the order both groups fall into lock
-    // step (exponentiate together, then wait for the tensor pipe together).
-    uint32_t n_exp = 0;         // exp phases (tiles) this group has been through
-    int trace_tile = 0; (void)trace_tile;
-    auto wait_turn = [&]() {
-      if (g == 0) { if (n_exp > 0) mbar_wait(&exp_done[1], (n_exp - 1) & 1u, 72); }
-      else mbar_wait(&exp_done[0], n_exp & 1u, 73);
-    };
-    // running max moved by more than the threshold somewhere in the group: wait for the previous PV, rescale own O columns
-    auto rescale = [&](bool need, float mt, float& m, float& l) {
-      mbar_wait(&o_done[g], (pv_count - 1) & 1u, 68);
+    uint32_t j = 0;        // half tiles processed by this group so far (score buffer = j & 1, phase = (j >> 1) & 1)
+    // the running max moved by more than the threshold: wait for the group's previous PV, rescale the own O row
+    auto rescale = [&](float mt, float& m, float& l) {
+      // (S(j) being ready implies PV(j-2) is complete, so o_done is at most one phase behind here: no aliasing)
+      mbar_wait(&o_done[g], (j - 1) & 1u, 68);
       tc_fence_after();
-      if (need) {
-        const float f = ex2_ftz(m - mt);
-        l *= f;
-        m = mt;
+      const float f = ex2_ftz(m - mt);
+      l *= f;
+      m = mt;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t ov[32];
-        tmem_ld_32x32b_x32(t_row + C::OCOL + 32 * half, ov);
+        tmem_ld_32x32b_x32(t_row + C::OCOL + 32 * c, ov);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ov[j] = __float_as_uint(__uint_as_float(ov[j]) * f);
-        tmem_st_32x32b_x32(t_row + C::OCOL + 32 * half, ov);
+        for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
+        tmem_st_32x32b_x32(t_row + C::OCOL + 32 * c, ov);
       }
     };
-
     for (int i = 0; i < n_my; ++i) {
       const int item = (int)blockIdx.x + i * (int)gridDim.x;
       const int bh = item / per_bh, qp = item - bh * per_bh;
       const int b = bh / H, h = bh - b * H;
       const bool cls_item = qp == n_qp;
-      if (cls_item && g == 1) {
-        // no queries for this group: T empty exp phases keep the ping-pong order in step
-        for (int t = 0; t < T; ++t) {
-          wait_turn();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&exp_done[1]);
-          ++n_exp;
-        }
-        continue;
-      }
+      if (cls_item && g == 1) continue;
       float m = -INFINITY, l = 0.f;
-      for (int t = 0; t < T; ++t) {
-        const bool cls_tile = t >= n_kt;
-        mbar_wait(&s_full[g], s_ph, 67);
-        s_ph ^= 1;
+      for (int u = 0; u < U; ++u, ++j) {
+        const int sb = g * 2 + (int)(j & 1);
+        const uint32_t t_s = t_row + (j & 1) * 64;
+        if (quarter == 0) TR(2 + g, j, 0);
+        mbar_wait(&s_full[sb], (j >> 1) & 1u, 67);
+        if (quarter == 0) TR(2 + g, j, 1);
         tc_fence_after();
-        TRACE(0);
-        if (!cls_tile) {
-          uint32_t v0[32], v1[32];   // (two plain arrays: taking the address of one 64-entry array forces it into local memory)
-          tmem_ld_32x32b_x32(t_row + 64 * half, v0);
-          tmem_ld_32x32b_x32(t_row + 64 * half + 32, v1);
+        if (u < 2 * n_kt) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32b_x32(t_s, v0);
+          tmem_ld_32x32b_x32(t_s + 32, v1);
           tmem_ld_wait();
-          TRACE(1);
           float mx[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mx[j] = fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j]));
+          for (int e = 0; e < 4; ++e) mx[e] = fmaxf(__uint_as_float(v0[e]), __uint_as_float(v1[e]));
 #pragma unroll
-          for (int j = 4; j < 32; j += 4)
+          for (int c = 4; c < 32; c += 4)
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v0[j + e]), __uint_as_float(v1[j + e])));
-          float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
-          *my_x = mt;
-          // lazy rescale: the running max only moves when a tile exceeds it by more than 8 (log2 units). The vote on
-          // the half-row maxima is exact (the row max exceeds the bound iff one of its halves does) and doubles as the
-          // barrier that publishes the partial maxima.
-          const uint32_t any = group_any256((t > 0 && mt > m + 8.f) ? 1u : 0u, 3 + g);
-          mt = fmaxf(mt, *peer_x);
-          if (t == 0) m = mt;
-          else if (any) rescale(mt > m + 8.f, mt, m, l);
-          TRACE(2);
-          wait_turn();
-          TRACE(3);
+              mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v0[c + e]), __uint_as_float(v1[c + e])));
+          const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
+          if (u == 0) m = mt;
+          else if (mt > m + 8.f) rescale(mt, m, l);      // lazy: probabilities stay <= 2^8 otherwise
           const float mneg = -m;
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
           {
             uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float p0 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j]), sl2, mneg));
-              const float p1 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j + 1]), sl2, mneg));
-              sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
-              pk[j] = pack_bf16(p0, p1);
+            for (int e = 0; e < 16; ++e) {
+              const float p0 = ex2_ftz(fmaf(__uint_as_float(v0[2 * e]), sl2, mneg));
+              const float p1 = ex2_ftz(fmaf(__uint_as_float(v0[2 * e + 1]), sl2, mneg));
+              sum[(2 * e) & 3] += p0; sum[(2 * e + 1) & 3] += p1;
+              pk[e] = pack_bf16(p0, p1);
             }
-            tmem_st_32x32b_x16(t_row + 32 * half, pk);
+            tmem_st_32x32b_x16(t_s, pk);
           }
           {
             uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float p0 = ex2_ftz(fmaf(__uint_as_float(v1[2 * j]), sl2, mneg));
-              const float p1 = ex2_ftz(fmaf(__uint_as_float(v1[2 * j + 1]), sl2, mneg));
-              sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
-              pk[j] = pack_bf16(p0, p1);
+            for (int e = 0; e < 16; ++e) {
+              const float p0 = ex2_ftz(fmaf(__uint_as_float(v1[2 * e]), sl2, mneg));
+              const float p1 = ex2_ftz(fmaf(__uint_as_float(v1[2 * e + 1]), sl2, mneg));
+              sum[(2 * e) & 3] += p0; sum[(2 * e + 1) & 3] += p1;
+              pk[e] = pack_bf16(p0, p1);
             }
-            tmem_st_32x32b_x16(t_row + 32 * half + 16, pk);
+            tmem_st_32x32b_x16(t_s + 16, pk);
           }
           l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
-          TRACE(4);
         } else {
-          // class-token key tile: column 0 is the only real key; both halves see it, half 0 owns it
+          // class-token key half tile: column 0 is the only real key
           uint32_t vc[8];
-          tmem_ld_32x32b_x8(t_row, vc);
+          tmem_ld_32x32b_x8(t_s, vc);
           tmem_ld_wait();
           const float mt = __uint_as_float(vc[0]) * sl2;
-          const uint32_t any = group_any256((t > 0 && mt > m + 8.f) ? 1u : 0u, 3 + g);
-          if (t == 0) m = mt;
-          else if (any) rescale(mt > m + 8.f, mt, m, l);
-          wait_turn();
-          if (half == 0) {
-            const float pc = ex2_ftz(mt - m);
-            l += pc;
-            uint32_t pc8[8] = {pack_bf16(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            tmem_st_32x32b_x8(t_row, pc8);
-          }
+          if (u == 0) m = mt;
+          else if (mt > m + 8.f) rescale(mt, m, l);
+          const float pc = ex2_ftz(mt - m);
+          l += pc;
+          uint32_t pc8[8] = {pack_bf16(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          tmem_st_32x32b_x8(t_s, pc8);
         }
         tmem_st_wait();
         tc_fence_before();
-        TRACE(5);
+        if (quarter == 0) TR(2 + g, j, 2);
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&p_ready[g]);      // 8 warps: all of P (and any rescaled O) is in TMEM -> the MMA warp issues PV
-          mbar_arrive(&exp_done[g]);     // 8 warps: this group's exp phase is over -> the other group's turn
-        }
-        ++n_exp;
-        ++pv_count;
-        TRACE(6);
-        TRACE(7);
-        ++trace_tile;
+        if (lane == 0) mbar_arrive(&p_ready[sb]);   // 4 warps: P (and any rescaled O row) is in TMEM -> PV may be issued
       }
-      // ---- item epilogue: O / l -> bf16 -> global (each thread writes its 32 of the row's 64 columns) ----
-      my_x[512] = l;        // separate slots: a fast thread may already publish the next item's first max
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
-      l += peer_x[512];
-      mbar_wait(&o_done[g], (pv_count - 1) & 1u, 71);
+      // ---- item epilogue: O / l -> bf16 -> global ----
+      // When the last scores arrived only PV(j-3) was known to be complete, so o_done may still be two phases behind:
+      // a single parity wait would alias. Wait for PV(j-2), then PV(j-1) (j >= 2: every item has >= 2 half tiles).
+      mbar_wait(&o_done[g], (j - 2) & 1u, 70);
+      mbar_wait(&o_done[g], (j - 1) & 1u, 71);
       tc_fence_after();
       {
         const float inv = 1.f / l;
@@ -629,29 +570,32 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         bool valid;
         if (cls_item) { valid = row == 0; orow = (size_t)a.n_seq * a.nq_patch + b; }
         else { valid = true; orow = (size_t)b * a.nq_patch + qp * 256 + g * 128 + row; }
-        uint4* dst = reinterpret_cast<uint4*>(a.o + orow * a.o_ld + h * C::HD + 32 * half);
-        uint32_t ov[32];
-        tmem_ld_32x32b_x32(t_row + C::OCOL + 32 * half, ov);
-        tmem_ld_wait();
-        tc_fence_before();   // (the next item's first PV overwrites O only after every warp has published its next P)
-        if (valid) {
+        uint4* dst = reinterpret_cast<uint4*>(a.o + orow * a.o_ld + h * C::HD);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 w;
-            w.x = pack_bf16(__uint_as_float(ov[8 * j + 0]) * inv, __uint_as_float(ov[8 * j + 1]) * inv);
-            w.y = pack_bf16(__uint_as_float(ov[8 * j + 2]) * inv, __uint_as_float(ov[8 * j + 3]) * inv);
-            w.z = pack_bf16(__uint_as_float(ov[8 * j + 4]) * inv, __uint_as_float(ov[8 * j + 5]) * inv);
-            w.w = pack_bf16(__uint_as_float(ov[8 * j + 6]) * inv, __uint_as_float(ov[8 * j + 7]) * inv);
-            dst[j] = w;
+        for (int c = 0; c < 2; ++c) {
+          uint32_t ov[32];
+          tmem_ld_32x32b_x32(t_row + C::OCOL + 32 * c, ov);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              uint4 w;
+              w.x = pack_bf16(__uint_as_float(ov[8 * e + 0]) * inv, __uint_as_float(ov[8 * e + 1]) * inv);
+              w.y = pack_bf16(__uint_as_float(ov[8 * e + 2]) * inv, __uint_as_float(ov[8 * e + 3]) * inv);
+              w.z = pack_bf16(__uint_as_float(ov[8 * e + 4]) * inv, __uint_as_float(ov[8 * e + 5]) * inv);
+              w.w = pack_bf16(__uint_as_float(ov[8 * e + 6]) * inv, __uint_as_float(ov[8 * e + 7]) * inv);
+              dst[4 * c + e] = w;
+            }
           }
         }
+        tc_fence_before();   // (the next item's first PV overwrites O only after every warp has published its next P)
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -722,8 +666,9 @@ int attention_tc(const AttnArgs& a, cudaStream_t stream) {
 
 }  // namespace vited
 
+
 #ifdef VITED_ATTN_TRACE
 extern "C" __attribute__((visibility("default"))) int vited_debug_attn_trace(unsigned long long* out) {
-  return (int)cudaMemcpyFromSymbol(out, vited::g_attn_trace, sizeof(unsigned long long) * 2 * 64 * 12);
+  return (int)cudaMemcpyFromSymbol(out, vited::g_attn_trace, sizeof(unsigned long long) * 4 * 128 * 4);
 }
 #endif

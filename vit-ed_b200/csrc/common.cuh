@@ -108,6 +108,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or the hint, in
 // ns, expires) instead of re-polling every ~80 cycles. Polling warps otherwise flood the MIO queue (ncu: MUFU / UTCMMA
 // issue of the working warps stalls on `mio_throttle` behind tens of millions of SYNCS try-waits).
+#ifndef VITED_MBAR_SUSPEND_NS
+#define VITED_MBAR_SUSPEND_NS 20000
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -117,7 +120,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       "selp.u32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)VITED_MBAR_SUSPEND_NS)
       : "memory");
   return ok;
 }
