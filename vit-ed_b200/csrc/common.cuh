@@ -298,6 +298,17 @@ __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* tm, uint64_t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// Same, multicast: the box lands at this shared-memory offset in every CTA of `cta_mask` (cluster ranks) and each
+// destination counts the bytes on the barrier at this offset in ITS pair's leader CTA (the peer bit is relative to the
+// destination). Used to share one weight stream between the two CTA pairs of a 4-CTA cluster.
+__device__ __forceinline__ void tma_load_2d_2cta_mc(const CUtensorMap* tm, uint64_t* bar, void* smem_dst, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+      "h"(cta_mask)
+      : "memory");
+}
 // D[tmem, both CTAs] (+)= A * B with M = 256 split over the pair; issued by ONE thread of the leader CTA
 __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
@@ -311,6 +322,13 @@ __device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a,
       : "memory");
 }
 // arrive on the mbarrier at this shared-memory offset in BOTH CTAs once the issued cta_group::2 MMAs have completed
+__device__ __forceinline__ void umma_commit_2cta_mask(uint64_t* bar, uint16_t mask) {   // explicit cluster-rank mask
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
   const uint16_t mask = 3;
   asm volatile(

@@ -535,6 +535,198 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// =====================================================================================================================
+// Quad variant: a cluster of FOUR CTAs = two cta_group::2 pairs that compute two different 256-row tiles against the
+// SAME weight tile. Every GEMM of the step moves 7.5-9.4 TB/s through L2 (profiles/): the weight tile is re-read from L2
+// for every 256 output rows. Here each CTA fetches only a QUARTER of the weight tile per k-block and TMA-multicasts it
+// to the CTA with the same pair rank in the other pair, so one L2 read serves 512 output rows. The shared stage is
+// released only when BOTH pairs' MMAs have read it (the leaders' commits are multicast to all four CTAs).
+// =====================================================================================================================
+template <int BN, int ACT>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(PairCfg<BN>::kThreads, 1)
+gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K) {
+  using Cfg = PairCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiWarps = Cfg::kEpiWarps;
+  constexpr uint32_t BQ_BYTES = Cfg::BH_BYTES / 2;   // the quarter of the weight tile this CTA fetches
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sC = smem + kStages * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + Cfg::C_BYTES);
+  uint64_t* full = bars;                     // pair leader: TMA bytes of both CTAs of the pair
+  uint64_t* empty = bars + kStages;          // per CTA: BOTH pair leaders' commits (count 2)
+  uint64_t* tfull = bars + 2 * kStages;      // per CTA: own pair's commit
+  uint64_t* tempty = bars + 2 * kStages + 2; // pair leader: epilogue warps of both CTAs of the pair
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank4 = cluster_ctarank();
+  const uint32_t r = rank4 & 1, p = rank4 >> 1;     // rank inside the pair, pair inside the cluster
+  const int cluster = (int)(blockIdx.x >> 2);
+  const int num_clusters = (int)(gridDim.x >> 2);
+
+  const int m2_blks = (M + 2 * BM - 1) / (2 * BM);
+  const int m4_blks = (m2_blks + 1) / 2;            // the two pairs of a cluster take 256-row blocks 2*m4 and 2*m4 + 1
+  const int n_blks = (N + BN - 1) / BN;
+  const int num_tiles = m4_blks * n_blks;           // (an odd tail block is computed on zero-filled rows, stores clipped)
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 2);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc_2cta(tmem_holder, Cfg::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer (all four CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const uint16_t mc_mask = (uint16_t)((1u << r) | (1u << (r + 2)));   // same pair rank in both pairs
+      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+        const int m4 = tile / n_blks, n_blk = tile % n_blks;
+        const int row0 = (2 * m4 + (int)p) * 2 * BM + (int)r * BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1, 10);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+          if (r == 0) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(&tmA, &full[stage], a_dst, kb * BK, row0);
+          tma_load_2d_2cta_mc(&tmB, &full[stage], a_dst + Cfg::A_BYTES + p * BQ_BYTES, kb * BK,
+                              n_blk * BN + (int)r * (BN / 2) + (int)p * (BN / 4), mc_mask);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA of each pair; warp-uniform, elected lane) =====================
+    if (r == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty[as], aphase ^ 1, 20);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase, 21);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = umma_desc_sw128(a_addr);
+          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta_mask(&empty[stage], 0xF);   // this pair is done with the stage: tell all four CTAs
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) umma_commit_2cta_mask(&tfull[as], pair_mask);
+        __syncwarp();
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (every CTA, own 128 rows) =====================
+    const int ew = warp - 4;
+    const int q = warp & 3;
+    const int sl = ew >> 2;
+    uint8_t* my_stage = sC + ew * 4096;
+    uint8_t* rowp = my_stage + lane * 128;
+    uint32_t as = 0, aphase = 0;
+    bool store_pending = false;
+    for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
+      const int m4 = tile / n_blks, n_blk = tile % n_blks;
+      const int row0 = (2 * m4 + (int)p) * 2 * BM + (int)r * BM;
+      const int n0 = n_blk * BN + sl * 64;
+      mbar_wait(&tfull[as], aphase, 30);
+      tc_fence_after();
+      uint32_t v0[32], v1[32];
+      const uint32_t taddr = tmem_base + as * BN + sl * 64 + (static_cast<uint32_t>(q * 32) << 16);
+      tmem_ld_32x32b_x32(taddr, v0);
+      tmem_ld_32x32b_x32(taddr + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[as]);
+      if (store_pending) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+      }
+      epilogue_tile<ACT>(v0, v1, bias, n0, N, rowp, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && n0 < N && row0 < M) {
+        tma_store_2d(&tmC, my_stage, n0, row0 + q * 32);
+        tma_store_commit();
+      }
+      store_pending = true;
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, int ACT>
+static int launch_quad(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
+                       int N, int K, cudaStream_t stream) {
+  using Cfg = PairCfg<BN>;
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_quad_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Cfg::SMEM_BYTES));
+    // how many 4-CTA clusters the device can hold at once (GPC sizes that are not multiples of 4 strand a few SMs)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * (g_num_sms / 4));
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    VITED_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, gemm_tc_quad_kernel<BN, ACT>, &cfg));
+    max_clusters = n > 0 ? n : 1;
+  }
+  const int m2_blks = (M + 2 * BM - 1) / (2 * BM);
+  const int tiles = ((m2_blks + 1) / 2) * ((N + BN - 1) / BN);
+  int clusters = max_clusters;
+  if (clusters > g_num_sms / 4) clusters = g_num_sms / 4;
+  if (clusters > tiles) clusters = tiles;
+  gemm_tc_quad_kernel<BN, ACT><<<4 * clusters, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <int BN, int ACT>
 static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                        int N, int K, cudaStream_t stream) {
@@ -592,6 +784,7 @@ int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
               cudaStream_t stream);
 
 static int g_block_n = 0;   // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic tile width (tuning knob)
+static int g_quad = -1;     // VITED_GEMM_QUAD=1 enables the 4-CTA-cluster kernel with multicast weight tiles (large M)
 static int g_pair = -1;     // VITED_GEMM_PAIR=0 disables the CTA-pair (cta_group::2) kernel (used for large M by default)
 static int g_resident = -1; // VITED_GEMM_RESIDENT=1 enables the resident-weights variant (measured slower: off by default)
 
@@ -615,6 +808,8 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
     g_order = o ? atoi(o) : 0;
     const char* pr = getenv("VITED_GEMM_PAIR");
     g_pair = pr ? atoi(pr) : 1;
+    const char* qd = getenv("VITED_GEMM_QUAD");
+    g_quad = qd ? atoi(qd) : 0;
   }
   const int m_blks = (M + BM - 1) / BM;
   // resident weights: K <= 384, 128-wide panels, and enough m-blocks per panel to amortise loading it
@@ -630,6 +825,15 @@ int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, i
   if (make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, BM)) return 1;
   if (g_pair && g_block_n != 128 && m_blks >= 2 * g_num_sms && (N % 256 == 0 || N % 192 == 0)) {
     const int pbn = (g_block_n == 192 || g_block_n == 256) ? g_block_n : (N % 256 == 0 ? 256 : 192);
+    if (g_quad && m_blks >= 4 * g_num_sms) {
+      if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)pbn / 4)) return 1;
+      if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
+      if (pbn == 256)
+        return act == ACT_GELU ? launch_quad<256, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                               : launch_quad<256, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+      return act == ACT_GELU ? launch_quad<192, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
+                             : launch_quad<192, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
+    }
     if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)pbn / 2)) return 1;
     if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
     if (pbn == 256)
