@@ -30,6 +30,23 @@ gemm(1152, 384, 0)
 gemm(1536, 384, 1)
 gemm(384, 1536, 0)
 gemm(384, 384, 0)
+
+
+def gemm_ln(K):
+    A = torch.randn(M, K, device='cuda').bfloat16()
+    W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).bfloat16()
+    b = torch.randn(384, device='cuda')
+    xx = torch.randn(M, 384, device='cuda')
+    lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
+    hh = torch.empty(M, 384, dtype=torch.bfloat16, device='cuda')
+    for _ in range(reps):
+        L.check(L.lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), xx.data_ptr(), lw.data_ptr(), lb.data_ptr(),
+                                             hh.data_ptr(), M, 384, K, 1e-6, None), 'gemm_ln')
+    torch.cuda.synchronize()
+
+
+gemm_ln(384)
+gemm_ln(1536)
 P, H, hd, Np = 4032, 12, 32, 64
 qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
 o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
