@@ -184,11 +184,15 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld_32x32b_x32(tlane + j * 32, acc);
         tmem_ld_wait();
         mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
-        uint8_t* rowp = xbox + (g & 1) * Cfg::XBOX + lane * 128;
+        const uint8_t* rowp = xbox + (g & 1) * Cfg::XBOX + lane * 128;
+        // the updated row leaves through the warp's second staging box (idle during this pass), NOT through the box it
+        // came in: the in-box can then be refilled as soon as the warp has read it, without waiting for a store
+        if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the out-box
+        __syncwarp();
+        uint8_t* outp = hbox + lane * 128;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          float4* px = reinterpret_cast<float4*>(rowp + ((i ^ sw) << 4));
-          const float4 xv = *px;
+          const float4 xv = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
           const float4 b4 = *reinterpret_cast<const float4*>(sBias + col0 + 4 * i);
           float4 v;
           v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
@@ -199,18 +203,17 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const float d0 = v.x - c0, d1 = v.y - c0, d2 = v.z - c0, d3 = v.w - c0;
           s += (d0 + d1) + (d2 + d3);
           ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
-          *px = v;
+          *reinterpret_cast<float4*>(outp + ((i ^ sw) << 4)) = v;
           acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
           acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
         }
         tmem_st_32x32b_x32(tlane + j * 32, acc);
         fence_proxy_async_smem();
-        __syncwarp();
+        __syncwarp();                             // every lane has read the in-box and written the out-box
         if (lane == 0) {
-          tma_store_2d(&tmX, xbox + (g & 1) * Cfg::XBOX, col0, row0);
+          issue_x(g + 2);                         // refill the in-box right away
+          tma_store_2d(&tmX, hbox, col0, row0);
           tma_store_commit();
-          tma_store_wait_read();      // the box is free again once the store has read it
-          issue_x(g + 2);
         }
       }
       tmem_st_wait();
