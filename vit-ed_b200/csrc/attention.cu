@@ -399,6 +399,10 @@ int attention_cls(const AttnArgs& a, cudaStream_t stream) {
   VITED_CHECK(a.head_dim == 32 || a.head_dim == 64, "attention_cls: head_dim %d not supported (32 or 64)", a.head_dim);
   VITED_CHECK(a.q_has_cls, "attention_cls: the query sequences have no class token");
   if (a.n_seq == 0) return 0;
+  {
+    const char* e = getenv("VITED_ATTN_TC");
+    if ((!e || atoi(e) != 0) && attention_tc_cls_supported(a)) return attention_tc_cls(a, stream);
+  }
   return attention_launch(a, 1, stream);
 }
 

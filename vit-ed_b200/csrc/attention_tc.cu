@@ -45,7 +45,7 @@ struct P64Maps {
 };
 
 __global__ void __launch_bounds__(P64::THREADS, 1)
-attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
+attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, int cls_only) {
   using C = P64;
   extern __shared__ uint8_t attn_tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_tc_smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,9 +100,10 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
         const int col = h * C::HD;
         mbar_wait(&empty[s], ph ^ 1, 50);
         uint8_t* st = smem + s * C::STAGE;
-        const uint32_t bytes = 3 * 64 * C::RB + (a.q_has_cls ? C::RB : 0) + (a.k_has_cls ? 2 * C::RB : 0);
+        // cls_only (last decoder layer, only the class-token row reaches the head): the 64 patch queries are not loaded
+        const uint32_t bytes = (cls_only ? 2 : 3) * 64 * C::RB + (a.q_has_cls ? C::RB : 0) + (a.k_has_cls ? 2 * C::RB : 0);
         mbar_arrive_expect_tx(&full[s], bytes);
-        tma_load_2d(&maps.q_tile, &full[s], st, col, b * 64);
+        if (!cls_only) tma_load_2d(&maps.q_tile, &full[s], st, col, b * 64);
         if (a.q_has_cls) tma_load_2d(&maps.q_row, &full[s], st + 64 * C::RB, col, a.n_seq * 64 + b);
         tma_load_2d(&maps.k_tile, &full[s], st + C::TB, col, kvb * 64);
         tma_load_2d(&maps.v_tile, &full[s], st + 2 * C::TB, col, kvb * 64);
@@ -121,7 +122,8 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
     // scores are ready by the time this unit's output has been written.
     const float sl2 = a.scale * kLog2e;
     const int row = quarter * 32 + lane;                  // query row of the unit's tile
-    const bool warp_active = quarter < 2 || a.q_has_cls;  // quarter 2 only carries the class-token query (row 64)
+    // quarter 2 only carries the class-token query (row 64); in cls_only mode it is the only live row
+    const bool warp_active = quarter < 2 ? !cls_only : a.q_has_cls != 0;
     const uint32_t t_col = tmem_base + group * C::TCOLS;
     const uint32_t t_stage = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t idesc_qk = umma_idesc_bf16(128, NK);
@@ -221,7 +223,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units) {
         const float inv = 1.f / l;
         size_t orow;
         bool valid = true;
-        if (row < 64) orow = (size_t)b * 64 + row;
+        if (row < 64) { orow = (size_t)b * 64 + row; valid = !cls_only; }
         else if (row == 64 && a.q_has_cls) orow = (size_t)a.n_seq * 64 + b;
         else { valid = false; orow = 0; }
         if (valid) {
@@ -636,9 +638,22 @@ static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream);
+
 int attention_tc(const AttnArgs& a, cudaStream_t stream) {
   VITED_CHECK(attention_tc_supported(a), "attention_tc: unsupported shape");
   if (l64_shape(a)) return attention_tc_l64(a, stream);
+  return attention_tc_p64(a, 0, stream);
+}
+
+// class-token query only (last decoder layer), puzzle shape
+bool attention_tc_cls_supported(const AttnArgs& a) { return a.n_heads >= 1 && p64_shape(a) && a.q_has_cls; }
+int attention_tc_cls(const AttnArgs& a, cudaStream_t stream) {
+  VITED_CHECK(attention_tc_cls_supported(a), "attention_tc_cls: unsupported shape");
+  return attention_tc_p64(a, 1, stream);
+}
+
+static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream) {
   const size_t units = (size_t)a.n_seq * a.n_heads;
   VITED_CHECK(units < ((size_t)1 << 31), "attention_tc: too many work units");
   static int sms = 0;
@@ -659,7 +674,7 @@ int attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_bf16_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 64, 64)) return 1;
   if (make_tmap_bf16_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 1, 64)) return 1;
   const unsigned grid = (unsigned)(units < (size_t)sms ? units : (size_t)sms);
-  attn_p64_kernel<<<grid, P64::THREADS, P64::BYTES, stream>>>(a, maps, (int)units);
+  attn_p64_kernel<<<grid, P64::THREADS, P64::BYTES, stream>>>(a, maps, (int)units, cls_only);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }
