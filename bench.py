@@ -217,7 +217,7 @@ def workload_config(n_gpus):
     if n_gpus == 1:
         return {'workload': 'configs[1]: puzzle all-pairs scoring, one synthetic 540-piece puzzle (18x30) at 64px, '
                             'erosion 7%, 4-bin patch8 model, 291060 ordered pairs per step',
-                'pairs_per_step': 540 * 539, 'l2': 'per-step working set (~3 GB of activations per 4032-pair chunk) >> 126 MB L2'}
+                'pairs_per_step': 540 * 539, 'l2': 'per-step working set (~5 GB of activations per 8065-pair chunk) >> 126 MB L2'}
     return {'workload': f'configs[2]: 1000-piece puzzles (25x40) at 64px, erosion 14%, {UNITS_PER_GPU} (puzzle,row) units '
                         f'per GPU x {n_gpus} GPUs, one NCCL all-gather of the score blocks per step',
             'pairs_per_step': n_gpus * UNITS_PER_GPU * 999, 'parallelism': f'grid rows sharded x{n_gpus}',

@@ -59,7 +59,7 @@ enum {
   VITED_OPT_GEMM_IMPL = 0,      /* 0 = tcgen05/TMA kernel (default), 1 = SIMT debugging reference kernel        */
   VITED_OPT_ATTN_IMPL = 1,      /* 0 = default (tcgen05/TMEM kernel where the shape has one, else the mma.sync flash
                                    kernel), 1 = SIMT debugging reference kernel, 2 = mma.sync flash kernel always   */
-  VITED_OPT_CHUNK_ROWS = 2,     /* target token rows per decoder chunk (default 262144)                          */
+  VITED_OPT_CHUNK_ROWS = 2,     /* target token rows per decoder chunk (default 524288)                          */
   VITED_OPT_CACHE_LAYER0 = 3,   /* 1 (default) = run decoder layer 0's self-attention once per item, not per pair */
   VITED_OPT_PROFILE = 4,        /* 1 = record a CUDA event before every launch (see vited_profile_json); default 0   */
   VITED_OPT_PRUNE_TAIL = 5,     /* 1 (default) = in the last decoder layer run everything after the K/V projection of

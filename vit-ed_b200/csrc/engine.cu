@@ -90,7 +90,7 @@ struct vited_engine {
   int loaded = 0;
   // options
   int gemm_impl = IMPL_FAST, attn_impl = IMPL_FAST;
-  int64_t chunk_rows = 262144;
+  int64_t chunk_rows = 524288;   // measured: 262144 -> 524288 rows per chunk +4.7 % (fewer launch tails), no gain beyond
   int cache_layer0 = 1;
   int prune_tail = 1;   // last decoder layer: only the class-token row continues past self-attention
   int fuse_ln = 1;      // residual + LayerNorm in the epilogue of the N = 384 GEMMs (gemm_ln.cu)
