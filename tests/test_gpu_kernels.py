@@ -131,6 +131,33 @@ def test_gemm_cta_pair_variant():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_gemm_quad_cluster_variant():
+    """The opt-in 4-CTA-cluster kernel (two cta_group::2 pairs sharing TMA-multicast weight tiles) against torch,
+    including an odd number of 256-row blocks (the second pair of the last cluster computes on zero-filled rows)."""
+    import subprocess, sys, os
+    from tests.conftest import ROOT
+    code = (
+        "import torch, math, sys; sys.path.insert(0, %r)\n"
+        "from vited_b200 import _lib as L\n"
+        "g = torch.Generator(device='cuda').manual_seed(1)\n"
+        "for (M, N, K, act) in [(80000, 1536, 384, 1), (80001, 384, 1536, 0), (76001, 1152, 384, 0), (79990, 768, 384, 0)]:\n"
+        "    A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
+        "    b = torch.randn(N, device='cuda', generator=g); C = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')\n"
+        "    st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, act, 0, None)\n"
+        "    torch.cuda.synchronize(); assert st == 0, L.last_error()\n"
+        "    ref = A.float() @ W.float().t() + b\n"
+        "    ref = torch.nn.functional.gelu(ref) if act else ref\n"
+        "    assert torch.isfinite(C.float()).all(), ('nan', M, N, K)\n"
+        "    err = (C.float() - ref).abs(); tol = 1e-2 * ref.abs() + 2e-2\n"
+        "    bad = err > tol\n"
+        "    assert not bad.any(), (M, N, K, int(bad.sum()), float(err.max()), bad.nonzero()[0].tolist())\n"
+        "    print('ok', M, N, K, float(err.max()))\n"
+    ) % ROOT
+    env = dict(os.environ, VITED_GEMM_QUAD='1')
+    r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize('D', [384, 768, 32, 96])
 @pytest.mark.parametrize('has_cls', [0, 1])
 def test_resid_ln(D, has_cls):

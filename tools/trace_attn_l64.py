@@ -1,5 +1,6 @@
-"""Debug: clock trace of the long-sequence attention kernel, block 0 (needs tools/bin/libvited_trace.so built with
--DVITED_ATTN_TRACE): MMA warp per group (wait P start / end, PV issued, QK issued) and softmax warp 0 per group
+"""Debug: clock trace of the long-sequence attention kernel, block 0. Needs tools/bin/libvited_trace.so = the library
+built with -DVITED_ATTN_TRACE (the nvcc line of vit-ed_b200/csrc/build.sh plus that define, -o tools/bin/libvited_trace.so);
+the current kernel keeps the softmax-side trace points only: MMA warp per group (wait P start / end, PV issued, QK issued) and softmax warp 0 per group
 (wait S start / end, P stored)."""
 import ctypes, os
 import numpy as np
