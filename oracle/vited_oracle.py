@@ -220,3 +220,32 @@ def puzzle_distance_lookup(logits, i, j, side_i, side_j):
     if side_j == bottom and side_i == top:
         return pred[3] * 1000.
     return float('inf')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# retrieval metrics of the Hisfrag consumer (misc/wi19_evaluate.py:12-56) -- used to check the north-star criterion
+# "identical retrieval top-1 / mAP to 3 decimals" on score matrices produced by the CUDA path and by this oracle
+# ---------------------------------------------------------------------------------------------------------------
+def wi19_metrics(distance_matrix, labels):
+    """get_metrics(distance_matrix, labels, remove_self_column=True) of misc/wi19_evaluate.py:12-22:
+    rows sorted by ascending distance (numpy argsort, :28), the first column (self) dropped (:29-30), relevance =
+    same label (:26-27); mAP over non-singleton queries of mean(precision@rank over relevant ranks) (:49-56),
+    top-1 (:18), Pr@10 / Pr@100 (:7-9). Returns (mAP, top_1, pr_a_k10, pr_a_k100)."""
+    import numpy as np
+    D = np.asarray(distance_matrix)
+    classes = np.asarray(labels)
+    correct = classes[None, :] == classes[:, None]
+    order = np.argsort(D, axis=1)[:, 1:]
+    rel = correct[np.arange(order.shape[0], dtype='int64')[:, None], order]
+    ranks = np.cumsum(np.ones_like(rel), axis=1)
+    precision_at = np.cumsum(rel, axis=1).astype('float') / ranks
+    keep = rel.sum(axis=1) > 0
+    ap = (precision_at[keep] * rel[keep]).sum(axis=1) / rel[keep].sum(axis=1)
+    m_ap = ap.mean()
+    top_1 = rel[:, 0].sum() / len(rel)
+
+    def pr_at(k):
+        v = rel[:, :k].sum(axis=1) / np.minimum(rel.sum(axis=1), k)
+        return v.sum() / len(v)
+
+    return float(m_ap), float(top_1), float(pr_at(10)), float(pr_at(100))
