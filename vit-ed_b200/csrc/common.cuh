@@ -354,6 +354,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// The same descriptor split into its two 32-bit halves: the high word is a constant of the layout, the low word is
+// (address >> 4) | LBO. An issuer loop keeps `lo` of stage 0 and adds stage * (stage bytes >> 4) and 2 * k per 16-wide
+// k-step: one integer add per operand instead of rebuilding the 64-bit descriptor from the address every k-block (the
+// issuer warp is a single dependent instruction stream; every instruction it does not execute is tensor-pipe time).
+__device__ __forceinline__ uint32_t umma_desc_sw128_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+constexpr uint32_t kUmmaDescSw128Hi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // General swizzled descriptor. swizzle_bytes 128 / 64: tile rows are that many bytes wide (what a TMA box with the same
 // swizzle writes), 8-row groups are 8*swizzle_bytes apart (SBO). For a K-major operand the rows are M/N indices; for an
 // "MN-major" operand (instruction-descriptor bit 15 / 16) the rows are K indices and a 16-wide k-step spans two groups.

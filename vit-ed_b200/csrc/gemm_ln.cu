@@ -120,6 +120,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== MMA issuer (leader CTA only): two N = 192 MMAs per k-step =====================
     if (rank == 0) {   // warp-uniform loop, tcgen05 instructions predicated on one elected lane
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, NH);
+      constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4, kA16 = Cfg::A_BYTES >> 4, kBH16 = Cfg::BH_BYTES >> 4;
+      const uint32_t lo0 = umma_desc_sw128_lo(smem_u32(smem));   // stage 0: A tile, then the two 96-row weight halves
       uint32_t stage = 0, phase = 0, aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(tempty, aphase ^ 1, 20);
@@ -127,15 +129,15 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 21);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db0 = umma_desc_sw128(a_addr + Cfg::A_BYTES);
-          const uint64_t db1 = umma_desc_sw128(a_addr + Cfg::A_BYTES + Cfg::BH_BYTES);
+          const uint32_t lo_a = lo0 + stage * kStage16;
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              umma_bf16_2cta(tmem_base, da + 2 * k, db0 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              umma_bf16_2cta(tmem_base + NH, da + 2 * k, db1 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint64_t da = umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi);
+              umma_bf16_2cta(tmem_base, da, umma_desc_pack(lo_a + kA16 + 2 * k, kUmmaDescSw128Hi), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_2cta(tmem_base + NH, da, umma_desc_pack(lo_a + kA16 + kBH16 + 2 * k, kUmmaDescSw128Hi), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit_2cta(&empty[stage]);
           }

@@ -298,14 +298,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 21);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db = umma_desc_sw128(kResident ? smem_u32(sPanel + kb * Cfg::B_BYTES) : a_addr + Cfg::A_BYTES);
+          const uint32_t lo_a = umma_desc_sw128_lo(smem_u32(smem)) + stage * (Cfg::STAGE_BYTES >> 4);
+          const uint32_t lo_b = kResident ? umma_desc_sw128_lo(smem_u32(sPanel)) + kb * (Cfg::B_BYTES >> 4)
+                                          : lo_a + (Cfg::A_BYTES >> 4);
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi), umma_desc_pack(lo_b + 2 * k, kUmmaDescSw128Hi),
+                        idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
           }
@@ -462,6 +463,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // predicated on one elected lane.
     if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4, kA16 = Cfg::A_BYTES >> 4;
+      const uint32_t lo0 = umma_desc_sw128_lo(smem_u32(smem));   // A tile of stage 0; the B half tile follows it
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tempty[as], aphase ^ 1, 20);
@@ -470,13 +473,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 21);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+          const uint32_t lo_a = lo0 + stage * kStage16;
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 B along K inside the swizzle atom: +2 in the address field
+              umma_bf16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
+                             umma_desc_pack(lo_a + kA16 + 2 * k, kUmmaDescSw128Hi), idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2cta(&empty[stage]);   // frees this stage in BOTH CTAs
           }
           __syncwarp();
@@ -629,13 +631,12 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 21);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = umma_desc_sw128(a_addr);
-          const uint64_t db = umma_desc_sw128(a_addr + Cfg::A_BYTES);
+          const uint32_t lo_a = umma_desc_sw128_lo(smem_u32(smem)) + stage * (Cfg::STAGE_BYTES >> 4);
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
+                             umma_desc_pack(lo_a + (Cfg::A_BYTES >> 4) + 2 * k, kUmmaDescSw128Hi), idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2cta_mask(&empty[stage], 0xF);   // this pair is done with the stage: tell all four CTAs
           }
           __syncwarp();
