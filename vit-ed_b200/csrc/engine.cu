@@ -760,8 +760,11 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
     TRY(upload_ints(e->ci, ci, s));
     TRY(upload_ints(e->xj, xj, s));
     const size_t total = ci.size();
-    for (size_t p0 = 0; p0 < total; p0 += pairs_per_chunk) {
-      const int P = (int)((total - p0 < (size_t)pairs_per_chunk) ? (total - p0) : pairs_per_chunk);
+    // equal chunks: a short last chunk would run every kernel of the stack at a fraction of a wave
+    const size_t n_chunks = (total + pairs_per_chunk - 1) / pairs_per_chunk;
+    const size_t chunk = (total + n_chunks - 1) / n_chunks;
+    for (size_t p0 = 0; p0 < total; p0 += chunk) {
+      const int P = (int)((total - p0 < chunk) ? (total - p0) : chunk);
       HeadArgs head = {};
       head.out = out + (size_t)(r0 - row_begin) * N * e->C;
       head.ci = e->ci.as<int>() + p0;
