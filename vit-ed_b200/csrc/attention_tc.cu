@@ -7,9 +7,9 @@
 //   TMEM, the probabilities go back to TMEM as packed bf16 (aliasing S) and feed the second MMA as its A operand,
 //   O = P V with V consumed in place as an MN-major operand (no transpose, no ldmatrix, no shuffles).
 //   Warp roles (16 warps, 1 CTA / SM): warp 3 = TMA producer (12-deep ring of Q/K/V tiles, hardware 64B swizzle),
-//   warp 11 = TMEM allocator, warps {4g, 4g+1, 4g+2} = softmax group g of TMEM stage g (rows 0-31, 32-63, 64); every
-//   group issues its own MMAs (PV of its unit, then QK^T of its next unit back to back), so no unit waits on another
-//   thread between its phases.
+//   warp 7 = MMA issuer (lean, warp-uniform, serves the groups' units in round-robin order: PV of a unit, then QK^T
+//   of the same group's next unit right behind it), warp 11 = TMEM allocator, warps {4g, 4g+1, 4g+2} = softmax group g
+//   of TMEM stage g (rows 0-31, 32-63, 64).
 // Operand conventions (SW64 K-major, MN-major V, A from TMEM) were pinned on B200 by tools/umma_probe.cu.
 #include "kernels.h"
 
@@ -36,7 +36,7 @@ struct P64 {
   static constexpr int TCOLS = 128;           // TMEM columns per stage: S/P at +0 (80), O at +96 (32)
   static constexpr int OCOL = 96;
   static constexpr int THREADS = 32 * 4 * NT;
-  static constexpr int BAR_BYTES = (2 * NS + 4 * NT) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * NS + 4 * NT) * 8 + 16;   // full, empty, s_full, o_full, p_ready + TMEM holder
   static constexpr int BYTES = 1024 + NS * STAGE + BAR_BYTES;
 };
 
@@ -54,7 +54,8 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
   uint64_t* empty = bars + C::NS;              // PV of the unit has read the stage (tcgen05.commit)
   uint64_t* s_full = bars + 2 * C::NS;         // S ready in TMEM (commit)
   uint64_t* o_full = s_full + C::NT;           // O ready in TMEM (commit)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_full + C::NT);
+  uint64_t* p_ready = o_full + C::NT;          // P written to TMEM (the group's 3 softmax warps)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(p_ready + C::NT);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (keeps MMA operands in uniform registers)
@@ -71,7 +72,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
   if (tid == 0) {
     for (int s = 0; s < C::NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int t = 0; t < C::NT; ++t) {
-      mbar_init(&s_full[t], 1); mbar_init(&o_full[t], 1);
+      mbar_init(&s_full[t], 1); mbar_init(&o_full[t], 1); mbar_init(&p_ready[t], 3);
     }
     fence_mbar_init();
     tma_prefetch_desc(&maps.q_tile);
@@ -89,14 +90,17 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
   const uint32_t tmem_base = *tmem_holder;
 
   if (quarter == 3) {
-    if (group == 0 && lane == 0) {
+    if (group == 0) {
       // ===================== TMA producer =====================
+      // Lane 0 issues. With a key/value index (cross-attention: kv_index[b]) the whole warp fetches the indices of the
+      // next 32 units at once. A dependent __ldg per unit in the issuing thread's chain (~600 cycles) was the whole per-unit
+      // budget of the cross-attention launch (~880 cycles per unit and SM).
       int s = 0;
       uint32_t ph = 0;
-      for (int i = 0; i < n_my; ++i) {
+      auto issue_unit = [&](int i, int kvb) {     // lane 0: the TMA loads of local unit i
         const int u = (int)blockIdx.x + i * (int)gridDim.x;
         const int b = u / H, h = u - b * H;
-        const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;
+        if (kvb < 0) kvb = b;
         const int col = h * C::HD;
         mbar_wait(&empty[s], ph ^ 1, 50);
         uint8_t* st = smem + s * C::STAGE;
@@ -112,37 +116,78 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
           tma_load_2d(&maps.v_row, &full[s], st + 2 * C::TB + 64 * C::RB, col, a.n_kv_seq * 64 + kvb);
         }
         if (++s == C::NS) { s = 0; ph ^= 1; }
+      };
+      if (a.kv_index == nullptr) {
+        if (lane == 0)
+          for (int i = 0; i < n_my; ++i) issue_unit(i, -1);
+      } else {
+        for (int i0 = 0; i0 < n_my; i0 += 32) {
+          int my_kvb = 0;
+          if (i0 + lane < n_my) my_kvb = __ldg(a.kv_index + ((int)blockIdx.x + (i0 + lane) * (int)gridDim.x) / H);
+          const int jn = n_my - i0 < 32 ? n_my - i0 : 32;
+          for (int j = 0; j < jn; ++j) {
+            const int kvb = __shfl_sync(0xffffffffu, my_kvb, j);
+            if (lane == 0) issue_unit(i0 + j, kvb);
+          }
+        }
+      }
+    } else if (group == 1) {
+      // ===================== MMA issuer for all four groups (warp-uniform code, one elected lane) =====================
+      // Units go to the groups round robin, so the issuer serves them in unit order: PV(i) as soon as the group's
+      // probabilities are in TMEM, QK^T of the same group's next unit (i + NT) right behind it (the tensor pipe runs in
+      // issue order, so those scores may overwrite P(i)). When the groups' first warps issued their own MMAs that cost
+      // them ~850 cycles per unit on the group's critical path (tools/trace_attn_p64.py).
+      const uint32_t idesc_qk = umma_idesc_bf16(128, NK);
+      const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
+      const uint32_t smem0 = smem_u32(smem);
+      auto issue_qk = [&](int i) {      // S(stage i % NT) = Q K^T of local unit i
+        const int s = i % C::NS, t = i % C::NT;
+        mbar_wait(&full[s], (uint32_t)(i / C::NS) & 1u, 51);
+        tc_fence_after();
+        const uint32_t q_addr = smem0 + s * C::STAGE;
+        const uint64_t dq = umma_desc_sw(q_addr, 64);
+        const uint64_t dk = umma_desc_sw(q_addr + C::TB, 64);
+        const uint32_t t_col = tmem_base + t * C::TCOLS;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < C::HD / 16; ++k) umma_bf16(t_col, dq + 2 * k, dk + 2 * k, idesc_qk, k);
+          umma_commit(&s_full[t]);
+        }
+        __syncwarp();
+      };
+      for (int i = 0; i < C::NT && i < n_my; ++i) issue_qk(i);
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i % C::NS, t = i % C::NT;
+        const uint32_t t_col = tmem_base + t * C::TCOLS;
+        mbar_wait(&p_ready[t], (uint32_t)(i / C::NT) & 1u, 53);
+        tc_fence_after();
+        const uint64_t dv = umma_desc_sw(smem0 + s * C::STAGE + 2 * C::TB, 64);
+        if (elect_one_sync()) {
+          if (NK == 80) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k)   // 16 keys per step = two 8-key groups of 512 B = +64 in the (addr >> 4) field
+              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&o_full[t]);
+        }
+        __syncwarp();
+        if (i + C::NT < n_my) issue_qk(i + C::NT);
       }
     }
   } else {
     // ===================== softmax group `group`, TMEM lane quarter `quarter` =====================
-    // The group owns TMEM stage `group` and issues its own MMAs (lane 0 of its first warp): PV of the current unit as
-    // soon as the three warps' probabilities are in TMEM, and QK^T of the group's NEXT unit right behind it (the
-    // tensor pipe executes in issue order, so S of the next unit may overwrite P of this one), which means the next
-    // scores are ready by the time this unit's output has been written.
+    // The group owns TMEM stage `group`: scores -> probabilities (packed bf16 over S) -> signal the issuer -> read O.
     const float sl2 = a.scale * kLog2e;
     const int row = quarter * 32 + lane;                  // query row of the unit's tile
     // quarter 2 only carries the class-token query (row 64); in cls_only mode it is the only live row
     const bool warp_active = quarter < 2 ? !cls_only : a.q_has_cls != 0;
     const uint32_t t_col = tmem_base + group * C::TCOLS;
     const uint32_t t_stage = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t idesc_qk = umma_idesc_bf16(128, NK);
-    const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
-    auto issue_qk = [&](int i) {      // first warp of the group, warp-uniform: S(stage) = Q K^T of local unit i
-      const int s = i % C::NS;
-      mbar_wait(&full[s], (uint32_t)(i / C::NS) & 1u, 51);
-      tc_fence_after();
-      const uint32_t q_addr = smem_u32(smem + s * C::STAGE);
-      const uint64_t dq = umma_desc_sw(q_addr, 64);
-      const uint64_t dk = umma_desc_sw(q_addr + C::TB, 64);
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int k = 0; k < C::HD / 16; ++k) umma_bf16(t_col, dq + 2 * k, dk + 2 * k, idesc_qk, k);
-        umma_commit(&s_full[group]);
-      }
-      __syncwarp();
-    };
-    if (quarter == 0 && group < n_my) issue_qk(group);
     uint32_t ph = 0;
     for (int i = group; i < n_my; i += C::NT) {
       const int u = (int)blockIdx.x + i * (int)gridDim.x;
@@ -192,28 +237,8 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
         tmem_st_wait();
       }
       tc_fence_before();
-      asm volatile("bar.sync %0, 96;" ::"r"(group + 1) : "memory");   // the group's three warps: all of P is in TMEM
-      if (quarter == 0) {     // the group's first warp issues (warp-uniform code, one elected lane)
-        tc_fence_after();
-        const int s = i % C::NS;
-        const uint64_t dv = umma_desc_sw(smem_u32(smem + s * C::STAGE + 2 * C::TB), 64);
-        if (elect_one_sync()) {
-          if (NK == 80) {
-#pragma unroll
-            for (int k = 0; k < 5; ++k)   // 16 keys per step = two 8-key groups of 512 B = +64 in the (addr >> 4) field
-              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
-          }
-          umma_commit(&empty[s]);
-          umma_commit(&o_full[group]);
-        }
-        __syncwarp();
-        if (i + C::NT < n_my) issue_qk(i + C::NT);
-      }
       __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[group]);   // 3 warps: all of P is in TMEM -> the issuer may run PV
       mbar_wait(&o_full[group], ph, 55);
       tc_fence_after();
       if (warp_active) {
