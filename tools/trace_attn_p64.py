@@ -21,10 +21,10 @@ buf = np.zeros(4 * 64 * 8, dtype=np.uint64)
 assert lib.vited_debug_p64_trace(buf.ctypes.data_as(vp)) == 0
 tr = buf.reshape(4, 64, 8).astype(np.int64)
 t0 = tr[0, 10, 0]
-names = ['waitS', 'softmax', 'bar', 'issue PV+QK', 'waitO', 'epilogue']
+names = ['waitS', 'softmax -> P', 'wait O (PV round trip)', 'epilogue']
 for g in range(2):
     print(f'--- group {g}: unit | start | ' + ' | '.join(names) + ' | total')
     for k in range(10, 30):
         e = tr[g, k]
-        d = [e[i + 1] - e[i] for i in range(6)]
-        print(f'  {k:3d} | {e[0] - t0:7d} | ' + ' | '.join(f'{x:6d}' for x in d) + f' | {e[6] - e[0]:6d}')
+        d = [e[i + 1] - e[i] for i in range(4)]
+        print(f'  {k:3d} | {e[0] - t0:7d} | ' + ' | '.join(f'{x:6d}' for x in d) + f' | {e[4] - e[0]:6d}')

@@ -1,5 +1,5 @@
 """Debug: clock trace of the fused GEMM + residual + LayerNorm kernel, CTA 0 (needs tools/bin/libvited_trace.so = the
-library built with -DVITED_LN_TRACE)."""
+library built with -DVITED_LN_TRACE: the nvcc line of vit-ed_b200/csrc/build.sh plus that define)."""
 import ctypes, math, os, sys
 import numpy as np
 import torch

@@ -40,6 +40,13 @@ struct P64 {
   static constexpr int BYTES = 1024 + NS * STAGE + BAR_BYTES;
 };
 
+#ifdef VITED_ATTN_TRACE   // clock64 trace of block 0 (tools/trace_attn_p64.py); compiled out of the product library
+__device__ unsigned long long g_p64_trace[4 * 64 * 8];   // [group][unit k][event], first warp lane 0
+#define TRP(ev) do { if (blockIdx.x == 0 && quarter == 0 && lane == 0 && tk < 64) g_p64_trace[(group * 64 + tk) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TRP(ev) do { } while (0)
+#endif
+
 struct P64Maps {
   CUtensorMap q_tile, q_row, k_tile, k_row, v_tile, v_row;   // boxes {32, 64} and {32, 1}, 64B swizzle
 };
@@ -189,10 +196,13 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
     const uint32_t t_col = tmem_base + group * C::TCOLS;
     const uint32_t t_stage = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t ph = 0;
-    for (int i = group; i < n_my; i += C::NT) {
+    int tk = 0; (void)tk;
+    for (int i = group; i < n_my; i += C::NT, ++tk) {
       const int u = (int)blockIdx.x + i * (int)gridDim.x;
       const int b = u / H, h = u - b * H;
+      TRP(0);
       mbar_wait(&s_full[group], ph, 54);
+      TRP(1);
       tc_fence_after();
       float l = 1.f;
       if (warp_active) {
@@ -239,7 +249,9 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[group]);   // 3 warps: all of P is in TMEM -> the issuer may run PV
+      TRP(2);
       mbar_wait(&o_full[group], ph, 55);
+      TRP(3);
       tc_fence_after();
       if (warp_active) {
         uint32_t ov[32];
@@ -264,6 +276,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
           }
         }
       }
+      TRP(4);
       ph ^= 1;
     }
   }
@@ -332,8 +345,8 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   uint64_t* q_empty = q_full + 4;              // [group*2 + buffer] the item's last QK^T has read the Q tile (commit)
   uint64_t* s_full = q_empty + 4;              // [group*2 + buffer] scores of a half tile are in TMEM (commit)
   uint64_t* p_ready = s_full + 4;              // [group*2 + buffer] probabilities are in TMEM (4 warps)
-  uint64_t* o_done = p_ready + 4;              // [group] a PV has finished (commit)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_ready + 4;              // [group*2 + (half tile & 1)] PV of that half tile has finished (commit)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(o_done + 4);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -353,7 +366,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
     for (int j = 0; j < 4; ++j) {
       mbar_init(&q_full[j], 1); mbar_init(&q_empty[j], 1); mbar_init(&s_full[j], 1); mbar_init(&p_ready[j], 4);
     }
-    mbar_init(&o_done[0], 1); mbar_init(&o_done[1], 1);
+    for (int j = 0; j < 4; ++j) mbar_init(&o_done[j], 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.q_tile);
     tma_prefetch_desc(&maps.k_tile);
@@ -475,7 +488,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
             for (int k = 0; k < 4; ++k)   // 16 keys per step = two 8-key groups of 1024 B = +128 in the (addr >> 4) field
               umma_bf16_ts(t_col + C::OCOL, t_p + 8 * k, dv + 128 * k, idesc_pv, (u | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&o_done[g]);
+          umma_commit(&o_done[g * 2 + (pj & 1)]);
           if (stage_done) umma_commit(&kv_empty[stage]);
         }
         __syncwarp();
@@ -493,10 +506,15 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
     const uint32_t t_col = tmem_base + g * C::GCOLS;
     const uint32_t t_row = t_col + (static_cast<uint32_t>(quarter * 32) << 16);
     uint32_t j = 0;        // half tiles processed by this group so far (score buffer = j & 1, phase = (j >> 1) & 1)
+    // Wait until PV of this group's half tile number jj (and, the tensor pipe being in order, every earlier one) has
+    // finished. PV(jj) commits to o_done[parity of jj]; the next commit on the same barrier is PV(jj + 2), which cannot
+    // be issued before this thread has published P(jj + 2) -- so the barrier is never more than one phase ahead of the
+    // waiter and the parity wait cannot alias. (A single barrier per group can: with both final PVs already complete, a
+    // wait for the older parity equals the parity of the current, incomplete phase and never returns.)
+    auto wait_pv = [&](uint32_t jj, int tag) { mbar_wait(&o_done[g * 2 + (jj & 1)], (jj >> 1) & 1u, tag); };
     // the running max moved by more than the threshold: wait for the group's previous PV, rescale the own O row
     auto rescale = [&](float mt, float& m, float& l) {
-      // (S(j) being ready implies PV(j-2) is complete, so o_done is at most one phase behind here: no aliasing)
-      mbar_wait(&o_done[g], (j - 1) & 1u, 68);
+      wait_pv(j - 1, 68);
       tc_fence_after();
       const float f = ex2_ftz(m - mt);
       l *= f;
@@ -586,10 +604,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         if (lane == 0) mbar_arrive(&p_ready[sb]);   // 4 warps: P (and any rescaled O row) is in TMEM -> PV may be issued
       }
       // ---- item epilogue: O / l -> bf16 -> global ----
-      // When the last scores arrived only PV(j-3) was known to be complete, so o_done may still be two phases behind:
-      // a single parity wait would alias. Wait for PV(j-2), then PV(j-1) (j >= 2: every item has >= 2 half tiles).
-      mbar_wait(&o_done[g], (j - 2) & 1u, 70);
-      mbar_wait(&o_done[g], (j - 1) & 1u, 71);
+      wait_pv(j - 1, 71);
       tc_fence_after();
       {
         const float inv = 1.f / l;
@@ -708,6 +723,9 @@ static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream
 
 
 #ifdef VITED_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int vited_debug_p64_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, vited::g_p64_trace, sizeof(unsigned long long) * 4 * 64 * 8);
+}
 extern "C" __attribute__((visibility("default"))) int vited_debug_attn_trace(unsigned long long* out) {
   return (int)cudaMemcpyFromSymbol(out, vited::g_attn_trace, sizeof(unsigned long long) * 4 * 128 * 4);
 }

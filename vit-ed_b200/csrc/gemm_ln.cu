@@ -39,6 +39,13 @@ struct LnCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
+#ifdef VITED_LN_TRACE   // clock64 trace of CTA 0 (tools/trace_gemm_ln.py); compiled out of the product library
+__device__ unsigned long long g_ln_trace[3 * 32 * 8];   // [0 = epilogue warp (q0,c0), 1 = MMA warp, 2 = epilogue warp (q3,c1)][tile][event]
+#define TRL(who, t, ev) do { if (blockIdx.x == 0 && lane == 0 && (t) < 32) g_ln_trace[((who) * 32 + (t)) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TRL(who, t, ev) do { } while (0)
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LnCfg::kThreads, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
@@ -123,8 +130,11 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4, kA16 = Cfg::A_BYTES >> 4, kBH16 = Cfg::BH_BYTES >> 4;
       const uint32_t lo0 = umma_desc_sw128_lo(smem_u32(smem));   // stage 0: A tile, then the two 96-row weight halves
       uint32_t stage = 0, phase = 0, aphase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      int tt = 0; (void)tt;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++tt) {
+        TRL(1, tt, 0);
         mbar_wait(tempty, aphase ^ 1, 20);
+        TRL(1, tt, 1);
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase, 21);
@@ -146,6 +156,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (elect_one_sync()) umma_commit_2cta(tfull);
         __syncwarp();
+        TRL(1, tt, 2);
         aphase ^= 1;
       }
     }
@@ -175,7 +186,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = pair + t * num_pairs;
       const int row0 = tile * 2 * BM + (int)rank * BM + q * 32;
+      const int who = ew == 0 ? 0 : (ew == 7 ? 2 : -1); (void)who;
+      if (who >= 0) TRL(who, t, 0);
       mbar_wait(tfull, aphase, 30);
+      if (who >= 0) TRL(who, t, 1);
       tc_fence_after();
       // ---- pass 1: v = acc + bias + x; park v in TMEM, write it back to the residual stream, shifted statistics ----
       float s = 0.f, ss = 0.f, c0 = 0.f;
@@ -219,6 +233,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       tmem_st_wait();
+      if (who >= 0) TRL(who, t, 2);
       // ---- combine the two column halves of every row (Chan): n = 192 each ----
       sPart[c * BM + q * 32 + lane] = make_float4(s, ss, c0, 0.f);
       asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
@@ -230,6 +245,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float mean = 0.5f * (mean_a + mean_b);
       const float var = (m2_a + m2_b + dm * dm * (0.5f * NH)) * (1.f / LN_N);
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+      if (who >= 0) TRL(who, t, 3);
       // ---- pass 2: normalise out of TMEM, bf16, 64-column slabs through the warp's staging box ----
 #pragma unroll 1
       for (int jj = 0; jj < CHUNKS / 2; ++jj) {
@@ -271,6 +287,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_store_commit();
         }
       }
+      if (who >= 0) TRL(who, t, 4);
       aphase ^= 1;
     }
     if (lane == 0) tma_store_wait_all();
@@ -316,3 +333,9 @@ int gemm_resid_ln(const bf16* A, const bf16* W, const float* bias, float* x, con
 }
 
 }  // namespace vited
+
+#ifdef VITED_LN_TRACE
+extern "C" __attribute__((visibility("default"))) int vited_debug_ln_trace(unsigned long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, vited::g_ln_trace, sizeof(unsigned long long) * 3 * 32 * 8);
+}
+#endif
