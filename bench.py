@@ -373,7 +373,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': vited_b200.ACT_NAME,
             'data': 'synthetic', 'config': workload_config(world),
             'clocks': clock_info,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
@@ -430,7 +430,7 @@ def run_hisfrag(args):
     flops = n_pairs * 89.50e9 + n * (63.42e9 + 7.248e9 + 0.604e9)
     print(json.dumps({
         'metric': METRIC, 'value': n_pairs / (ms / 1e3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': ms, 'dtype': 'bf16', 'data': 'synthetic',
+        'ms_per_step': ms, 'dtype': vited_b200.ACT_NAME, 'data': 'synthetic',
         'config': {'workload': f'configs[3] model (Hisfrag20 patch16 512px), {n} synthetic fragments, {n_pairs} pairs (a<=b), 1 GPU'},
         'step_tensor_frac': flops / (ms / 1e3) / 1e12 / peaks['tf_sustained'],
         'classes': {k: {'ms': round(v['ms'], 3), 'share': round(v['ms'] / total, 4),

@@ -78,7 +78,7 @@ VITED_API int vited_set_option(vited_engine* e, int option, int64_t value);
 
 /* replaces: load_pretrained -> model.load_state_dict (misc/utils.py:48-127). `name` is the state_dict key
  * (e.g. "cross_blocks.3.cross_attn.kv.weight"), `data` a device pointer to the fp32 tensor in PyTorch layout
- * (Linear weights [out, in], conv weight [D, C, p, p]); the engine packs its own bf16 copy, the caller's tensor is
+ * (Linear weights [out, in], conv weight [D, C, p, p]); the engine packs its own 16-bit copy, the caller's tensor is
  * only borrowed for the duration of the call (synchronises `stream`). Unknown keys are an error. */
 VITED_API int vited_load_weight(vited_engine* e, const char* name, const float* data, int64_t numel, void* stream);
 /* number of state_dict tensors the engine expects / has received; forward calls fail until they match */
@@ -114,25 +114,29 @@ VITED_API int64_t vited_launch_count(vited_engine* e);
  * {"<class>": {"ms":, "flops":, "bytes":, "launches":}, ...} (algorithmic flops / bytes of the launches). Synchronises
  * `stream`, resets the counters. The string is owned by the engine and valid until the next call. */
 VITED_API const char* vited_profile_json(vited_engine* e, void* stream);
+/* 16-bit type of the GEMM / attention operands and of the buffers of the single-kernel entry points below:
+ * 0 = IEEE fp16 (default; the reference's autocast dtype, config.py:216), 1 = bf16 (-DVITED_ACT_BF16=1 builds).
+ * Accumulators, the residual stream, LayerNorm statistics and softmax are fp32 in both. */
+VITED_API int vited_act_dtype(void);
 /* bytes of device workspace currently held */
 VITED_API int64_t vited_workspace_bytes(vited_engine* e);
 
 /* ---- single-kernel entry points (used by tests/ and profiles/ to check and time each kernel in isolation) ---- */
-/* C[M,N] bf16 = act(A[M,K] bf16 * W[N,K]^T bf16 + bias[N] f32); act: 0 none, 1 exact-erf GELU; impl as GEMM_IMPL */
+/* ("h16" = the 16-bit type vited_act_dtype() names) C[M,N] h16 = act(A[M,K] h16 * W[N,K]^T h16 + bias[N] f32); act: 0 none, 1 exact-erf GELU; impl as GEMM_IMPL */
 VITED_API int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,
                   void* stream);
-/* fused Linear + residual + LayerNorm (N must be 384): x[M,384] f32 += A[M,K] bf16 * W[384,K]^T bf16 + bias;
- * h[M,384] bf16 = LayerNorm(x) * ln_w + ln_b */
+/* fused Linear + residual + LayerNorm (N must be 384): x[M,384] f32 += A[M,K] h16 * W[384,K]^T h16 + bias;
+ * h[M,384] h16 = LayerNorm(x) * ln_w + ln_b */
 VITED_API int vited_op_gemm_resid_ln(const void* A, const void* W, const float* bias, float* x, const float* ln_w,
                            const float* ln_b, void* h, int M, int N, int K, float eps, void* stream);
-/* x += delta (bf16, may be NULL); h = LayerNorm(x) * w + b as bf16 (w NULL => skipped). Split token layout. */
+/* x += delta (h16, may be NULL); h = LayerNorm(x) * w + b as h16 (w NULL => skipped). Split token layout. */
 VITED_API int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
                       int n_patch, int has_cls, int D, float eps, void* stream);
-/* q/k/v/o bf16 in the split token layout; kv_index NULL => identity */
+/* q/k/v/o h16 in the split token layout; kv_index NULL => identity */
 VITED_API int vited_op_attention(const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o, int o_ld,
                        int n_seq, int n_heads, int head_dim, int nq_patch, int q_has_cls, int nk_patch,
                        int k_has_cls, int n_kv_seq, const int32_t* kv_index, float scale, int impl, void* stream);
-/* images [B,C,S,S] f32 -> [B*(S/p)^2, C*p*p] bf16 */
+/* images [B,C,S,S] f32 -> [B*(S/p)^2, C*p*p] h16 */
 VITED_API int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, void* stream);
 
 #ifdef __cplusplus

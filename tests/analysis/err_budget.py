@@ -2,7 +2,7 @@
 choices contribute to the error budget of 2e-2)."""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import vited_b200
 from vited_b200 import grid, synthetic
@@ -29,5 +29,5 @@ for seed in (0, 5):
         agree = (got.argmax(-1) == want.argmax(-1))[off].float().mean().item()
         top2 = want.topk(2, dim=-1).values
         close = ((top2[..., 0] - top2[..., 1]) <= 2 * err.max().item())[off].float().mean().item()
-        print(f'weights seed {seed}  {name:34s} max err {err.max().item():.5f}  mean err {err.mean().item():.5f}  '
+        print(f'[{vited_b200.ACT_NAME}] weights seed {seed}  {name:34s} max err {err.max().item():.5f}  mean err {err.mean().item():.5f}  '
               f'argmax agreement {agree:.4f}  (pairs whose fp32 top-2 margin is within 2 x max err: {close:.4f})')

@@ -1,5 +1,5 @@
 """GPU: every kernel behind the C-ABI, in isolation, against plain torch on the same device (fp32 math on the same
-bf16-rounded operands). Tolerances are stated per test."""
+16-bit-rounded operands; fp16 unless the library was built with -DVITED_ACT_BF16=1). Tolerances are stated per test."""
 import ctypes
 import math
 
@@ -14,6 +14,15 @@ def _lib():
     return _lib
 
 
+def _act():
+    return _lib().act_dtype()
+
+
+def _r16():
+    """tolerance scale of the 16-bit rounding terms: 1 for bf16 (8 significand bits), 0.2 for fp16 (11 bits)"""
+    return 1.0 if _act() == torch.bfloat16 else 0.2
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -26,7 +35,7 @@ def _gemm(A, W, bias, act, impl):
     L = _lib()
     M, K = A.shape
     N = W.shape[0]
-    C = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')
+    C = torch.full((M, N), float('nan'), dtype=_act(), device='cuda')
     L.check(L.lib.vited_op_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(C), M, N, K, act, impl, _stream()), 'op_gemm')
     torch.cuda.synchronize()
     return C
@@ -50,17 +59,17 @@ def test_gemm(shape, act, impl):
     if impl == 1 and M * N * K > 3e9:
         pytest.skip('debug kernel: skip the largest shape')
     g = torch.Generator(device='cuda').manual_seed(M * 7 + N * 3 + K)
-    A = torch.randn(M, K, device='cuda', generator=g).to(torch.bfloat16)
-    W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    A = torch.randn(M, K, device='cuda', generator=g).to(_act())
+    W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(_act())
     bias = torch.randn(N, device='cuda', generator=g)
     C = _gemm(A, W, bias, act, impl)
     ref = A.float() @ W.float().t() + bias
     if act:
         ref = torch.nn.functional.gelu(ref)
     assert torch.isfinite(C.float()).all(), 'output has NaN/inf (unwritten tile?)'
-    # bf16 output rounding (2^-9 relative) + fp32 accumulation-order noise
+    # 16-bit output rounding (bf16 2^-9 / fp16 2^-12 relative) + fp32 accumulation-order noise
     err = (C.float() - ref).abs()
-    tol = 1e-2 * ref.abs() + 2e-2
+    tol = (1e-2 * ref.abs() + 2e-2) * _r16()
     bad = (err > tol)
     assert not bad.any(), f'{int(bad.sum())} / {bad.numel()} mismatches, max err {float(err.max()):.4f}, ' \
                           f'first bad index {bad.nonzero()[0].tolist()}'
@@ -68,17 +77,17 @@ def test_gemm(shape, act, impl):
 
 def test_gelu_epilogue_accuracy():
     """The single-MUFU GELU of the GEMM epilogue against the exact erf definition (timm Mlp act_layer=nn.GELU) on a
-    dense grid of pre-activations: |error| <= 1e-4 + the bf16 rounding of the stored result."""
+    dense grid of pre-activations: |error| <= 1e-4 + the 16-bit rounding of the stored result."""
     M, N, K = 8192, 8, 8
-    v = torch.linspace(-12, 12, M, device='cuda').to(torch.bfloat16)
-    A = torch.zeros(M, K, dtype=torch.bfloat16, device='cuda')
+    v = torch.linspace(-12, 12, M, device='cuda').to(_act())
+    A = torch.zeros(M, K, dtype=_act(), device='cuda')
     A[:, 0] = v
-    W = torch.eye(N, K, device='cuda').to(torch.bfloat16)
+    W = torch.eye(N, K, device='cuda').to(_act())
     bias = torch.zeros(N, device='cuda')
     C = _gemm(A, W, bias, 1, 0)
     ref = torch.nn.functional.gelu(v.double())
     err = (C[:, 0].double() - ref).abs()
-    tol = 1e-4 + ref.abs() * 2.0 ** -8
+    tol = 1e-4 + ref.abs() * (2.0 ** -8 if _act() == torch.bfloat16 else 2.0 ** -11)
     assert (err <= tol).all(), f'max excess {(err - tol).max().item()}'
     assert (C[:, 1:] == 0).all()
 
@@ -93,8 +102,8 @@ def test_gemm_tile_shapes_agree(bn, monkeypatch):
         "from vited_b200 import _lib as L\n"
         "g = torch.Generator(device='cuda').manual_seed(1)\n"
         "M, N, K = 1111, 1536, 384\n"
-        "A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
-        "b = torch.randn(N, device='cuda', generator=g); C = torch.zeros(M, N, dtype=torch.bfloat16, device='cuda')\n"
+        "A = torch.randn(M, K, device='cuda', generator=g).to(L.act_dtype()); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(L.act_dtype())\n"
+        "b = torch.randn(N, device='cuda', generator=g); C = torch.zeros(M, N, dtype=L.act_dtype(), device='cuda')\n"
         "st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, 0, 0, None)\n"
         "torch.cuda.synchronize(); assert st == 0, L.last_error()\n"
         "ref = A.float() @ W.float().t() + b\n"
@@ -114,8 +123,8 @@ def test_gemm_cta_pair_variant():
         "from vited_b200 import _lib as L\n"
         "g = torch.Generator(device='cuda').manual_seed(1)\n"
         "for (M, N, K, act) in [(40000, 1536, 384, 1), (40001, 384, 1536, 0), (38001, 1152, 384, 0), (40000, 384, 384, 0), (39990, 768, 384, 0)]:\n"
-        "    A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
-        "    b = torch.randn(N, device='cuda', generator=g); C = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')\n"
+        "    A = torch.randn(M, K, device='cuda', generator=g).to(L.act_dtype()); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(L.act_dtype())\n"
+        "    b = torch.randn(N, device='cuda', generator=g); C = torch.full((M, N), float('nan'), dtype=L.act_dtype(), device='cuda')\n"
         "    st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, act, 0, None)\n"
         "    torch.cuda.synchronize(); assert st == 0, L.last_error()\n"
         "    ref = A.float() @ W.float().t() + b\n"
@@ -141,8 +150,8 @@ def test_gemm_quad_cluster_variant():
         "from vited_b200 import _lib as L\n"
         "g = torch.Generator(device='cuda').manual_seed(1)\n"
         "for (M, N, K, act) in [(80000, 1536, 384, 1), (80001, 384, 1536, 0), (76001, 1152, 384, 0), (79990, 768, 384, 0)]:\n"
-        "    A = torch.randn(M, K, device='cuda', generator=g).bfloat16(); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).bfloat16()\n"
-        "    b = torch.randn(N, device='cuda', generator=g); C = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')\n"
+        "    A = torch.randn(M, K, device='cuda', generator=g).to(L.act_dtype()); W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(L.act_dtype())\n"
+        "    b = torch.randn(N, device='cuda', generator=g); C = torch.full((M, N), float('nan'), dtype=L.act_dtype(), device='cuda')\n"
         "    st = L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, act, 0, None)\n"
         "    torch.cuda.synchronize(); assert st == 0, L.last_error()\n"
         "    ref = A.float() @ W.float().t() + b\n"
@@ -166,30 +175,30 @@ def test_resid_ln(D, has_cls):
     rows = n_seq * n_patch + (n_seq if has_cls else 0)
     g = torch.Generator(device='cuda').manual_seed(D + has_cls)
     x = torch.randn(rows, D, device='cuda', generator=g)
-    delta = torch.randn(rows, D, device='cuda', generator=g).to(torch.bfloat16)
+    delta = torch.randn(rows, D, device='cuda', generator=g).to(_act())
     w = 1 + 0.1 * torch.randn(D, device='cuda', generator=g)
     b = 0.1 * torch.randn(D, device='cuda', generator=g)
     x_ref = x + delta.float()
     h_ref = torch.nn.functional.layer_norm(x_ref, (D,), w, b, 1e-6)
-    h = torch.zeros(rows, D, dtype=torch.bfloat16, device='cuda')
+    h = torch.zeros(rows, D, dtype=_act(), device='cuda')
     L.check(L.lib.vited_op_resid_ln(_ptr(x), _ptr(delta), _ptr(w), _ptr(b), _ptr(h), n_seq, n_patch, has_cls, D, 1e-6,
                                     _stream()), 'op_resid_ln')
     torch.cuda.synchronize()
     assert torch.equal(x, x_ref), 'residual update must be exact fp32'
-    # bf16 rounding of the normalised row: 2^-9 relative
-    assert (h.float() - h_ref).abs().max().item() <= 1e-2 * h_ref.abs().max().item() + 1e-3
+    # 16-bit rounding of the normalised row
+    assert (h.float() - h_ref).abs().max().item() <= (1e-2 * h_ref.abs().max().item() + 1e-3) * _r16()
 
 
 @pytest.mark.parametrize('shape', [(256, 384), (70000, 384), (33333, 1536), (1, 384), (300, 64), (40000, 192)],
                          ids=lambda s: 'x'.join(map(str, s)))
 def test_gemm_resid_ln_fused(shape):
-    """x += A W^T + b; h = LayerNorm(x): the fused tcgen05 epilogue against fp32 torch on the same bf16 operands."""
+    """x += A W^T + b; h = LayerNorm(x): the fused tcgen05 epilogue against fp32 torch on the same 16-bit operands."""
     L = _lib()
     M, K = shape
     N = 384
     g = torch.Generator(device='cuda').manual_seed(M + K)
-    A = torch.randn(M, K, device='cuda', generator=g).to(torch.bfloat16)
-    W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(torch.bfloat16)
+    A = torch.randn(M, K, device='cuda', generator=g).to(_act())
+    W = (torch.randn(N, K, device='cuda', generator=g) / math.sqrt(K)).to(_act())
     bias = torch.randn(N, device='cuda', generator=g)
     # rows with a large common offset exercise the shifted variance
     x = torch.randn(M, N, device='cuda', generator=g) * 2 + torch.randn(M, 1, device='cuda', generator=g) * 5
@@ -197,19 +206,19 @@ def test_gemm_resid_ln_fused(shape):
     lb = 0.1 * torch.randn(N, device='cuda', generator=g)
     x_ref = x + A.float() @ W.float().t() + bias
     h_ref = torch.nn.functional.layer_norm(x_ref, (N,), lw, lb, 1e-6)
-    h = torch.full((M, N), float('nan'), dtype=torch.bfloat16, device='cuda')
+    h = torch.full((M, N), float('nan'), dtype=_act(), device='cuda')
     L.check(L.lib.vited_op_gemm_resid_ln(_ptr(A), _ptr(W), _ptr(bias), _ptr(x), _ptr(lw), _ptr(lb), _ptr(h), M, N, K,
                                          1e-6, _stream()), 'op_gemm_resid_ln')
     torch.cuda.synchronize()
     assert torch.isfinite(h.float()).all() and torch.isfinite(x).all()
-    # fp32 accumulation-order noise only (the accumulator is never rounded to bf16 on this path)
+    # fp32 accumulation-order noise only (the accumulator is never rounded to 16 bits on this path)
     assert (x - x_ref).abs().max().item() < 1e-3 * max(1.0, x_ref.abs().max().item())
-    # bf16 rounding of the normalised row: 2^-9 relative
-    assert (h.float() - h_ref).abs().max().item() <= 1e-2 * h_ref.abs().max().item() + 2e-3
+    # 16-bit rounding of the normalised row
+    assert (h.float() - h_ref).abs().max().item() <= (1e-2 * h_ref.abs().max().item() + 2e-3) * _r16()
 
 
 def _attn_reference(q, k, v, scale):
-    # q [B,H,Nq,hd] etc, fp32 math on bf16-rounded inputs
+    # q [B,H,Nq,hd] etc, fp32 math on the 16-bit-rounded inputs
     s = (q.float() @ k.float().transpose(-1, -2)) * scale
     return s.softmax(dim=-1) @ v.float()
 
@@ -227,8 +236,8 @@ def test_self_attention(cfg, impl):
     D = H * hd
     rows = n_seq * n_patch + (n_seq if has_cls else 0)
     g = torch.Generator(device='cuda').manual_seed(sum(cfg))
-    qkv = torch.randn(rows, 3 * D, device='cuda', generator=g).to(torch.bfloat16)
-    o = torch.full((rows, D), float('nan'), dtype=torch.bfloat16, device='cuda')
+    qkv = torch.randn(rows, 3 * D, device='cuda', generator=g).to(_act())
+    o = torch.full((rows, D), float('nan'), dtype=_act(), device='cuda')
     scale = hd ** -0.5
     st = L.lib.vited_op_attention(_ptr(qkv), 3 * D, ctypes.c_void_p(qkv.data_ptr() + 2 * D), 3 * D,
                                   ctypes.c_void_p(qkv.data_ptr() + 4 * D), 3 * D, _ptr(o), D, n_seq, H, hd, n_patch,
@@ -243,8 +252,8 @@ def test_self_attention(cfg, impl):
     got_patch = o[:n_seq * n_patch].view(n_seq, n_patch, D).float()
     got = torch.cat([o[n_seq * n_patch:].view(n_seq, 1, D).float(), got_patch], dim=1) if has_cls else got_patch
     assert torch.isfinite(got).all()
-    # P is rounded to bf16 before P.V and the output is bf16: 2e-2 absolute on O(1) values
-    assert (got - ref).abs().max().item() < 2e-2, f'max err {(got - ref).abs().max().item()}'
+    # P is rounded to 16 bits before P.V and so is the output: 2e-2 (bf16) / 4e-3 (fp16) absolute on O(1) values
+    assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
 
 
 @pytest.mark.parametrize('impl', [0, 1, 2], ids=['fast', 'simt', 'mma_sync'])
@@ -258,10 +267,10 @@ def test_cross_attention(cfg, impl):
     D = H * hd
     rows = P * (n_patch + 1)
     g = torch.Generator(device='cuda').manual_seed(sum(cfg))
-    qb = torch.randn(rows, D, device='cuda', generator=g).to(torch.bfloat16)
-    kv = torch.randn(n_ctx * n_patch, 2 * D, device='cuda', generator=g).to(torch.bfloat16)
+    qb = torch.randn(rows, D, device='cuda', generator=g).to(_act())
+    kv = torch.randn(n_ctx * n_patch, 2 * D, device='cuda', generator=g).to(_act())
     idx = torch.randint(0, n_ctx, (P,), device='cuda', generator=g, dtype=torch.int32)
-    o = torch.full((rows, D), float('nan'), dtype=torch.bfloat16, device='cuda')
+    o = torch.full((rows, D), float('nan'), dtype=_act(), device='cuda')
     scale = hd ** -0.5
     st = L.lib.vited_op_attention(_ptr(qb), D, _ptr(kv), 2 * D, ctypes.c_void_p(kv.data_ptr() + 2 * D), 2 * D, _ptr(o),
                                   D, P, H, hd, n_patch, 1, n_patch, 0, n_ctx, _ptr(idx), scale, impl, _stream())
@@ -275,7 +284,7 @@ def test_cross_attention(cfg, impl):
     ref = _attn_reference(q, k, v, scale).permute(0, 2, 1, 3).reshape(P, n_patch + 1, D)
     got = torch.cat([o[P * n_patch:].view(P, 1, D), o[:P * n_patch].view(P, n_patch, D)], dim=1).float()
     assert torch.isfinite(got).all()
-    assert (got - ref).abs().max().item() < 2e-2, f'max err {(got - ref).abs().max().item()}'
+    assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
 
 
 @pytest.mark.parametrize('cfg', [(3, 3, 64, 8), (2, 3, 512, 16), (5, 3, 64, 32)])
@@ -285,8 +294,8 @@ def test_im2col_patch_indexing_is_exact(cfg):
     g = torch.Generator(device='cuda').manual_seed(0)
     img = torch.randn(B, C, S, S, device='cuda', generator=g)
     G = S // p
-    out = torch.zeros(B * G * G, C * p * p, dtype=torch.bfloat16, device='cuda')
+    out = torch.zeros(B * G * G, C * p * p, dtype=_act(), device='cuda')
     L.check(L.lib.vited_op_im2col(_ptr(img), _ptr(out), B, C, S, p, _stream()), 'op_im2col')
     torch.cuda.synchronize()
-    ref = img.reshape(B, C, G, p, G, p).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, C * p * p).to(torch.bfloat16)
+    ref = img.reshape(B, C, G, p, G, p).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, C * p * p).to(_act())
     assert torch.equal(out, ref), 'patch indexing must be bit-exact (SURVEY 8b)'

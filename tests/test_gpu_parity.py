@@ -1,8 +1,10 @@
 """GPU: the CUDA path through the reference-facing API against (a) the fixtures produced by the reference's own
 model file and (b) the fp32 oracle on the same seeded inputs; plus size-independent properties of the grid.
 
-Tolerance (BASELINE.json north_star): logits within 2e-2 absolute of the fp32 reference (bf16 operands, fp32
+Tolerance (BASELINE.json north_star): logits within 2e-2 absolute of the fp32 reference (16-bit operands, fp32
 accumulation); identical argmax on >= 99.9 % of pairs; integer work (pair placement, patch indexing) bit-exact.
+The default build rounds operands to fp16 (the reference's autocast dtype) and is held to the much tighter TIGHT below;
+a -DVITED_ACT_BF16=1 build is held to the north-star tolerance only (its measured error is 6e-3 .. 1.1e-2).
 """
 import numpy as np
 import pytest
@@ -13,6 +15,7 @@ from tests import helpers
 pytestmark = pytest.mark.gpu
 
 TOL = 2e-2
+TIGHT = 4e-3   # fp16 operands: measured max 1.1e-3 on the puzzle model (tests/analysis/err_budget.py)
 
 
 @pytest.mark.parametrize('name', helpers.MODEL_CASES)
@@ -26,7 +29,7 @@ def test_three_forward_modes_match_reference_fixture(name):
     one_shot = model(torch.stack([x1, x2], dim=1))
     torch.cuda.synchronize()
     assert tokens.shape == (x1.shape[0], (kw['img_size'] // kw['patch_size']) ** 2, kw['embed_dim'])
-    # encoder tokens: bf16 operands through `depth` blocks; values are O(1)
+    # encoder tokens: 16-bit operands through `depth` blocks; values are O(1)
     np.testing.assert_allclose(tokens[:, :4].cpu().numpy(), z['tokens_head'], rtol=0, atol=6e-2)
     rel = np.abs(tokens.double().sum(dim=(1, 2)).cpu().numpy() - z['tokens_sum']) / z['tokens_abs_sum']
     assert rel.max() < 2e-3
@@ -78,6 +81,30 @@ def test_puzzle_grid_matches_oracle(name, n_items):
         assert agree >= 0.9, f'argmax agreement {agree}'
 
 
+@pytest.mark.parametrize('weight_seed', [0, 5])
+def test_puzzle_model_north_star_tolerances(weight_seed):
+    """The north-star parity clause on the real puzzle model, 64 pieces = 4,032 ordered pairs per weight seed: logits
+    within tolerance of the fp32 oracle and the same argmax adjacency bin on >= 99.9 % of the pairs (random-init
+    weights: the four bins of a pair differ by ~0.15, so this is a far harder argmax case than a trained model)."""
+    import vited_b200
+    from oracle import vited_oracle as orc
+    from vited_b200 import grid
+    n_items = 64
+    model, sd, kw, images = _grid_case('puzzle_patch8_64', n_items, weight_seed=weight_seed, image_seed=33)
+    got = grid.score_puzzle(model, images.cuda()).cpu()
+    want = orc.score_puzzle_grid(sd, kw['num_heads'], images, batch=126)
+    off = ~torch.eye(n_items, dtype=torch.bool)
+    err = (got - want).abs()[off]
+    agree = (got.argmax(-1) == want.argmax(-1))[off].float().mean().item()
+    print(f'[{vited_b200.ACT_NAME}] seed {weight_seed}: max err {err.max().item():.5f} mean {err.mean().item():.5f} '
+          f'argmax agreement {agree:.5f}')
+    if vited_b200.ACT_NAME == 'fp16':
+        assert err.max().item() < TIGHT
+        assert agree >= 0.999, f'argmax agreement {agree}'
+    else:
+        assert err.max().item() < TOL
+
+
 @pytest.mark.parametrize('name,n_items', [('small_hd64', 7), ('test_patch32_64', 5)])
 def test_fragment_grid_matches_oracle(name, n_items):
     from oracle import vited_oracle as orc
@@ -104,7 +131,7 @@ def test_grid_properties_puzzle_model():
     off = ~torch.eye(n, dtype=torch.bool, device='cuda')
     assert (full[off] != 0).any(dim=-1).all(), 'an off-diagonal pair was left unwritten'
     # (1) grid entries == model(pairs) on sampled pairs (the 64-pair call is below the row count where the fused
-    #     GEMM + residual + LayerNorm epilogue is used, so its projections are rounded to bf16 once more: bf16 noise)
+    #     GEMM + residual + LayerNorm epilogue is used, so its projections are rounded to 16 bits once more: rounding noise)
     g = torch.Generator().manual_seed(3)
     pi = torch.randint(0, n, (64,), generator=g)
     pj = (pi + 1 + torch.randint(0, n - 1, (64,), generator=g)) % n
@@ -116,19 +143,19 @@ def test_grid_properties_puzzle_model():
     # (3) smaller chunks: same values
     model.set_option(vited_b200.OPT_CHUNK_ROWS, 65 * 50)
     small = grid.score_puzzle(model, images)
-    # (chunks this small take the unfused residual + LayerNorm path: one more bf16 rounding per sub-block)
+    # (chunks this small take the unfused residual + LayerNorm path: one more 16-bit rounding per sub-block)
     np.testing.assert_allclose(small.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=1e-2)
-    # (4) without the layer-0 cache (self-attention recomputed per pair): same values up to bf16 noise
+    # (4) without the layer-0 cache (self-attention recomputed per pair): same values up to rounding noise
     model.set_option(vited_b200.OPT_CACHE_LAYER0, 0)
     nocache = grid.score_puzzle(model, images)
     np.testing.assert_allclose(nocache.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=1e-2)
-    # (5) without last-layer pruning (all 65 rows carried to the end): same values up to bf16 noise
+    # (5) without last-layer pruning (all 65 rows carried to the end): same values up to rounding noise
     model.set_option(vited_b200.OPT_CACHE_LAYER0, 1)
     model.set_option(vited_b200.OPT_PRUNE_TAIL, 0)
     noprune = grid.score_puzzle(model, images)
     np.testing.assert_allclose(noprune.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=1e-2)
-    # (6) residual + LayerNorm as a separate kernel instead of the fused GEMM epilogue: same values up to bf16 noise
-    #     (the fused path never rounds the projection output to bf16 before the residual add)
+    # (6) residual + LayerNorm as a separate kernel instead of the fused GEMM epilogue: same values up to rounding noise
+    #     (the fused path never rounds the projection output to 16 bits before the residual add)
     model.set_option(vited_b200.OPT_PRUNE_TAIL, 1)
     model.set_option(vited_b200.OPT_FUSE_LN, 0)
     unfused = grid.score_puzzle(model, images)

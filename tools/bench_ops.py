@@ -47,10 +47,10 @@ def main():
     out = []
     for name, N, K, act in (('qkv', 1152, 384, 0), ('proj', 384, 384, 0), ('fc1_gelu', 1536, 384, 1),
                             ('fc2', 384, 1536, 0), ('kv', 768, 384, 0)):
-        A = torch.randn(M, K, device='cuda').bfloat16()
-        W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+        A = torch.randn(M, K, device='cuda').to(L.act_dtype())
+        W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).to(L.act_dtype())
         b = torch.randn(N, device='cuda')
-        C = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+        C = torch.empty(M, N, dtype=L.act_dtype(), device='cuda')
         for impl in (0,):
             ms = timeit(lambda: L.check(L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K,
                                                               act, impl, st), 'gemm'), flush=flush)
@@ -62,12 +62,12 @@ def main():
         out.append(dict(op=f'cublas_{name}', M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9))
     # fused GEMM + residual + LayerNorm (N = 384)
     for name, K in (('proj', 384), ('fc2', 1536)):
-        A = torch.randn(M, K, device='cuda').bfloat16()
-        W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).bfloat16()
+        A = torch.randn(M, K, device='cuda').to(L.act_dtype())
+        W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).to(L.act_dtype())
         b = torch.randn(384, device='cuda')
         xx = torch.randn(M, 384, device='cuda')
         lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
-        hh = torch.empty(M, 384, dtype=torch.bfloat16, device='cuda')
+        hh = torch.empty(M, 384, dtype=L.act_dtype(), device='cuda')
         ms = timeit(lambda: L.check(L.lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), xx.data_ptr(), lw.data_ptr(),
                                                                   lb.data_ptr(), hh.data_ptr(), M, 384, K, 1e-6, st), 'gemm_ln'), flush=flush)
         fl = 2.0 * M * 384 * K
@@ -77,17 +77,17 @@ def main():
     # resid + LN
     D = 384
     x = torch.randn(M, D, device='cuda')
-    delta = torch.randn(M, D, device='cuda').bfloat16()
+    delta = torch.randn(M, D, device='cuda').to(L.act_dtype())
     w = torch.ones(D, device='cuda'); bb = torch.zeros(D, device='cuda')
-    h = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+    h = torch.empty(M, D, dtype=L.act_dtype(), device='cuda')
     ms = timeit(lambda: L.check(L.lib.vited_op_resid_ln(x.data_ptr(), delta.data_ptr(), w.data_ptr(), bb.data_ptr(), h.data_ptr(),
                                                          4032, 64, 1, D, 1e-6, st), 'ln'), flush=flush)
     by = M * D * (4 + 2 + 4 + 2)
     out.append(dict(op='resid_ln', rows=M, ms=ms, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
     # attention (puzzle): self and cross
     P, H, hd, Np = 4032, 12, 32, 64
-    qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
-    o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+    qkv = torch.randn(M, 3 * D, device='cuda').to(L.act_dtype())
+    o = torch.empty(M, D, dtype=L.act_dtype(), device='cuda')
     for impl in (0, 2):
         ms = timeit(lambda: L.check(L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D,
                                                               3 * D, o.data_ptr(), D, P, H, hd, Np, 1, Np, 1, P, None, hd ** -0.5, impl, st),
@@ -95,8 +95,8 @@ def main():
         fl = 4.0 * P * H * 65 * 65 * hd
         by = M * D * 2 * 4
         out.append(dict(op=f'attn_self_impl{impl}', ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
-    kv = torch.randn(540 * Np, 2 * D, device='cuda').bfloat16()
-    q = torch.randn(M, D, device='cuda').bfloat16()
+    kv = torch.randn(540 * Np, 2 * D, device='cuda').to(L.act_dtype())
+    q = torch.randn(M, D, device='cuda').to(L.act_dtype())
     idx = (torch.arange(P, device='cuda') // 539).int()
     for impl in (0, 2):
         ms = timeit(lambda: L.check(L.lib.vited_op_attention(q.data_ptr(), D, kv.data_ptr(), 2 * D, kv.data_ptr() + 2 * D, 2 * D, o.data_ptr(), D,

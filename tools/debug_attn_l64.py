@@ -9,8 +9,8 @@ def run(n_seq, H, hd, n_patch, has_cls):
     D = H * hd
     rows = n_seq * n_patch + (n_seq if has_cls else 0)
     g = torch.Generator(device='cuda').manual_seed(1)
-    qkv = torch.randn(rows, 3 * D, device='cuda', generator=g).to(torch.bfloat16)
-    o = torch.full((rows, D), float('nan'), dtype=torch.bfloat16, device='cuda')
+    qkv = torch.randn(rows, 3 * D, device='cuda', generator=g).to(L.act_dtype())
+    o = torch.full((rows, D), float('nan'), dtype=L.act_dtype(), device='cuda')
     st = L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D, 3 * D, o.data_ptr(), D,
                                   n_seq, H, hd, n_patch, has_cls, n_patch, has_cls, n_seq, None, hd ** -0.5, 0, None)
     L.check(st, 'attn'); torch.cuda.synchronize()

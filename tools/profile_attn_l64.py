@@ -11,10 +11,10 @@ from vited_b200 import _lib as L  # noqa: E402
 P, H, hd, Np, D = 255, 6, 64, 1024, 384
 M = P * (Np + 1)
 torch.manual_seed(0)
-qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
-o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
-kv = torch.randn(32 * Np, 2 * D, device='cuda').bfloat16()
-q = torch.randn(M, D, device='cuda').bfloat16()
+qkv = torch.randn(M, 3 * D, device='cuda').to(L.act_dtype())
+o = torch.empty(M, D, dtype=L.act_dtype(), device='cuda')
+kv = torch.randn(32 * Np, 2 * D, device='cuda').to(L.act_dtype())
+q = torch.randn(M, D, device='cuda').to(L.act_dtype())
 idx = (torch.arange(P, device='cuda') % 32).int()
 
 

@@ -17,10 +17,10 @@ reps = int(os.environ.get('REPS', '2'))
 
 
 def gemm(N, K, act):
-    A = torch.randn(M, K, device='cuda').bfloat16()
-    W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).bfloat16()
+    A = torch.randn(M, K, device='cuda').to(L.act_dtype())
+    W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).to(L.act_dtype())
     b = torch.randn(N, device='cuda')
-    C = torch.empty(M, N, dtype=torch.bfloat16, device='cuda')
+    C = torch.empty(M, N, dtype=L.act_dtype(), device='cuda')
     for _ in range(reps):
         L.check(L.lib.vited_op_gemm(A.data_ptr(), W.data_ptr(), b.data_ptr(), C.data_ptr(), M, N, K, act, 0, None), 'gemm')
     torch.cuda.synchronize()
@@ -33,12 +33,12 @@ gemm(384, 384, 0)
 
 
 def gemm_ln(K):
-    A = torch.randn(M, K, device='cuda').bfloat16()
-    W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).bfloat16()
+    A = torch.randn(M, K, device='cuda').to(L.act_dtype())
+    W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).to(L.act_dtype())
     b = torch.randn(384, device='cuda')
     xx = torch.randn(M, 384, device='cuda')
     lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
-    hh = torch.empty(M, 384, dtype=torch.bfloat16, device='cuda')
+    hh = torch.empty(M, 384, dtype=L.act_dtype(), device='cuda')
     for _ in range(reps):
         L.check(L.lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), xx.data_ptr(), lw.data_ptr(), lb.data_ptr(),
                                              hh.data_ptr(), M, 384, K, 1e-6, None), 'gemm_ln')
@@ -48,21 +48,21 @@ def gemm_ln(K):
 gemm_ln(384)
 gemm_ln(1536)
 P, H, hd, Np = 4032, 12, 32, 64
-qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
-o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+qkv = torch.randn(M, 3 * D, device='cuda').to(L.act_dtype())
+o = torch.empty(M, D, dtype=L.act_dtype(), device='cuda')
 for _ in range(reps):
     L.check(L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D, 3 * D,
                                      o.data_ptr(), D, P, H, hd, Np, 1, Np, 1, P, None, hd ** -0.5, 0, None), 'attn')
-kv = torch.randn(540 * Np, 2 * D, device='cuda').bfloat16()
-q = torch.randn(M, D, device='cuda').bfloat16()
+kv = torch.randn(540 * Np, 2 * D, device='cuda').to(L.act_dtype())
+q = torch.randn(M, D, device='cuda').to(L.act_dtype())
 idx = (torch.arange(P, device='cuda') // 539).int()
 for _ in range(reps):
     L.check(L.lib.vited_op_attention(q.data_ptr(), D, kv.data_ptr(), 2 * D, kv.data_ptr() + 2 * D, 2 * D, o.data_ptr(), D,
                                      P, H, hd, Np, 1, Np, 0, 540, idx.data_ptr(), hd ** -0.5, 0, None), 'attn')
 x = torch.randn(M, D, device='cuda')
-delta = torch.randn(M, D, device='cuda').bfloat16()
+delta = torch.randn(M, D, device='cuda').to(L.act_dtype())
 w = torch.ones(D, device='cuda'); bb = torch.zeros(D, device='cuda')
-h = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+h = torch.empty(M, D, dtype=L.act_dtype(), device='cuda')
 for _ in range(reps):
     L.check(L.lib.vited_op_resid_ln(x.data_ptr(), delta.data_ptr(), w.data_ptr(), bb.data_ptr(), h.data_ptr(), 4032, 64, 1, D,
                                     1e-6, None), 'ln')

@@ -11,8 +11,8 @@ lib.vited_op_attention.restype = ci
 P, H, hd, Np, D = 4032, 12, 32, 64, 384
 M = P * 65
 torch.manual_seed(0)
-qkv = torch.randn(M, 3 * D, device='cuda').bfloat16()
-o = torch.empty(M, D, dtype=torch.bfloat16, device='cuda')
+qkv = torch.randn(M, 3 * D, device='cuda').to(torch.float16)
+o = torch.empty(M, D, dtype=torch.float16, device='cuda')
 for _ in range(2):
     assert lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D, 3 * D,
                                   o.data_ptr(), D, P, H, hd, Np, 1, Np, 1, P, None, hd ** -0.5, 0, None) == 0

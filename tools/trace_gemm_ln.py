@@ -10,11 +10,11 @@ lib.vited_op_gemm_resid_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, c
 lib.vited_op_gemm_resid_ln.restype = ci
 M = 4032 * 65
 for K in (384, 1536):
-    A = torch.randn(M, K, device='cuda').bfloat16()
-    W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).bfloat16()
+    A = torch.randn(M, K, device='cuda').to(torch.float16)
+    W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).to(torch.float16)
     b = torch.randn(384, device='cuda'); x = torch.randn(M, 384, device='cuda')
     lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
-    h = torch.empty(M, 384, dtype=torch.bfloat16, device='cuda')
+    h = torch.empty(M, 384, dtype=torch.float16, device='cuda')
     for _ in range(2):
         assert lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), x.data_ptr(), lw.data_ptr(), lb.data_ptr(), h.data_ptr(), M, 384, K, 1e-6, None) == 0
     torch.cuda.synchronize()

@@ -63,6 +63,7 @@ SIGNATURES = {
     "vited_score_grid": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "vited_profile_json": (ctypes.c_char_p, [_vp, _vp]),
     "vited_launch_count": (_i64, [_vp]),
+    "vited_act_dtype": (_i, []),
     "vited_workspace_bytes": (_i64, [_vp]),
     "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vited_op_gemm_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
@@ -87,6 +88,16 @@ def _load():
 
 
 lib = _load()
+
+
+def act_dtype():
+    """torch dtype of the 16-bit operands the single-kernel entry points take (fp16 unless built with
+    -DVITED_ACT_BF16=1); ``ACT_NAME`` is the matching string for bench.py's ``dtype``."""
+    import torch
+    return torch.bfloat16 if lib.vited_act_dtype() == 1 else torch.float16
+
+
+ACT_NAME = 'bf16' if lib.vited_act_dtype() == 1 else 'fp16'
 
 
 def last_error() -> str:

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArg
   constexpr int PIECES = HD / 8;
   extern __shared__ uint8_t attn_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_smem_raw) + 1023) & ~uintptr_t(1023));
-  bf16* sO = reinterpret_cast<bf16*>(smem + NST * SM::STAGE);
+  act_t* sO = reinterpret_cast<act_t*>(smem + NST * SM::STAGE);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * SM::STAGE + SM::OB);
   uint64_t* empty = full + NST;
 
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArg
           const int c16 = ks * 2 + (mi & 1);
           uint32_t b0, b1, b2, b3;
           ldsm_x4(sK + key * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
-          mma_bf16_16816(s[2 * np], qf[ks], b0, b1);
-          mma_bf16_16816(s[2 * np + 1], qf[ks], b2, b3);
+          mma_f16_16816(s[2 * np], qf[ks], b0, b1);
+          mma_f16_16816(s[2 * np + 1], qf[ks], b2, b3);
         }
       }
       if (with_cls_key) {
@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArg
           const int c16 = ks * 2 + mi;
           uint32_t b0, b1, b2, b3;
           ldsm_x4(sK + (64 + ri) * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
-          mma_bf16_16816(s[8], qf[ks], b0, b1);
-          mma_bf16_16816(s[8], qf[ks + 1], b2, b3);
+          mma_f16_16816(s[8], qf[ks], b0, b1);
+          mma_f16_16816(s[8], qf[ks + 1], b2, b3);
         }
       }
       // ---- online softmax (rows g and g+8 of this warp's tile) ----
@@ -251,25 +251,25 @@ __global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArg
 #pragma unroll
       for (int k2 = 0; k2 < 4; ++k2) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * k2][0], s[2 * k2][1]);
-        pa[1] = pack_bf16(s[2 * k2][2], s[2 * k2][3]);
-        pa[2] = pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
-        pa[3] = pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+        pa[0] = pack_act(s[2 * k2][0], s[2 * k2][1]);
+        pa[1] = pack_act(s[2 * k2][2], s[2 * k2][3]);
+        pa[2] = pack_act(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+        pa[3] = pack_act(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
 #pragma unroll
         for (int dp = 0; dp < HD / 16; ++dp) {
           const int key = k2 * 16 + (mi & 1) * 8 + ri;
           const int c16 = dp * 2 + (mi >> 1);
           uint32_t b0, b1, b2, b3;
           ldsm_x4_trans(sV + key * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
-          mma_bf16_16816(o_acc[2 * dp], pa, b0, b1);
-          mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
+          mma_f16_16816(o_acc[2 * dp], pa, b0, b1);
+          mma_f16_16816(o_acc[2 * dp + 1], pa, b2, b3);
         }
       }
       if (with_cls_key) {
         // fifth k-step: keys 64..79 (64 = class token, 65..79 are zero rows with zero probabilities)
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[8][0], s[8][1]);
-        pa[1] = pack_bf16(s[8][2], s[8][3]);
+        pa[0] = pack_act(s[8][0], s[8][1]);
+        pa[1] = pack_act(s[8][2], s[8][3]);
         pa[2] = 0u;
         pa[3] = 0u;
 #pragma unroll
@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArg
           const int c16 = dp * 2 + (mi >> 1);
           uint32_t b0, b1, b2, b3;
           ldsm_x4_trans(sV + key * RB + ((c16 ^ sw) << 4), b0, b1, b2, b3);
-          mma_bf16_16816(o_acc[2 * dp], pa, b0, b1);
-          mma_bf16_16816(o_acc[2 * dp + 1], pa, b2, b3);
+          mma_f16_16816(o_acc[2 * dp], pa, b0, b1);
+          mma_f16_16816(o_acc[2 * dp + 1], pa, b2, b3);
         }
       }
     }
@@ -300,13 +300,13 @@ __global__ void __launch_bounds__(160, HD == 32 ? 4 : 2) attn_mma_kernel(AttnArg
 #pragma unroll
       for (int nt = 0; nt < HD / 8; ++nt) {
         *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g) * OLD + nt * 8 + 2 * t]) =
-            pack_bf16(o_acc[nt][0] * i0, o_acc[nt][1] * i0);
+            pack_act(o_acc[nt][0] * i0, o_acc[nt][1] * i0);
         *reinterpret_cast<uint32_t*>(&sO[(warp * 16 + g + 8) * OLD + nt * 8 + 2 * t]) =
-            pack_bf16(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
+            pack_act(o_acc[nt][2] * i1, o_acc[nt][3] * i1);
       }
       __syncwarp();
       if (warp < 4) {
-        bf16* obase = a.o + ((size_t)b * a.nq_patch + q0) * a.o_ld + h * HD;
+        act_t* obase = a.o + ((size_t)b * a.nq_patch + q0) * a.o_ld + h * HD;
         for (int idx = lane; idx < 16 * PIECES; idx += 32) {
           const int row = warp * 16 + idx / PIECES, pc = idx % PIECES;
           if (q0 + row < a.nq_patch)
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(AttnArgs a) {
   if (valid) {
     const size_t row = tok_row(a.n_seq, a.nq_patch, a.q_has_cls, b, sq);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = __bfloat162float(a.q[row * a.q_ld + h * HD + d]);
+    for (int d = 0; d < HD; ++d) q[d] = act2f(a.q[row * a.q_ld + h * HD + d]);
   }
 #pragma unroll
   for (int d = 0; d < HD; ++d) o[d] = 0.f;
@@ -360,8 +360,8 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(AttnArgs a) {
       float kv = 0.f, vv = 0.f;
       if (k0 + kk < nk) {
         const size_t row = tok_row(a.n_kv_seq, a.nk_patch, a.k_has_cls, kvb, k0 + kk);
-        kv = __bfloat162float(a.k[row * a.k_ld + h * HD + d]);
-        vv = __bfloat162float(a.v[row * a.v_ld + h * HD + d]);
+        kv = act2f(a.k[row * a.k_ld + h * HD + d]);
+        vv = act2f(a.v[row * a.v_ld + h * HD + d]);
       }
       Ks[kk][d] = kv;
       Vs[kk][d] = vv;
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(AttnArgs a) {
     const size_t row = tok_row(a.n_seq, a.nq_patch, a.q_has_cls, b, sq);
     const float inv = 1.f / l;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) a.o[row * a.o_ld + h * HD + d] = __float2bfloat16_rn(o[d] * inv);
+    for (int d = 0; d < HD; ++d) a.o[row * a.o_ld + h * HD + d] = f2act(o[d] * inv);
   }
 }
 
@@ -454,12 +454,12 @@ static int attention_launch(const AttnArgs& a, int cls_only, cudaStream_t stream
   const uint64_t q_rows = (uint64_t)a.n_seq * a.nq_patch + (a.q_has_cls ? a.n_seq : 0);
   const uint64_t k_rows = (uint64_t)a.n_kv_seq * a.nk_patch + (a.k_has_cls ? a.n_kv_seq : 0);
   AttnMaps maps;
-  if (make_tmap_bf16_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, HD, 64, swz)) return 1;
-  if (make_tmap_bf16_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, HD, 1, swz)) return 1;
-  if (make_tmap_bf16_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, HD, 64, swz)) return 1;
-  if (make_tmap_bf16_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, HD, 1, swz)) return 1;
-  if (make_tmap_bf16_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, HD, 64, swz)) return 1;
-  if (make_tmap_bf16_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, HD, 1, swz)) return 1;
+  if (make_tmap_act_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, HD, 64, swz)) return 1;
+  if (make_tmap_act_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, HD, 1, swz)) return 1;
+  if (make_tmap_act_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, HD, 64, swz)) return 1;
+  if (make_tmap_act_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, HD, 1, swz)) return 1;
+  if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, HD, 64, swz)) return 1;
+  if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, HD, 1, swz)) return 1;
   if (a.head_dim == 32)
     attn_mma_kernel<32><<<(unsigned)grid, 160, AttnSmem<32>::BYTES, stream>>>(a, maps, (int)items, cls_only);
   else

@@ -4,7 +4,7 @@
 // attn_p64_kernel -- puzzle model: 64 patch tokens (+ class token) per sequence, head_dim 32.
 //   One work unit = one (sequence, head): S = Q K^T is ONE 128 x {64|80} tcgen05.mma pair (rows 0..63 = patch queries,
 //   row 64 = the class-token query, rows 65..127 unused), softmax runs with one thread per query row straight out of
-//   TMEM, the probabilities go back to TMEM as packed bf16 (aliasing S) and feed the second MMA as its A operand,
+//   TMEM, the probabilities go back to TMEM as packed fp16 (aliasing S) and feed the second MMA as its A operand,
 //   O = P V with V consumed in place as an MN-major operand (no transpose, no ldmatrix, no shuffles).
 //   Warp roles (16 warps, 1 CTA / SM): warp 3 = TMA producer (12-deep ring of Q/K/V tiles, hardware 64B swizzle),
 //   warp 7 = MMA issuer (lean, warp-uniform, serves the groups' units in round-robin order: PV of a unit, then QK^T
@@ -144,8 +144,8 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
       // probabilities are in TMEM, QK^T of the same group's next unit (i + NT) right behind it (the tensor pipe runs in
       // issue order, so those scores may overwrite P(i)). When the groups' first warps issued their own MMAs that cost
       // them ~850 cycles per unit on the group's critical path (tools/trace_attn_p64.py).
-      const uint32_t idesc_qk = umma_idesc_bf16(128, NK);
-      const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
+      const uint32_t idesc_qk = umma_idesc_f16(128, NK);
+      const uint32_t idesc_pv = umma_idesc_f16(128, C::HD) | kIdescBMajorMN;
       const uint32_t smem0 = smem_u32(smem);
       auto issue_qk = [&](int i) {      // S(stage i % NT) = Q K^T of local unit i
         const int s = i % C::NS, t = i % C::NT;
@@ -157,7 +157,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
         const uint32_t t_col = tmem_base + t * C::TCOLS;
         if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < C::HD / 16; ++k) umma_bf16(t_col, dq + 2 * k, dk + 2 * k, idesc_qk, k);
+          for (int k = 0; k < C::HD / 16; ++k) umma_f16(t_col, dq + 2 * k, dk + 2 * k, idesc_qk, k);
           umma_commit(&s_full[t]);
         }
         __syncwarp();
@@ -173,11 +173,11 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
           if (NK == 80) {
 #pragma unroll
             for (int k = 0; k < 5; ++k)   // 16 keys per step = two 8-key groups of 512 B = +64 in the (addr >> 4) field
-              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
+              umma_f16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
+              umma_f16_ts(t_col + C::OCOL, t_col + 8 * k, dv + 64 * k, idesc_pv, k);
           }
           umma_commit(&empty[s]);
           umma_commit(&o_full[t]);
@@ -188,7 +188,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
     }
   } else {
     // ===================== softmax group `group`, TMEM lane quarter `quarter` =====================
-    // The group owns TMEM stage `group`: scores -> probabilities (packed bf16 over S) -> signal the issuer -> read O.
+    // The group owns TMEM stage `group`: scores -> probabilities (packed fp16 over S) -> signal the issuer -> read O.
     const float sl2 = a.scale * kLog2e;
     const int row = quarter * 32 + lane;                  // query row of the unit's tile
     // quarter 2 only carries the class-token query (row 64); in cls_only mode it is the only live row
@@ -227,20 +227,20 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
           const float p0 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j]), sl2, mneg));
           const float p1 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j + 1]), sl2, mneg));
           sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
-          pk[j] = pack_bf16(p0, p1);
+          pk[j] = pack_act(p0, p1);
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float p0 = ex2_ftz(fmaf(__uint_as_float(v1[2 * j]), sl2, mneg));
           const float p1 = ex2_ftz(fmaf(__uint_as_float(v1[2 * j + 1]), sl2, mneg));
           sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
-          pk[16 + j] = pack_bf16(p0, p1);
+          pk[16 + j] = pack_act(p0, p1);
         }
         tmem_st_32x32b_x32(t_stage, pk);
         if (a.k_has_cls) {
           const float pc = ex2_ftz(fmaf(__uint_as_float(vc[0]), sl2, mneg));
           sum[0] += pc;
-          uint32_t pc8[8] = {pack_bf16(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          uint32_t pc8[8] = {pack_act(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           tmem_st_32x32b_x8(t_stage + 32, pc8);
         }
         l = (sum[0] + sum[1]) + (sum[2] + sum[3]);
@@ -268,10 +268,10 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 w;
-            w.x = pack_bf16(__uint_as_float(ov[8 * c + 0]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
-            w.y = pack_bf16(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
-            w.z = pack_bf16(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
-            w.w = pack_bf16(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
+            w.x = pack_act(__uint_as_float(ov[8 * c + 0]) * inv, __uint_as_float(ov[8 * c + 1]) * inv);
+            w.y = pack_act(__uint_as_float(ov[8 * c + 2]) * inv, __uint_as_float(ov[8 * c + 3]) * inv);
+            w.z = pack_act(__uint_as_float(ov[8 * c + 4]) * inv, __uint_as_float(ov[8 * c + 5]) * inv);
+            w.w = pack_act(__uint_as_float(ov[8 * c + 6]) * inv, __uint_as_float(ov[8 * c + 7]) * inv);
             dst[c] = w;
           }
         }
@@ -294,7 +294,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
 // attn_l64_kernel -- Hisfrag model: long sequences (patch tokens a multiple of 256 queries / 128 keys), head_dim 64.
 //   Work item = (sequence, head, 256 patch queries): two softmax groups (128 query rows = 4 warps, one thread per row)
 //   share one ring of 128-key K/V stages. A group consumes a stage as two 64-key HALF TILES with two score buffers in
-//   TMEM: while its threads run the softmax of half tile u (tcgen05.ld -> row max -> ex2 -> packed bf16 P written back
+//   TMEM: while its threads run the softmax of half tile u (tcgen05.ld -> row max -> ex2 -> packed fp16 P written back
 //   over S with tcgen05.st), the tensor pipe executes PV(u-1) and QK^T(u+1), issued earlier by the MMA warp -- the MMA
 //   round trip is hidden behind the other buffer's softmax and the group never idles. P feeds the second MMA straight
 //   from TMEM (A operand), V is consumed in place as an MN-major operand.
@@ -432,8 +432,8 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
     // no bookkeeping beyond a few counters: an earlier version with one generic cursor-driven warp for both groups
     // spent ~1300 cycles per PV + QK^T pair and starved the softmax warps (tools/trace_attn_l64.py).
     const int g = warp - 9;
-    const uint32_t idesc_qk64 = umma_idesc_bf16(128, 64), idesc_qk16 = umma_idesc_bf16(128, 16);
-    const uint32_t idesc_pv = umma_idesc_bf16(128, C::HD) | kIdescBMajorMN;
+    const uint32_t idesc_qk64 = umma_idesc_f16(128, 64), idesc_qk16 = umma_idesc_f16(128, 16);
+    const uint32_t idesc_pv = umma_idesc_f16(128, C::HD) | kIdescBMajorMN;
     const uint32_t t_col = tmem_base + g * C::GCOLS;
     const uint32_t kv_base = smem_u32(sKV);
     int stage = 0, qs = 0;          // K/V stage of the next PV / of the next QK^T
@@ -463,7 +463,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         if (elect_one_sync()) {
 #pragma unroll
           for (int k = 0; k < C::HD / 16; ++k)
-            umma_bf16(t_s, dq + 2 * k, dk + 2 * k, cls_tile ? idesc_qk16 : idesc_qk64, k);
+            umma_f16(t_s, dq + 2 * k, dk + 2 * k, cls_tile ? idesc_qk16 : idesc_qk64, k);
           umma_commit(&s_full[g * 2 + (j & 1)]);
           if (last) umma_commit(&q_empty[qb]);
         }
@@ -482,11 +482,11 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         const uint64_t dv = umma_desc_sw(kv_base + stage * C::STAGE + C::KVB + (u & 1) * (64 * C::RB), 128);
         if (elect_one_sync()) {
           if (cls_tile) {
-            umma_bf16_ts(t_col + C::OCOL, t_p, dv, idesc_pv, u != 0 ? 1u : 0u);
+            umma_f16_ts(t_col + C::OCOL, t_p, dv, idesc_pv, u != 0 ? 1u : 0u);
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)   // 16 keys per step = two 8-key groups of 1024 B = +128 in the (addr >> 4) field
-              umma_bf16_ts(t_col + C::OCOL, t_p + 8 * k, dv + 128 * k, idesc_pv, (u | k) != 0 ? 1u : 0u);
+              umma_f16_ts(t_col + C::OCOL, t_p + 8 * k, dv + 128 * k, idesc_pv, (u | k) != 0 ? 1u : 0u);
           }
           umma_commit(&o_done[g * 2 + (pj & 1)]);
           if (stage_done) umma_commit(&kv_empty[stage]);
@@ -568,7 +568,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
               const float p0 = ex2_ftz(fmaf(__uint_as_float(v0[2 * e]), sl2, mneg));
               const float p1 = ex2_ftz(fmaf(__uint_as_float(v0[2 * e + 1]), sl2, mneg));
               sum[(2 * e) & 3] += p0; sum[(2 * e + 1) & 3] += p1;
-              pk[e] = pack_bf16(p0, p1);
+              pk[e] = pack_act(p0, p1);
             }
             tmem_st_32x32b_x16(t_s, pk);
           }
@@ -579,7 +579,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
               const float p0 = ex2_ftz(fmaf(__uint_as_float(v1[2 * e]), sl2, mneg));
               const float p1 = ex2_ftz(fmaf(__uint_as_float(v1[2 * e + 1]), sl2, mneg));
               sum[(2 * e) & 3] += p0; sum[(2 * e + 1) & 3] += p1;
-              pk[e] = pack_bf16(p0, p1);
+              pk[e] = pack_act(p0, p1);
             }
             tmem_st_32x32b_x16(t_s + 16, pk);
           }
@@ -594,7 +594,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
           else if (mt > m + 8.f) rescale(mt, m, l);
           const float pc = ex2_ftz(mt - m);
           l += pc;
-          uint32_t pc8[8] = {pack_bf16(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+          uint32_t pc8[8] = {pack_act(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};
           tmem_st_32x32b_x8(t_s, pc8);
         }
         tmem_st_wait();
@@ -603,7 +603,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[sb]);   // 4 warps: P (and any rescaled O row) is in TMEM -> PV may be issued
       }
-      // ---- item epilogue: O / l -> bf16 -> global ----
+      // ---- item epilogue: O / l -> fp16 -> global ----
       wait_pv(j - 1, 71);
       tc_fence_after();
       {
@@ -622,10 +622,10 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               uint4 w;
-              w.x = pack_bf16(__uint_as_float(ov[8 * e + 0]) * inv, __uint_as_float(ov[8 * e + 1]) * inv);
-              w.y = pack_bf16(__uint_as_float(ov[8 * e + 2]) * inv, __uint_as_float(ov[8 * e + 3]) * inv);
-              w.z = pack_bf16(__uint_as_float(ov[8 * e + 4]) * inv, __uint_as_float(ov[8 * e + 5]) * inv);
-              w.w = pack_bf16(__uint_as_float(ov[8 * e + 6]) * inv, __uint_as_float(ov[8 * e + 7]) * inv);
+              w.x = pack_act(__uint_as_float(ov[8 * e + 0]) * inv, __uint_as_float(ov[8 * e + 1]) * inv);
+              w.y = pack_act(__uint_as_float(ov[8 * e + 2]) * inv, __uint_as_float(ov[8 * e + 3]) * inv);
+              w.z = pack_act(__uint_as_float(ov[8 * e + 4]) * inv, __uint_as_float(ov[8 * e + 5]) * inv);
+              w.w = pack_act(__uint_as_float(ov[8 * e + 6]) * inv, __uint_as_float(ov[8 * e + 7]) * inv);
               dst[4 * c + e] = w;
             }
           }
@@ -666,12 +666,12 @@ static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
   const uint64_t q_rows = (uint64_t)a.n_seq * a.nq_patch + (a.q_has_cls ? a.n_seq : 0);
   const uint64_t k_rows = (uint64_t)a.n_kv_seq * a.nk_patch + (a.k_has_cls ? a.n_kv_seq : 0);
   L64Maps maps;
-  if (make_tmap_bf16_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 64, 128, 128)) return 1;
-  if (make_tmap_bf16_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 64, 1, 128)) return 1;
-  if (make_tmap_bf16_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 64, 128, 128)) return 1;
-  if (make_tmap_bf16_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 64, 1, 128)) return 1;
-  if (make_tmap_bf16_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 128, 128)) return 1;
-  if (make_tmap_bf16_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 1, 128)) return 1;
+  if (make_tmap_act_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 64, 128, 128)) return 1;
+  if (make_tmap_act_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 64, 1, 128)) return 1;
+  if (make_tmap_act_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 64, 128, 128)) return 1;
+  if (make_tmap_act_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 64, 1, 128)) return 1;
+  if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 128, 128)) return 1;
+  if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 1, 128)) return 1;
   const unsigned grid = (unsigned)(items < (size_t)sms ? items : (size_t)sms);
   attn_l64_kernel<<<grid, L64::THREADS, L64::BYTES, stream>>>(a, maps, (int)items);
   VITED_CUDA_OK(cudaGetLastError());
@@ -707,12 +707,12 @@ static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream
   const uint64_t q_rows = (uint64_t)a.n_seq * 64 + (a.q_has_cls ? a.n_seq : 0);
   const uint64_t k_rows = (uint64_t)a.n_kv_seq * 64 + (a.k_has_cls ? a.n_kv_seq : 0);
   P64Maps maps;
-  if (make_tmap_bf16_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 32, 64, 64)) return 1;
-  if (make_tmap_bf16_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 32, 1, 64)) return 1;
-  if (make_tmap_bf16_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 32, 64, 64)) return 1;
-  if (make_tmap_bf16_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 32, 1, 64)) return 1;
-  if (make_tmap_bf16_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 64, 64)) return 1;
-  if (make_tmap_bf16_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 1, 64)) return 1;
+  if (make_tmap_act_2d(&maps.q_tile, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 32, 64, 64)) return 1;
+  if (make_tmap_act_2d(&maps.q_row, a.q, cols, q_rows, (uint64_t)a.q_ld * 2, 32, 1, 64)) return 1;
+  if (make_tmap_act_2d(&maps.k_tile, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 32, 64, 64)) return 1;
+  if (make_tmap_act_2d(&maps.k_row, a.k, cols, k_rows, (uint64_t)a.k_ld * 2, 32, 1, 64)) return 1;
+  if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 64, 64)) return 1;
+  if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 1, 64)) return 1;
   const unsigned grid = (unsigned)(units < (size_t)sms ? units : (size_t)sms);
   attn_p64_kernel<<<grid, P64::THREADS, P64::BYTES, stream>>>(a, maps, (int)units, cls_only);
   VITED_CUDA_OK(cudaGetLastError());

@@ -3,13 +3,27 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
 
 namespace vited {
 
-typedef __nv_bfloat16 bf16;
+// The 16-bit type of every GEMM / attention operand and of every activation buffer. fp16 (11 significand bits) by
+// default: it is the reference's own autocast dtype (config.py:216 AMP_ENABLE, fp16 GradScaler path) and gives ~6x
+// smaller logit error against the fp32 reference than bf16 at the same speed and bytes (tests/analysis/
+// sim_operand_dtype.py: max 1e-3 vs 6e-3..8e-3). Everything that can grow -- residual stream, LayerNorm statistics,
+// softmax, accumulators -- stays fp32, and conversions saturate to +-65504 instead of producing inf.
+// -DVITED_ACT_BF16=1 builds the bf16 variant (same kernels; used for the A/B error measurement).
+#ifndef VITED_ACT_BF16
+#define VITED_ACT_BF16 0
+#endif
+#if VITED_ACT_BF16
+typedef __nv_bfloat16 act_t;
+#else
+typedef __half act_t;
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // host side error plumbing (no exceptions cross the C-ABI; see include/vited_b200.h)
@@ -42,14 +56,40 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_act(float lo, float hi) {
+#if VITED_ACT_BF16
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+#else
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+#endif
 }
 
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+__device__ __forceinline__ float2 unpack_act(uint32_t u) {
+#if VITED_ACT_BF16
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+#else
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+#endif
+}
+
+__device__ __forceinline__ float act2f(act_t v) {
+#if VITED_ACT_BF16
+  return __bfloat162float(v);
+#else
+  return __half2float(v);
+#endif
+}
+__device__ __forceinline__ act_t f2act(float v) {
+#if VITED_ACT_BF16
+  return __float2bfloat16_rn(v);
+#else
+  return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+#endif
 }
 
 // one lane of a converged warp (always the same one: lane 0 for a full mask). Issuing tcgen05.mma / commit under this
@@ -192,8 +232,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]; bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc]; fp16 x fp16 -> fp32, issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -228,7 +268,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[
                : "r"(taddr)
                : "memory");
 }
-// registers -> TMEM (each thread writes its own lane = tile row); used to hand softmax probabilities (packed bf16
+// registers -> TMEM (each thread writes its own lane = tile row); used to hand softmax probabilities (packed fp16
 // pairs, one 32-bit column = two consecutive K elements) to tcgen05.mma as the A operand
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
@@ -254,8 +294,8 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// D[tmem] (+)= A[tmem, packed bf16 pairs] * B[smem desc]
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[tmem, packed fp16 pairs] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -310,7 +350,7 @@ __device__ __forceinline__ void tma_load_2d_2cta_mc(const CUtensorMap* tm, uint6
       : "memory");
 }
 // D[tmem, both CTAs] (+)= A * B with M = 256 split over the pair; issued by ONE thread of the leader CTA
-__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -342,7 +382,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (tile rows are 128 B = 64 bf16; 8-row groups are
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (tile rows are 128 B = 64 fp16; 8-row groups are
 // 1024 B apart). Field layout follows the PTX ISA "matrix descriptor" (start>>4 | LBO>>4 @16 | SBO>>4 @32 |
 // version=1 @46 | swizzle mode @61, 2 = 128B).
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
@@ -381,10 +421,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr, uint32_t sw
   return d;
 }
 constexpr uint32_t kIdescBMajorMN = 1u << 16;   // B operand is MN-major (rows of the smem tile are K indices)
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, MxN.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32 (bit 4), A and B formats in bits 7..9 / 10..12 (0 = fp16, 1 = bf16), both
+// K-major, MxN.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(VITED_ACT_BF16) << 7) | (static_cast<uint32_t>(VITED_ACT_BF16) << 10) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -401,9 +442,13 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint3
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
+#if VITED_ACT_BF16
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+#else
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+#endif
       "{%0, %1, %2, %3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));

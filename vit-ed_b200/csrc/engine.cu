@@ -5,10 +5,10 @@
 // Data layout in HBM:
 //   * token rows use the "split" layout: n_seq*N_e patch rows followed by n_seq class-token rows, so that 64/1024
 //     patch tokens per sequence tile exactly into 64-row attention tiles and GEMMs run over one flat row space;
-//   * residual stream x is fp32 [rows, D]; every GEMM operand/result is bf16; sub-block outputs are written as a
-//     bf16 `delta` and folded into x by the fused residual+LayerNorm kernel;
+//   * residual stream x is fp32 [rows, D]; every GEMM operand/result is fp16; sub-block outputs are written as a
+//     fp16 `delta` and folded into x by the fused residual+LayerNorm kernel;
 //   * per grid: Xsrc = decoder input of every item (after layer-0 self-attention when cached), fp32 split layout;
-//     KV[l] = kv(norm_context(enc_tokens)) for the current block of context rows, bf16 [rows*N_e, 2D].
+//     KV[l] = kv(norm_context(enc_tokens)) for the current block of context rows, fp16 [rows*N_e, 2D].
 #include "../../include/vited_b200.h"
 #include "kernels.h"
 
@@ -55,14 +55,14 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct Linear { bf16* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct Linear { act_t* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
 struct LNorm { float* w = nullptr; float* b = nullptr; };
 struct EncBlock { LNorm norm1, norm2; Linear qkv, proj, fc1, fc2; };
 struct DecBlock { LNorm norm1, norm_cross, norm_context, norm2; Linear qkv, proj, q, kv, cproj, fc1, fc2; };
 
 struct Slot {
   void* dst;
-  bool to_bf16;
+  bool to_act;
   int64_t numel;
   bool loaded;
 };
@@ -125,20 +125,20 @@ static int alloc_f32(vited_engine* e, float** p, size_t n) {
   e->owned.push_back(*p);
   return 0;
 }
-static int alloc_bf16(vited_engine* e, bf16** p, size_t n) {
-  VITED_CUDA_OK(cudaMalloc(p, n * sizeof(bf16)));
-  VITED_CUDA_OK(cudaMemset(*p, 0, n * sizeof(bf16)));
+static int alloc_act(vited_engine* e, act_t** p, size_t n) {
+  VITED_CUDA_OK(cudaMalloc(p, n * sizeof(act_t)));
+  VITED_CUDA_OK(cudaMemset(*p, 0, n * sizeof(act_t)));
   e->owned.push_back(*p);
   return 0;
 }
-static void reg(vited_engine* e, const std::string& name, void* dst, bool to_bf16, int64_t numel) {
-  e->slots[name] = Slot{dst, to_bf16, numel, false};
+static void reg(vited_engine* e, const std::string& name, void* dst, bool to_act, int64_t numel) {
+  e->slots[name] = Slot{dst, to_act, numel, false};
   e->names.push_back(name);
 }
 static int make_linear(vited_engine* e, const std::string& prefix, Linear* l, int out, int in, bool bias) {
   l->out = out;
   l->in = in;
-  TRY(alloc_bf16(e, &l->w, (size_t)out * in));
+  TRY(alloc_act(e, &l->w, (size_t)out * in));
   TRY(alloc_f32(e, &l->b, out));  // stays zero when the reference layer has no bias (qkv_bias=False)
   reg(e, prefix + ".weight", l->w, true, (int64_t)out * in);
   if (bias) reg(e, prefix + ".bias", l->b, false, out);
@@ -238,7 +238,7 @@ static void prof_mark(vited_engine* e, const char* name, double flops, double by
   e->recs.push_back({ev, prof_class(e, name), flops, bytes});
 }
 
-static int L_gemm(vited_engine* e, const bf16* A, const Linear& l, bf16* Cout, int M, int act, cudaStream_t s) {
+static int L_gemm(vited_engine* e, const act_t* A, const Linear& l, act_t* Cout, int M, int act, cudaStream_t s) {
   if (e->profile) {
     char nm[64];
     snprintf(nm, sizeof(nm), "gemm_n%d_k%d%s", l.out, l.in, act == ACT_GELU ? "_gelu" : "");
@@ -246,13 +246,13 @@ static int L_gemm(vited_engine* e, const bf16* A, const Linear& l, bf16* Cout, i
   } else {
     e->launches++;
   }
-  return gemm_bf16(A, l.w, l.b, Cout, M, l.out, l.in, act, e->gemm_impl, s);
+  return gemm_act(A, l.w, l.b, Cout, M, l.out, l.in, act, e->gemm_impl, s);
 }
 // fused x += A W^T + b; h = LN(x)  (gemm_ln.cu). Caller has checked use_fused_ln().
 static bool use_fused_ln(vited_engine* e, size_t rows, const Linear& l) {
   return e->fuse_ln && e->gemm_impl == IMPL_FAST && rows >= 8192 && gemm_resid_ln_supported((int)rows, l.out, l.in);
 }
-static int L_gemm_ln(vited_engine* e, const bf16* A, const Linear& l, float* x, const LNorm& ln, bf16* h, int M,
+static int L_gemm_ln(vited_engine* e, const act_t* A, const Linear& l, float* x, const LNorm& ln, act_t* h, int M,
                      cudaStream_t s) {
   if (e->profile) {
     char nm[64];
@@ -264,8 +264,8 @@ static int L_gemm_ln(vited_engine* e, const bf16* A, const Linear& l, float* x, 
   }
   return gemm_resid_ln(A, l.w, l.b, x, ln.w, ln.b, h, M, l.out, l.in, 1e-6f, s);
 }
-static int L_resid_ln(vited_engine* e, float* x, const bf16* delta, const float* gsrc, const int* gidx, int n_src,
-                      const LNorm* ln, bf16* h, int n_seq, int has_cls, int write_x, cudaStream_t s) {
+static int L_resid_ln(vited_engine* e, float* x, const act_t* delta, const float* gsrc, const int* gidx, int n_src,
+                      const LNorm* ln, act_t* h, int n_seq, int has_cls, int write_x, cudaStream_t s) {
   ResidLnArgs a;
   a.x = x; a.delta = delta; a.gather_src = gsrc; a.gather_idx = gidx; a.n_src_seq = n_src;
   a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
@@ -277,7 +277,7 @@ static int L_resid_ln(vited_engine* e, float* x, const bf16* delta, const float*
   }
   return resid_ln(a, s);
 }
-static int L_attn_self(vited_engine* e, const bf16* qkv, bf16* o, int n_seq, int has_cls, cudaStream_t s) {
+static int L_attn_self(vited_engine* e, const act_t* qkv, act_t* o, int n_seq, int has_cls, cudaStream_t s) {
   AttnArgs a;
   const int D = e->D;
   a.q = qkv; a.q_ld = 3 * D; a.k = qkv + D; a.k_ld = 3 * D; a.v = qkv + 2 * D; a.v_ld = 3 * D; a.o = o; a.o_ld = D;
@@ -290,7 +290,7 @@ static int L_attn_self(vited_engine* e, const bf16* qkv, bf16* o, int n_seq, int
   }
   return attention(a, e->attn_impl, s);
 }
-static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o, int n_seq, int n_kv_seq,
+static int L_attn_cross(vited_engine* e, const act_t* q, const act_t* kv, act_t* o, int n_seq, int n_kv_seq,
                         const int* kv_index, cudaStream_t s) {
   AttnArgs a;
   const int D = e->D;
@@ -304,7 +304,7 @@ static int L_attn_cross(vited_engine* e, const bf16* q, const bf16* kv, bf16* o,
 
 // class-token-only attention (last decoder layer). q/o are the full split-layout buffers: only their class-token rows
 // (row n_seq*Ne + b) are read / written.
-static int L_attn_cls(vited_engine* e, const bf16* q, int q_ld, const bf16* k, const bf16* v, int kv_ld, bf16* o,
+static int L_attn_cls(vited_engine* e, const act_t* q, int q_ld, const act_t* k, const act_t* v, int kv_ld, act_t* o,
                       int n_seq, int k_has_cls, int n_kv_seq, const int* kv_index, cudaStream_t s) {
   AttnArgs a;
   a.q = q; a.q_ld = q_ld; a.k = k; a.k_ld = kv_ld; a.v = v; a.v_ld = kv_ld; a.o = o; a.o_ld = e->D;
@@ -316,8 +316,8 @@ static int L_attn_cls(vited_engine* e, const bf16* q, int q_ld, const bf16* k, c
   return attention_cls(a, s);
 }
 // resid_ln over a plain block of `rows` rows (no split-layout bookkeeping): used for the class-token rows alone
-static int L_resid_ln_rows(vited_engine* e, float* x, const bf16* delta, const float* gsrc_cls_rows, const int* gidx,
-                           const LNorm* ln, bf16* h, int rows, cudaStream_t s) {
+static int L_resid_ln_rows(vited_engine* e, float* x, const act_t* delta, const float* gsrc_cls_rows, const int* gidx,
+                           const LNorm* ln, act_t* h, int rows, cudaStream_t s) {
   ResidLnArgs a;
   a.x = x; a.delta = delta; a.gather_src = gsrc_cls_rows; a.gather_idx = gidx; a.n_src_seq = 0;
   a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
@@ -352,7 +352,7 @@ static int items_per_batch(vited_engine* e) {
   return (int)(n < 1 ? 1 : n);
 }
 
-// patch tokens of B images -> e->tok (bf16 [B*Ne, D]); img_stride = elements between consecutive images
+// patch tokens of B images -> e->tok (fp16 [B*Ne, D]); img_stride = elements between consecutive images
 static int patch_tokens(vited_engine* e, const float* images, size_t img_stride, int B, cudaStream_t s) {
   const vited_config& c = e->cfg;
   const size_t rows = (size_t)B * e->Ne;
@@ -361,15 +361,15 @@ static int patch_tokens(vited_engine* e, const float* images, size_t img_stride,
   const size_t img_elems = (size_t)c.in_chans * c.img_size * c.img_size;
   if (img_stride == img_elems) {
     prof_mark(e, "im2col", 0.0, (double)rows * e->Kpe * 6.0, s);
-    TRY(im2col_patches(images, e->col.as<bf16>(), B, c.in_chans, c.img_size, c.patch_size, s));
+    TRY(im2col_patches(images, e->col.as<act_t>(), B, c.in_chans, c.img_size, c.patch_size, s));
   } else {
     for (int b = 0; b < B; ++b) {
       prof_mark(e, "im2col", 0.0, (double)e->Ne * e->Kpe * 6.0, s);
-      TRY(im2col_patches(images + (size_t)b * img_stride, e->col.as<bf16>() + (size_t)b * e->Ne * e->Kpe, 1, c.in_chans,
+      TRY(im2col_patches(images + (size_t)b * img_stride, e->col.as<act_t>() + (size_t)b * e->Ne * e->Kpe, 1, c.in_chans,
                          c.img_size, c.patch_size, s));
     }
   }
-  TRY(L_gemm(e, e->col.as<bf16>(), e->patch, e->tok.as<bf16>(), (int)rows, ACT_NONE, s));
+  TRY(L_gemm(e, e->col.as<act_t>(), e->patch, e->tok.as<act_t>(), (int)rows, ACT_NONE, s));
   return 0;
 }
 
@@ -378,19 +378,19 @@ static int encoder_stack(vited_engine* e, int B, float* out_tokens, cudaStream_t
   const size_t rows = (size_t)B * e->Ne;
   TRY(ensure_rows(e, rows));
   float* x = e->x.as<float>();
-  bf16* h = e->h.as<bf16>();
-  bf16* delta = e->delta.as<bf16>();
+  act_t* h = e->h.as<act_t>();
+  act_t* delta = e->delta.as<act_t>();
   prof_mark(e, "assemble", 0.0, (double)rows * e->D * 6.0, s);
-  TRY(assemble_tokens(e->tok.as<bf16>(), e->pos, e->cls, x, B, e->Ne, e->D, 0, s));
+  TRY(assemble_tokens(e->tok.as<act_t>(), e->pos, e->cls, x, B, e->Ne, e->D, 0, s));
   for (size_t l = 0; l < e->enc.size(); ++l) {
     EncBlock& b = e->enc[l];
     TRY(L_resid_ln(e, x, l == 0 ? nullptr : delta, nullptr, nullptr, 0, &b.norm1, h, B, 0, l == 0 ? 0 : 1, s));
-    TRY(L_gemm(e, h, b.qkv, e->qkv.as<bf16>(), (int)rows, ACT_NONE, s));
-    TRY(L_attn_self(e, e->qkv.as<bf16>(), e->o.as<bf16>(), B, 0, s));
-    TRY(L_gemm(e, e->o.as<bf16>(), b.proj, delta, (int)rows, ACT_NONE, s));
+    TRY(L_gemm(e, h, b.qkv, e->qkv.as<act_t>(), (int)rows, ACT_NONE, s));
+    TRY(L_attn_self(e, e->qkv.as<act_t>(), e->o.as<act_t>(), B, 0, s));
+    TRY(L_gemm(e, e->o.as<act_t>(), b.proj, delta, (int)rows, ACT_NONE, s));
     TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, B, 0, 1, s));
-    TRY(L_gemm(e, h, b.fc1, e->hid.as<bf16>(), (int)rows, ACT_GELU, s));
-    TRY(L_gemm(e, e->hid.as<bf16>(), b.fc2, delta, (int)rows, ACT_NONE, s));
+    TRY(L_gemm(e, h, b.fc1, e->hid.as<act_t>(), (int)rows, ACT_GELU, s));
+    TRY(L_gemm(e, e->hid.as<act_t>(), b.fc2, delta, (int)rows, ACT_NONE, s));
   }
   prof_mark(e, "add_delta_out", 0.0, (double)rows * e->D * 10.0, s);
   TRY(add_delta_out(x, delta, out_tokens, rows, e->D, s));
@@ -404,14 +404,14 @@ static int decoder_item_state(vited_engine* e, int B, cudaStream_t s) {
   TRY(ensure_rows(e, rows));
   float* x = e->x.as<float>();
   prof_mark(e, "assemble", 0.0, (double)rows * e->D * 6.0, s);
-  TRY(assemble_tokens(e->tok.as<bf16>(), e->pos, e->cls, x, B, e->Ne, e->D, 1, s));
+  TRY(assemble_tokens(e->tok.as<act_t>(), e->pos, e->cls, x, B, e->Ne, e->D, 1, s));
   if (e->cache_layer0) {
     DecBlock& b = e->dec[0];
-    TRY(L_resid_ln(e, x, nullptr, nullptr, nullptr, 0, &b.norm1, e->h.as<bf16>(), B, 1, 0, s));
-    TRY(L_gemm(e, e->h.as<bf16>(), b.qkv, e->qkv.as<bf16>(), (int)rows, ACT_NONE, s));
-    TRY(L_attn_self(e, e->qkv.as<bf16>(), e->o.as<bf16>(), B, 1, s));
-    TRY(L_gemm(e, e->o.as<bf16>(), b.proj, e->delta.as<bf16>(), (int)rows, ACT_NONE, s));
-    TRY(L_resid_ln(e, x, e->delta.as<bf16>(), nullptr, nullptr, 0, nullptr, nullptr, B, 1, 1, s));
+    TRY(L_resid_ln(e, x, nullptr, nullptr, nullptr, 0, &b.norm1, e->h.as<act_t>(), B, 1, 0, s));
+    TRY(L_gemm(e, e->h.as<act_t>(), b.qkv, e->qkv.as<act_t>(), (int)rows, ACT_NONE, s));
+    TRY(L_attn_self(e, e->qkv.as<act_t>(), e->o.as<act_t>(), B, 1, s));
+    TRY(L_gemm(e, e->o.as<act_t>(), b.proj, e->delta.as<act_t>(), (int)rows, ACT_NONE, s));
+    TRY(L_resid_ln(e, x, e->delta.as<act_t>(), nullptr, nullptr, 0, nullptr, nullptr, B, 1, 1, s));
   }
   return 0;
 }
@@ -428,7 +428,7 @@ static int scatter_split(vited_engine* e, float* dst, int N, int i0, int B, cuda
 }
 
 // kv(norm_context(ctx)) for every decoder layer (vision_transformer.py:270, :178): ctx [n*Ne, D] f32 ->
-// e->kv, layer l at offset l * n*Ne*2D (bf16)
+// e->kv, layer l at offset l * n*Ne*2D (fp16)
 static int build_kv(vited_engine* e, const float* ctx, int n, cudaStream_t s) {
   const size_t rows = (size_t)n * e->Ne;
   const size_t per_layer = rows * 2 * e->D;
@@ -436,9 +436,9 @@ static int build_kv(vited_engine* e, const float* ctx, int n, cudaStream_t s) {
   TRY(e->h.ensure(rows * e->D * 2));
   for (size_t l = 0; l < e->dec.size(); ++l) {
     DecBlock& b = e->dec[l];
-    TRY(L_resid_ln(e, const_cast<float*>(ctx), nullptr, nullptr, nullptr, 0, &b.norm_context, e->h.as<bf16>(), n, 0, 0,
+    TRY(L_resid_ln(e, const_cast<float*>(ctx), nullptr, nullptr, nullptr, 0, &b.norm_context, e->h.as<act_t>(), n, 0, 0,
                    s));
-    TRY(L_gemm(e, e->h.as<bf16>(), b.kv, e->kv.as<bf16>() + l * per_layer, (int)rows, ACT_NONE, s));
+    TRY(L_gemm(e, e->h.as<act_t>(), b.kv, e->kv.as<act_t>() + l * per_layer, (int)rows, ACT_NONE, s));
   }
   return 0;
 }
@@ -452,12 +452,12 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
   const size_t D = e->D;
   const size_t cls_off = (size_t)P * e->Ne;      // first class-token row in every [rows, *] buffer
   float* x = e->x.as<float>();
-  bf16* h = e->h.as<bf16>();
-  bf16* delta = e->delta.as<bf16>();
-  bf16* qkv = e->qkv.as<bf16>();
-  bf16* o = e->o.as<bf16>();
-  bf16* q = e->q.as<bf16>();
-  bf16* hid = e->hid.as<bf16>();
+  act_t* h = e->h.as<act_t>();
+  act_t* delta = e->delta.as<act_t>();
+  act_t* qkv = e->qkv.as<act_t>();
+  act_t* o = e->o.as<act_t>();
+  act_t* q = e->q.as<act_t>();
+  act_t* hid = e->hid.as<act_t>();
   const size_t kv_per_layer = (size_t)n_kv_seq * e->Ne * 2 * D;
   const size_t L = e->dec.size();
   // With FUSE_LN the residual add + LayerNorm of a sub-block boundary runs in the epilogue of the GEMM that produces
@@ -471,7 +471,7 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
     // In the last layer only row 0 (the class token) of every sequence reaches the head, so after the keys/values of
     // its self-attention are formed every kernel runs on the P class-token rows alone.
     const bool tail = e->prune_tail && (l + 1 == L);
-    const bf16* kvl = e->kv.as<bf16>() + l * kv_per_layer;
+    const act_t* kvl = e->kv.as<act_t>() + l * kv_per_layer;
     if (!tail) {
       if (first && e->cache_layer0) {
         TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s));
@@ -505,10 +505,10 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
       }
     } else {
       float* x_c = x + cls_off * D;
-      bf16* h_c = h + cls_off * D;
-      bf16* d_c = delta + cls_off * D;
-      bf16* q_c = q + cls_off * D;
-      bf16* o_c = o + cls_off * D;
+      act_t* h_c = h + cls_off * D;
+      act_t* d_c = delta + cls_off * D;
+      act_t* q_c = q + cls_off * D;
+      act_t* o_c = o + cls_off * D;
       if (first && e->cache_layer0) {
         // single-layer decoder with the layer-0 cache: gather the class-token rows only
         TRY(L_resid_ln_rows(e, x_c, nullptr, xsrc + (size_t)n_src * e->Ne * D, xj, &b.norm_cross, h_c, P, s));
@@ -625,8 +625,8 @@ int vited_load_weight(vited_engine* e, const char* name, const float* data, int6
   VITED_CHECK(sl.numel == numel, "size mismatch for %s: expected %lld elements, got %lld", name, (long long)sl.numel,
               (long long)numel);
   cudaStream_t s = (cudaStream_t)stream;
-  if (sl.to_bf16) {
-    TRY(f32_to_bf16(data, reinterpret_cast<bf16*>(sl.dst), (size_t)numel, s));
+  if (sl.to_act) {
+    TRY(f32_to_act(data, reinterpret_cast<act_t*>(sl.dst), (size_t)numel, s));
   } else {
     VITED_CUDA_OK(cudaMemcpyAsync(sl.dst, data, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
   }
@@ -814,24 +814,25 @@ const char* vited_profile_json(vited_engine* e, void* stream) {
 }
 
 int64_t vited_launch_count(vited_engine* e) { return e ? e->launches : 0; }
+int vited_act_dtype(void) { return VITED_ACT_BF16 ? 1 : 0; }
 int64_t vited_workspace_bytes(vited_engine* e) { return e ? e->workspace_bytes() : 0; }
 
 // ---- single-kernel entry points ----
 int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,
                   void* stream) {
-  return gemm_bf16((const bf16*)A, (const bf16*)W, bias, (bf16*)C, M, N, K, act, impl, (cudaStream_t)stream);
+  return gemm_act((const act_t*)A, (const act_t*)W, bias, (act_t*)C, M, N, K, act, impl, (cudaStream_t)stream);
 }
 
 int vited_op_gemm_resid_ln(const void* A, const void* W, const float* bias, float* x, const float* ln_w,
                            const float* ln_b, void* h, int M, int N, int K, float eps, void* stream) {
-  return gemm_resid_ln((const bf16*)A, (const bf16*)W, bias, x, ln_w, ln_b, (bf16*)h, M, N, K, eps, (cudaStream_t)stream);
+  return gemm_resid_ln((const act_t*)A, (const act_t*)W, bias, x, ln_w, ln_b, (act_t*)h, M, N, K, eps, (cudaStream_t)stream);
 }
 
 int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
                       int n_patch, int has_cls, int D, float eps, void* stream) {
   ResidLnArgs a;
-  a.x = x; a.delta = (const bf16*)delta; a.gather_src = nullptr; a.gather_idx = nullptr; a.n_src_seq = 0;
-  a.ln_w = ln_w; a.ln_b = ln_b; a.h = (bf16*)h; a.n_seq = n_seq; a.n_patch = n_patch; a.has_cls = has_cls; a.D = D;
+  a.x = x; a.delta = (const act_t*)delta; a.gather_src = nullptr; a.gather_idx = nullptr; a.n_src_seq = 0;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.h = (act_t*)h; a.n_seq = n_seq; a.n_patch = n_patch; a.has_cls = has_cls; a.D = D;
   a.write_x = 1; a.eps = eps;
   return resid_ln(a, (cudaStream_t)stream);
 }
@@ -840,15 +841,15 @@ int vited_op_attention(const void* q, int q_ld, const void* k, int k_ld, const v
                        int n_seq, int n_heads, int head_dim, int nq_patch, int q_has_cls, int nk_patch,
                        int k_has_cls, int n_kv_seq, const int32_t* kv_index, float scale, int impl, void* stream) {
   AttnArgs a;
-  a.q = (const bf16*)q; a.q_ld = q_ld; a.k = (const bf16*)k; a.k_ld = k_ld; a.v = (const bf16*)v; a.v_ld = v_ld;
-  a.o = (bf16*)o; a.o_ld = o_ld; a.n_seq = n_seq; a.n_heads = n_heads; a.head_dim = head_dim;
+  a.q = (const act_t*)q; a.q_ld = q_ld; a.k = (const act_t*)k; a.k_ld = k_ld; a.v = (const act_t*)v; a.v_ld = v_ld;
+  a.o = (act_t*)o; a.o_ld = o_ld; a.n_seq = n_seq; a.n_heads = n_heads; a.head_dim = head_dim;
   a.nq_patch = nq_patch; a.q_has_cls = q_has_cls; a.nk_patch = nk_patch; a.k_has_cls = k_has_cls;
   a.n_kv_seq = n_kv_seq; a.kv_index = kv_index; a.scale = scale;
   return attention(a, impl, (cudaStream_t)stream);
 }
 
 int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, void* stream) {
-  return im2col_patches(images, (bf16*)out, B, C, S, p, (cudaStream_t)stream);
+  return im2col_patches(images, (act_t*)out, B, C, S, p, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,10 +1,10 @@
 // Fused Linear + residual add + LayerNorm for the N = embed_dim = 384 projections of the ViT-ED blocks:
 //     x += A * W^T + bias          (attn.proj / cross_attn.proj / mlp.fc2; vision_transformer.py:125-126, :269-271)
 //     h  = LayerNorm(x) * g + b    (the NEXT sub-block's norm: norm_cross / norm2 / next layer's norm1; eps 1e-6)
-// The unfused path writes the GEMM result as a bf16 `delta`, and a second kernel (resid_ln, 98 % of HBM peak, 23 % of the
+// The unfused path writes the GEMM result as a fp16 `delta`, and a second kernel (resid_ln, 98 % of HBM peak, 23 % of the
 // step) re-reads it together with x. Here a CTA pair owns complete 256 x 384 output rows: the accumulator row stays in
 // TMEM (384 fp32 columns), the residual tile streams through small TMA boxes, the updated row is parked back in TMEM
-// (tcgen05.st) while the row statistics are combined, and the normalised bf16 row leaves through TMA stores.
+// (tcgen05.st) while the row statistics are combined, and the normalised fp16 row leaves through TMA stores.
 //
 // Structure = gemm_tc_pair_kernel (cta_group::2, TMA ring, one MMA thread) with N = 384 issued as two N = 192 MMAs per
 // k-step and a full-row epilogue: 8 epilogue warps per CTA, warp (q, c) owns TMEM lane quarter q (32 rows) and the
@@ -31,7 +31,7 @@ struct LnCfg {
   static constexpr int kStages = 3;
   static constexpr uint32_t XBOX = 32 * 32 * 4;                    // 32 rows x 32 fp32, 128B-swizzled
   static constexpr uint32_t X_BYTES = kEpiWarps * 2 * XBOX;
-  static constexpr uint32_t H_BYTES = kEpiWarps * 4096;            // 32 rows x 64 bf16 per warp
+  static constexpr uint32_t H_BYTES = kEpiWarps * 4096;            // 32 rows x 64 fp16 per warp
   static constexpr uint32_t PARAM_BYTES = 3 * LN_N * 4;
   static constexpr uint32_t PART_BYTES = 2 * BM * 16;
   static constexpr uint32_t BAR_BYTES = 512;
@@ -126,7 +126,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only): two N = 192 MMAs per k-step =====================
     if (rank == 0) {   // warp-uniform loop, tcgen05 instructions predicated on one elected lane
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, NH);
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, NH);
       constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4, kA16 = Cfg::A_BYTES >> 4, kBH16 = Cfg::BH_BYTES >> 4;
       const uint32_t lo0 = umma_desc_sw128_lo(smem_u32(smem));   // stage 0: A tile, then the two 96-row weight halves
       uint32_t stage = 0, phase = 0, aphase = 0;
@@ -144,9 +144,9 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t da = umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi);
-              umma_bf16_2cta(tmem_base, da, umma_desc_pack(lo_a + kA16 + 2 * k, kUmmaDescSw128Hi), idesc,
+              umma_f16_2cta(tmem_base, da, umma_desc_pack(lo_a + kA16 + 2 * k, kUmmaDescSw128Hi), idesc,
                              (kb | k) != 0 ? 1u : 0u);
-              umma_bf16_2cta(tmem_base + NH, da, umma_desc_pack(lo_a + kA16 + kBH16 + 2 * k, kUmmaDescSw128Hi), idesc,
+              umma_f16_2cta(tmem_base + NH, da, umma_desc_pack(lo_a + kA16 + kBH16 + 2 * k, kUmmaDescSw128Hi), idesc,
                              (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit_2cta(&empty[stage]);
@@ -246,7 +246,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float var = (m2_a + m2_b + dm * dm * (0.5f * NH)) * (1.f / LN_N);
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
       if (who >= 0) TRL(who, t, 3);
-      // ---- pass 2: normalise out of TMEM, bf16, 64-column slabs through the warp's staging box ----
+      // ---- pass 2: normalise out of TMEM, fp16, 64-column slabs through the warp's staging box ----
 #pragma unroll 1
       for (int jj = 0; jj < CHUNKS / 2; ++jj) {
         if (lane == 0) tma_store_wait_read();
@@ -273,10 +273,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               y[e] = fmaf(__uint_as_float(v[8 * i + e]) - mean, ga, sBt[col0 + 8 * i + e]);
             }
             uint4 pk;
-            pk.x = pack_bf16(y[0], y[1]);
-            pk.y = pack_bf16(y[2], y[3]);
-            pk.z = pack_bf16(y[4], y[5]);
-            pk.w = pack_bf16(y[6], y[7]);
+            pk.x = pack_act(y[0], y[1]);
+            pk.y = pack_act(y[2], y[3]);
+            pk.z = pack_act(y[4], y[5]);
+            pk.w = pack_act(y[6], y[7]);
             *reinterpret_cast<uint4*>(hbox + lane * 128 + (((hh * 4 + i) ^ sw) << 4)) = pk;
           }
         }
@@ -306,8 +306,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 bool gemm_resid_ln_supported(int M, int N, int K) { return N == LN_N && K % 8 == 0 && K >= 8 && M >= 1; }
 
-int gemm_resid_ln(const bf16* A, const bf16* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
-                  bf16* h, int M, int N, int K, float eps, cudaStream_t stream) {
+int gemm_resid_ln(const act_t* A, const act_t* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
+                  act_t* h, int M, int N, int K, float eps, cudaStream_t stream) {
   VITED_CHECK(gemm_resid_ln_supported(M, N, K), "gemm_resid_ln: unsupported shape M=%d N=%d K=%d (N must be 384)", M, N, K);
   VITED_CHECK(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x) |
                 reinterpret_cast<uintptr_t>(h)) & 15) == 0, "gemm_resid_ln: operands must be 16-byte aligned");
@@ -320,10 +320,10 @@ int gemm_resid_ln(const bf16* A, const bf16* W, const float* bias, float* x, con
     attr_set = true;
   }
   CUtensorMap tA, tB, tX, tH;
-  if (make_tmap_bf16_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, BM, 128)) return 1;
-  if (make_tmap_bf16_2d(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, NH / 2, 128)) return 1;
+  if (make_tmap_act_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, BM, 128)) return 1;
+  if (make_tmap_act_2d(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, NH / 2, 128)) return 1;
   if (make_tmap_f32_2d(&tX, x, (uint64_t)N, (uint64_t)M, (uint64_t)N * 4, 32, 32, 128)) return 1;
-  if (make_tmap_bf16_2d(&tH, h, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 64, 32, 128)) return 1;
+  if (make_tmap_act_2d(&tH, h, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 64, 32, 128)) return 1;
   const int tiles = (M + 2 * BM - 1) / (2 * BM);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;

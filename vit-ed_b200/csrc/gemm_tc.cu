@@ -1,14 +1,14 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators
+// Persistent, warp-specialised fp16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma (accumulators
 // in TMEM, double buffered) -> tcgen05.ld epilogue (bias / exact-erf GELU) -> swizzled smem staging -> TMA store.
 //
 // Computes what every Linear on the ViT-ED hot path computes (reference: models/vision_transformer.py:34,38 qkv/proj,
 // :151-156 q/kv/proj, timm Mlp fc1/fc2, timm PatchEmbed conv-as-GEMM):  C = act(A * W^T + bias).
-//   A [M,K] bf16 row-major (activations), W [N,K] bf16 row-major (PyTorch Linear layout) -> both operands K-major.
+//   A [M,K] fp16 row-major (activations), W [N,K] fp16 row-major (PyTorch Linear layout) -> both operands K-major.
 //
 // Warp roles (128 + 32*4*BN/64 threads, 1 CTA / SM):
 //   warp 0 lane 0 : TMA producer            warp 1 lane 0 : tcgen05.mma issuer
 //   warp 2        : TMEM allocator          warps 4..     : epilogue; warp (q, sl) owns TMEM lane quarter q = warp%4
-//                                             and the 64-column slab sl, stages its 32x64 bf16 sub-tile in a private
+//                                             and the 64-column slab sl, stages its 32x64 fp16 sub-tile in a private
 //                                             4 KB swizzled buffer and TMA-stores it itself (no CTA-wide barrier).
 #include "kernels.h"
 #include <cudaTypedefs.h>
@@ -41,14 +41,14 @@ int gemm_num_sms() {
   return g_num_sms;
 }
 
-// 2-D bf16 tensor map: inner dim = cols (contiguous), outer dim = rows, 128B swizzle, box = 64 cols x box_rows.
+// 2-D fp16 tensor map: inner dim = cols (contiguous), outer dim = rows, 128B swizzle, box = 64 cols x box_rows.
 static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                      uint32_t box_rows) {
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {row_stride_bytes};
   cuuint32_t box[2] = {64, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = g_encode(tm, VITED_ACT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -59,8 +59,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t r
   return 0;
 }
 
-// generic 2-D bf16 tensor map for other kernels (attention): box = box_cols x box_rows, swizzle_bytes in {0, 64, 128}
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+// generic 2-D fp16 tensor map for other kernels (attention): box = box_cols x box_rows, swizzle_bytes in {0, 64, 128}
+int make_tmap_act_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   std::call_once(g_once, init_driver_once);
   if (g_init_status) return 1;
@@ -70,7 +70,7 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t 
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = g_encode(tm, VITED_ACT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -131,7 +131,7 @@ struct GemmCfg {
 
 // exact-erf GELU with ONE MUFU op: gelu(v) = max(v, 0) - 0.5*|v|*erfc(|v|/sqrt(2)), and erfc(a/sqrt(2)) = 2^(-Q(a)) with a
 // cubic Q (all coefficients positive, so 2^(-Q) decays monotonically for any |v|) fitted minimax on the GELU value:
-// |error| < 9e-5 everywhere, 1/50 of the bf16 rounding step of an O(1) activation (the result is stored as bf16).
+// |error| < 9e-5 everywhere, 1/50 of the fp16 rounding step of an O(1) activation (the result is stored as fp16).
 // 6 FP32 ops + ex2.approx. The fc1 epilogue is instruction-issue bound (16 epilogue warps x 64 columns per tile), so
 // every op counts: the degree-5 fit (6e-7) cost two more FMAs per element. (fit: tools/fit_gelu.py)
 __device__ __forceinline__ float gelu_fast(float v) {
@@ -144,7 +144,7 @@ __device__ __forceinline__ float gelu_fast(float v) {
   return fmaf(-0.5f * a, e, fmaxf(v, 0.0f));
 }
 
-// bias (+ GELU) on one thread's 64 accumulator columns, packed to bf16 and written into the warp's 32x128-byte staging
+// bias (+ GELU) on one thread's 64 accumulator columns, packed to fp16 and written into the warp's 32x128-byte staging
 // box in the 128B-swizzle pattern the TMA store expects (16-byte chunk c of row r lives at chunk c ^ (r & 7)).
 template <int ACT>
 __device__ __forceinline__ void epilogue_tile(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
@@ -177,10 +177,10 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t (&v0)[32], const ui
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       uint4 pk;
-      pk.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-      pk.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-      pk.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-      pk.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
+      pk.x = pack_act(f[8 * i + 0], f[8 * i + 1]);
+      pk.y = pack_act(f[8 * i + 2], f[8 * i + 3]);
+      pk.z = pack_act(f[8 * i + 4], f[8 * i + 5]);
+      pk.w = pack_act(f[8 * i + 6], f[8 * i + 7]);
       *reinterpret_cast<uint4*>(rowp + (((ch * 4 + i) ^ (lane & 7)) << 4)) = pk;
     }
   }
@@ -287,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     // warp-uniform loop, tcgen05 instructions predicated on one elected lane (see elect_one_sync)
     {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       if (kResident && tile0 < m_blks) mbar_wait(pfull, 0, 22);
       int m_blk, n_blk;
@@ -304,8 +304,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              // advance 16 bf16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              umma_bf16(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi), umma_desc_pack(lo_b + 2 * k, kUmmaDescSw128Hi),
+              // advance 16 fp16 = 32 B along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              umma_f16(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi), umma_desc_pack(lo_b + 2 * k, kUmmaDescSw128Hi),
                         idesc, (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
@@ -462,7 +462,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // The whole warp runs the loop (warp-uniform control flow and descriptors); only the tcgen05 instructions are
     // predicated on one elected lane.
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
       constexpr uint32_t kStage16 = Cfg::STAGE_BYTES >> 4, kA16 = Cfg::A_BYTES >> 4;
       const uint32_t lo0 = umma_desc_sw128_lo(smem_u32(smem));   // A tile of stage 0; the B half tile follows it
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
@@ -476,8 +476,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t lo_a = lo0 + stage * kStage16;
           if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)   // 16 bf16 = 32 B along K inside the swizzle atom: +2 in the address field
-              umma_bf16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
+            for (int k = 0; k < BK / 16; ++k)   // 16 fp16 = 32 B along K inside the swizzle atom: +2 in the address field
+              umma_f16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
                              umma_desc_pack(lo_a + kA16 + 2 * k, kUmmaDescSw128Hi), idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2cta(&empty[stage]);   // frees this stage in BOTH CTAs
           }
@@ -621,7 +621,7 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA of each pair; warp-uniform, elected lane) =====================
     if (r == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc = umma_idesc_f16(2 * BM, BN);
       const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = cluster; tile < num_tiles; tile += num_clusters) {
@@ -635,7 +635,7 @@ gemm_tc_quad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
+              umma_f16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
                              umma_desc_pack(lo_a + (Cfg::A_BYTES >> 4) + 2 * k, kUmmaDescSw128Hi), idesc, (kb | k) != 0 ? 1u : 0u);
             umma_commit_2cta_mask(&empty[stage], 0xF);   // this pair is done with the stage: tell all four CTAs
           }
@@ -781,7 +781,7 @@ static int launch_act(const CUtensorMap& tA, const CUtensorMap& tB, const CUtens
                          : launch_tc<BN, ACT_NONE, KB_RES>(tA, tB, tC, bias, M, N, K, stream);
 }
 
-int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act,
+int gemm_simt(const act_t* A, const act_t* W, const float* bias, act_t* C, int M, int N, int K, int act,
               cudaStream_t stream);
 
 static int g_block_n = 0;   // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic tile width (tuning knob)
@@ -789,17 +789,17 @@ static int g_quad = -1;     // VITED_GEMM_QUAD=1 enables the 4-CTA-cluster kerne
 static int g_pair = -1;     // VITED_GEMM_PAIR=0 disables the CTA-pair (cta_group::2) kernel (used for large M by default)
 static int g_resident = -1; // VITED_GEMM_RESIDENT=1 enables the resident-weights variant (measured slower: off by default)
 
-int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
+int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream) {
-  VITED_CHECK(M > 0 && N > 0 && K > 0, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
+  VITED_CHECK(M > 0 && N > 0 && K > 0, "gemm_act: empty problem M=%d N=%d K=%d", M, N, K);
   if (impl == IMPL_REF) return gemm_simt(A, W, bias, C, M, N, K, act, stream);
   std::call_once(g_once, init_driver_once);
   if (g_init_status) return 1;
-  VITED_CHECK(K % 8 == 0 && N % 8 == 0, "gemm_bf16: K and N must be multiples of 8 (TMA 16-byte strides), got K=%d N=%d",
+  VITED_CHECK(K % 8 == 0 && N % 8 == 0, "gemm_act: K and N must be multiples of 8 (TMA 16-byte strides), got K=%d N=%d",
               K, N);
   VITED_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(C) & 15) == 0,
-              "gemm_bf16: operands must be 16-byte aligned");
+              "gemm_act: operands must be 16-byte aligned");
   if (g_block_n == 0) {
     const char* e = getenv("VITED_GEMM_BN");
     g_block_n = e ? atoi(e) : -1;

@@ -9,55 +9,55 @@ enum { ACT_NONE = 0, ACT_GELU = 1 };
 enum { IMPL_FAST = 0, IMPL_REF = 1, IMPL_MMA_SYNC = 2 };  // IMPL_REF: plain SIMT debugging kernels; IMPL_MMA_SYNC (attention
                                                         // only): force the general mma.sync kernel even where a tcgen05 one exists
 
-// ---- GEMM: C[M,N] (bf16) = act(A[M,K] (bf16, row-major) * W[N,K]^T (bf16, row-major) + bias[N] (f32)) ----
+// ---- GEMM: C[M,N] (fp16) = act(A[M,K] (fp16, row-major) * W[N,K]^T (fp16, row-major) + bias[N] (f32)) ----
 // IMPL_FAST: persistent warp-specialised tcgen05/TMEM kernel fed by TMA (gemm_tc.cu).
-int gemm_bf16(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act, int impl,
+int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream);
 int gemm_num_sms();
-// 2-D bf16 TMA descriptor (driver entry point resolved in gemm_tc.cu); swizzle_bytes in {0, 64, 128}
-int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+// 2-D fp16 TMA descriptor (driver entry point resolved in gemm_tc.cu); swizzle_bytes in {0, 64, 128}
+int make_tmap_act_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
 int make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes);
 
 // ---- fused GEMM + residual + LayerNorm (gemm_ln.cu) ----
-//   x[M,384] (f32, in place) += A[M,K] (bf16) * W[384,K]^T (bf16) + bias;  h[M,384] (bf16) = LayerNorm(x) * ln_w + ln_b
+//   x[M,384] (f32, in place) += A[M,K] (fp16) * W[384,K]^T (fp16) + bias;  h[M,384] (fp16) = LayerNorm(x) * ln_w + ln_b
 // i.e. `x = x + proj(...)` followed by the next `normX(x)` (vision_transformer.py:124-127, :268-272) in ONE kernel: the
 // accumulator row never leaves the SM before it is normalised. Only N = 384 (the models' embed_dim) and large M.
 bool gemm_resid_ln_supported(int M, int N, int K);
-int gemm_resid_ln(const bf16* A, const bf16* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
-                  bf16* h, int M, int N, int K, float eps, cudaStream_t stream);
+int gemm_resid_ln(const act_t* A, const act_t* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
+                  act_t* h, int M, int N, int K, float eps, cudaStream_t stream);
 
 // ---- row-wise kernels (rowops.cu) ----
-// x[r,:] = (gather ? src[map(r),:] : x[r,:]) + delta[r,:]; optionally h[r,:] = LayerNorm(x[r,:]) * w + b (bf16).
+// x[r,:] = (gather ? src[map(r),:] : x[r,:]) + delta[r,:]; optionally h[r,:] = LayerNorm(x[r,:]) * w + b (fp16).
 // Row space is the "split" layout: n_seq*n_patch patch rows followed by n_cls cls rows (n_cls = n_seq or 0).
 struct ResidLnArgs {
   float* x;              // [R, D] residual stream (fp32), updated in place when write_x
-  const bf16* delta;     // [R, D] or null
+  const act_t* delta;     // [R, D] or null
   const float* gather_src;   // split-layout source [n_src_seq*n_patch (+ n_src_seq cls rows), D] or null
   const int* gather_idx;     // [n_seq] source sequence of every destination sequence
   int n_src_seq;
   const float* ln_w;     // null -> no LayerNorm output
   const float* ln_b;
-  bf16* h;               // [R, D]
+  act_t* h;               // [R, D]
   int n_seq, n_patch, has_cls, D;
   int write_x;
   float eps;
 };
 int resid_ln(const ResidLnArgs& a, cudaStream_t stream);
 
-// images [B,3,S,S] f32 -> patch matrix [B*G*G, 3*p*p] bf16, column = c*p*p + py*p + px (Conv2d weight.view order)
-int im2col_patches(const float* images, bf16* out, int B, int C, int S, int p, cudaStream_t stream);
+// images [B,3,S,S] f32 -> patch matrix [B*G*G, 3*p*p] fp16, column = c*p*p + py*p + px (Conv2d weight.view order)
+int im2col_patches(const float* images, act_t* out, int B, int C, int S, int p, cudaStream_t stream);
 
-// x0 (f32, split layout, B sequences): patch rows = tok (bf16 [B*Np, D]) + pos[1+t]; cls rows = cls + pos[0]
-int assemble_tokens(const bf16* tok, const float* pos_embed, const float* cls_token, float* x, int B, int n_patch,
+// x0 (f32, split layout, B sequences): patch rows = tok (fp16 [B*Np, D]) + pos[1+t]; cls rows = cls + pos[0]
+int assemble_tokens(const act_t* tok, const float* pos_embed, const float* cls_token, float* x, int B, int n_patch,
                     int D, int with_cls, cudaStream_t stream);
 
 // final: y = LayerNorm(x_cls + delta_cls); logits = y * Wh^T + bh; scattered into the score matrix.
 struct HeadArgs {
   const float* x;       // cls rows [P, D] f32
-  const bf16* delta;    // cls rows [P, D] or null
+  const act_t* delta;    // cls rows [P, D] or null
   const float* ln_w;
   const float* ln_b;
   const float* head_w;  // [C, D]
@@ -72,16 +72,16 @@ struct HeadArgs {
 int head_logits(const HeadArgs& a, cudaStream_t stream);
 
 // plain copy/convert helpers
-int f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t stream);
-int add_delta_out(const float* x, const bf16* delta, float* out, size_t rows, int D, cudaStream_t stream);
+int f32_to_act(const float* in, act_t* out, size_t n, cudaStream_t stream);
+int add_delta_out(const float* x, const act_t* delta, float* out, size_t rows, int D, cudaStream_t stream);
 
 // ---- attention (attention.cu) ----
 // Sequences live in the split layout. Logical token s of sequence b: s==0 && has_cls ? cls row : patch row.
 struct AttnArgs {
-  const bf16* q; int q_ld;      // row stride in elements
-  const bf16* k; int k_ld;
-  const bf16* v; int v_ld;
-  bf16* o; int o_ld;
+  const act_t* q; int q_ld;      // row stride in elements
+  const act_t* k; int k_ld;
+  const act_t* v; int v_ld;
+  act_t* o; int o_ld;
   int n_seq;                    // number of query sequences (pairs / items)
   int n_heads, head_dim;
   int nq_patch, q_has_cls;      // query tokens per sequence = nq_patch + q_has_cls

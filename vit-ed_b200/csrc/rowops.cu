@@ -9,7 +9,7 @@ namespace vited {
 // im2col for Conv2d(kernel = stride = p)  (timm PatchEmbed; called from models/vision_transformer.py:383,391)
 // token t = gy*G + gx covers pixels [gy*p:(gy+1)*p, gx*p:(gx+1)*p]; column = c*p*p + py*p + px.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int S, int p) {
+__global__ void im2col_kernel(const float* __restrict__ img, act_t* __restrict__ out, int B, int C, int S, int p) {
   const int G = S / p;
   const int K = C * p * p;
   const int segs_per_row = K / 4;  // 4 consecutive px per thread (p % 4 == 0)
@@ -26,13 +26,13 @@ __global__ void im2col_kernel(const float* __restrict__ img, bf16* __restrict__ 
     const int gy = t / G, gx = t % G;
     const float4 v = *reinterpret_cast<const float4*>(img + (((size_t)b * C + c) * S + (gy * p + py)) * S + gx * p + px);
     uint2 pk;
-    pk.x = pack_bf16(v.x, v.y);
-    pk.y = pack_bf16(v.z, v.w);
+    pk.x = pack_act(v.x, v.y);
+    pk.y = pack_act(v.z, v.w);
     *reinterpret_cast<uint2*>(out + row * K + col) = pk;
   }
 }
 
-int im2col_patches(const float* images, bf16* out, int B, int C, int S, int p, cudaStream_t stream) {
+int im2col_patches(const float* images, act_t* out, int B, int C, int S, int p, cudaStream_t stream) {
   VITED_CHECK(p % 4 == 0 && S % p == 0, "im2col: patch size %d must be a multiple of 4 and divide img size %d", p, S);
   const size_t total = (size_t)B * (S / p) * (S / p) * (C * p * p / 4);
   int blocks = (int)((total + 255) / 256);
@@ -47,7 +47,7 @@ int im2col_patches(const float* images, bf16* out, int B, int C, int S, int p, c
 // x0 = patch tokens + pos_embed[:, 1:]  (vision_transformer.py:378-380);  cls row = cls_token + pos_embed[:, 0]
 // (timm _pos_embed, called at :392).  Split layout: B*Np patch rows, then B cls rows.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void assemble_kernel(const bf16* __restrict__ tok, const float* __restrict__ pos,
+__global__ void assemble_kernel(const act_t* __restrict__ tok, const float* __restrict__ pos,
                                 const float* __restrict__ cls, float* __restrict__ x, int B, int Np, int D,
                                 int with_cls) {
   const int D4 = D / 4;
@@ -61,7 +61,7 @@ __global__ void assemble_kernel(const bf16* __restrict__ tok, const float* __res
     if (row < n_patch_rows) {
       const int t = (int)(row % Np);
       const uint2 tk = *reinterpret_cast<const uint2*>(tok + row * D + d);
-      const float2 a = unpack_bf16(tk.x), b = unpack_bf16(tk.y);
+      const float2 a = unpack_act(tk.x), b = unpack_act(tk.y);
       const float4 pe = *reinterpret_cast<const float4*>(pos + (size_t)(1 + t) * D + d);
       o = make_float4(a.x + pe.x, a.y + pe.y, b.x + pe.z, b.y + pe.w);
     } else {
@@ -73,7 +73,7 @@ __global__ void assemble_kernel(const bf16* __restrict__ tok, const float* __res
   }
 }
 
-int assemble_tokens(const bf16* tok, const float* pos_embed, const float* cls_token, float* x, int B, int n_patch,
+int assemble_tokens(const act_t* tok, const float* pos_embed, const float* cls_token, float* x, int B, int n_patch,
                     int D, int with_cls, cudaStream_t stream) {
   VITED_CHECK(D % 4 == 0, "assemble: D=%d must be a multiple of 4", D);
   const size_t total = ((size_t)B * n_patch + (with_cls ? B : 0)) * (D / 4);
@@ -86,7 +86,7 @@ int assemble_tokens(const bf16* tok, const float* pos_embed, const float* cls_to
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// fused residual add (+ gather from the per-item cache) + LayerNorm(eps 1e-6) -> bf16 GEMM operand.
+// fused residual add (+ gather from the per-item cache) + LayerNorm(eps 1e-6) -> fp16 GEMM operand.
 // Mirrors `x = x + sub_block(...)` followed by the next block's `normX(x)` (vision_transformer.py:124-127, 268-272).
 // One warp per row; NV = D / 128 float4 per lane.
 // ------------------------------------------------------------------------------------------------------------
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(ResidLnArgs a) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const uint2 dl = *reinterpret_cast<const uint2*>(a.delta + row * D + i * 128 + lane * 4);
-        const float2 d0 = unpack_bf16(dl.x), d1 = unpack_bf16(dl.y);
+        const float2 d0 = unpack_act(dl.x), d1 = unpack_act(dl.y);
         v[i].x += d0.x; v[i].y += d0.y; v[i].z += d1.x; v[i].w += d1.y;
       }
     }
@@ -142,8 +142,8 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(ResidLnArgs a) {
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w + i * 128 + lane * 4));
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + i * 128 + lane * 4));
         uint2 pk;
-        pk.x = pack_bf16((v[i].x - mean) * rstd * w4.x + b4.x, (v[i].y - mean) * rstd * w4.y + b4.y);
-        pk.y = pack_bf16((v[i].z - mean) * rstd * w4.z + b4.z, (v[i].w - mean) * rstd * w4.w + b4.w);
+        pk.x = pack_act((v[i].x - mean) * rstd * w4.x + b4.x, (v[i].y - mean) * rstd * w4.y + b4.y);
+        pk.y = pack_act((v[i].z - mean) * rstd * w4.z + b4.z, (v[i].w - mean) * rstd * w4.w + b4.w);
         *reinterpret_cast<uint2*>(a.h + row * D + i * 128 + lane * 4) = pk;
       }
     }
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) resid_ln_generic_kernel(ResidLnArgs a) {
       float4 v = *reinterpret_cast<const float4*>(src + i * 4);
       if (a.delta != nullptr) {
         const uint2 dl = *reinterpret_cast<const uint2*>(a.delta + row * D + i * 4);
-        const float2 d0 = unpack_bf16(dl.x), d1 = unpack_bf16(dl.y);
+        const float2 d0 = unpack_act(dl.x), d1 = unpack_act(dl.y);
         v.x += d0.x; v.y += d0.y; v.z += d1.x; v.w += d1.y;
       }
       // keep the updated row in x (also used as scratch for the second pass when !write_x is never requested
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(256) resid_ln_generic_kernel(ResidLnArgs a) {
       const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w + i * 4));
       const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + i * 4));
       uint2 pk;
-      pk.x = pack_bf16((v.x - mean) * rstd * w4.x + b4.x, (v.y - mean) * rstd * w4.y + b4.y);
-      pk.y = pack_bf16((v.z - mean) * rstd * w4.z + b4.z, (v.w - mean) * rstd * w4.w + b4.w);
+      pk.x = pack_act((v.x - mean) * rstd * w4.x + b4.x, (v.y - mean) * rstd * w4.y + b4.y);
+      pk.y = pack_act((v.z - mean) * rstd * w4.z + b4.z, (v.w - mean) * rstd * w4.w + b4.w);
       *reinterpret_cast<uint2*>(a.h + row * D + i * 4) = pk;
     }
   }
@@ -237,14 +237,14 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
     float s = 0.f;
     for (int d = lane; d < D; d += 32) {
       float v = xr[d];
-      if (a.delta != nullptr) v += __bfloat162float(a.delta[p * D + d]);
+      if (a.delta != nullptr) v += act2f(a.delta[p * D + d]);
       s += v;
     }
     const float mean = warp_sum(s) / (float)D;
     float ss = 0.f;
     for (int d = lane; d < D; d += 32) {
       float v = xr[d];
-      if (a.delta != nullptr) v += __bfloat162float(a.delta[p * D + d]);
+      if (a.delta != nullptr) v += act2f(a.delta[p * D + d]);
       ss += (v - mean) * (v - mean);
     }
     const float rstd = rsqrtf(warp_sum(ss) / (float)D + a.eps);
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) head_kernel(HeadArgs a) {
       float acc = 0.f;
       for (int d = lane; d < D; d += 32) {
         float v = xr[d];
-        if (a.delta != nullptr) v += __bfloat162float(a.delta[p * D + d]);
+        if (a.delta != nullptr) v += act2f(a.delta[p * D + d]);
         const float y = (v - mean) * rstd * __ldg(a.ln_w + d) + __ldg(a.ln_b + d);
         acc += y * __ldg(a.head_w + (size_t)c * D + d);
       }
@@ -280,25 +280,25 @@ int head_logits(const HeadArgs& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------------------
 // small converters
 // ------------------------------------------------------------------------------------------------------------
-__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+__global__ void f32_to_act_kernel(const float* __restrict__ in, act_t* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16_rn(in[i]);
+    out[i] = f2act(in[i]);
 }
-int f32_to_bf16(const float* in, bf16* out, size_t n, cudaStream_t stream) {
+int f32_to_act(const float* in, act_t* out, size_t n, cudaStream_t stream) {
   if (n == 0) return 0;
   size_t blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  f32_to_bf16_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, n);
+  f32_to_act_kernel<<<(int)blocks, 256, 0, stream>>>(in, out, n);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-__global__ void add_delta_out_kernel(const float* __restrict__ x, const bf16* __restrict__ delta,
+__global__ void add_delta_out_kernel(const float* __restrict__ x, const act_t* __restrict__ delta,
                                      float* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = x[i] + __bfloat162float(delta[i]);
+    out[i] = x[i] + act2f(delta[i]);
 }
-int add_delta_out(const float* x, const bf16* delta, float* out, size_t rows, int D, cudaStream_t stream) {
+int add_delta_out(const float* x, const act_t* delta, float* out, size_t rows, int D, cudaStream_t stream) {
   const size_t n = rows * D;
   if (n == 0) return 0;
   size_t blocks = (n + 255) / 256;
@@ -311,8 +311,8 @@ int add_delta_out(const float* x, const bf16* delta, float* out, size_t rows, in
 // ------------------------------------------------------------------------------------------------------------
 // debugging reference GEMM (SIMT, fp32 accumulate). Same contract as the tcgen05 kernel; never used by default.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ W,
-                                                        const float* __restrict__ bias, bf16* __restrict__ C, int M,
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const act_t* __restrict__ A, const act_t* __restrict__ W,
+                                                        const float* __restrict__ bias, act_t* __restrict__ C, int M,
                                                         int N, int K, int act) {
   __shared__ float sA[16][64 + 1];
   __shared__ float sW[16][64 + 1];
@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const bf16* __restrict__
   for (int k0 = 0; k0 < K; k0 += 16) {
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
       const int r = i / 16, kk = i % 16;
-      sA[kk][r] = (m0 + r < M && k0 + kk < K) ? __bfloat162float(A[(size_t)(m0 + r) * K + k0 + kk]) : 0.f;
-      sW[kk][r] = (n0 + r < N && k0 + kk < K) ? __bfloat162float(W[(size_t)(n0 + r) * K + k0 + kk]) : 0.f;
+      sA[kk][r] = (m0 + r < M && k0 + kk < K) ? act2f(A[(size_t)(m0 + r) * K + k0 + kk]) : 0.f;
+      sW[kk][r] = (n0 + r < N && k0 + kk < K) ? act2f(W[(size_t)(n0 + r) * K + k0 + kk]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -344,12 +344,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const bf16* __restrict__
       if (m < M && n < N) {
         float v = acc[i][j] + (bias ? bias[n] : 0.f);
         if (act == ACT_GELU) v = gelu_erf(v);
-        C[(size_t)m * N + n] = __float2bfloat16_rn(v);
+        C[(size_t)m * N + n] = f2act(v);
       }
     }
 }
 
-int gemm_simt(const bf16* A, const bf16* W, const float* bias, bf16* C, int M, int N, int K, int act,
+int gemm_simt(const act_t* A, const act_t* W, const float* bias, act_t* C, int M, int N, int K, int act,
               cudaStream_t stream) {
   dim3 grid((N + 63) / 64, (M + 63) / 64);
   gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, W, bias, C, M, N, K, act);
