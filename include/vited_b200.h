@@ -121,6 +121,25 @@ VITED_API int vited_act_dtype(void);
 /* bytes of device workspace currently held */
 VITED_API int64_t vited_workspace_bytes(vited_engine* e);
 
+/* ---- consumer side of the puzzle grid ----
+ * replaces: the tables InterPieceDistance.__init__ fills through 4*N*(N-1) callbacks into evaluation.py:116-131's
+ * distance_function -- PieceDistanceInformation.calculate_inter_piece_distances (paikin_tal_solver/
+ * inter_piece_distance.py:189-240: uint32 distances, minimum / second best, best-buddy candidates),
+ * calculate_asymmetric_compatibility (:325-372), InterPieceDistance.calculate_mutual_compatibility (:489-524) and the
+ * candidate matching of find_best_buddies (:626-648), for a type-1 puzzle (neighbour side = complementary side).
+ * scores  [N, N, 4] f32 indexed by origin piece id: logits (scores_are_logits = 1: 1 - sigmoid is applied, as
+ *         evaluation.py:109-114 does) or distances 1 - sigmoid(logit) (0);
+ * order   [N] i32 origin id of the piece at list position k (evaluation.py:87 shuffles the list), NULL = identity;
+ * All outputs are indexed by list position, rows (i, side) with side = PuzzlePieceSide value (top 0, right 1,
+ * bottom 2, left 3):  asym_dist [N,4,N] u32 (diagonal 2^31-1), min_dist / second_dist [N,4] i64 (sys.maxsize - 1 /
+ * sys.maxsize where the reference leaves its initial values), n_candidates [N,4] i32 = pieces at the minimum,
+ * candidate [N,4] i32 = the lowest such j (-1 if none), asym_compat / mutual_compat [N,4,N] f32 (diagonal +inf),
+ * best_buddy [N,4] i32 = j or -1. Every value is bit-identical to the reference's (NumPy >= 2 scalar rules). */
+VITED_API int vited_puzzle_tables(const float* scores, int scores_are_logits, const int32_t* order, int N,
+                                  uint32_t* asym_dist, int64_t* min_dist, int64_t* second_dist, int32_t* n_candidates,
+                                  int32_t* candidate, float* asym_compat, float* mutual_compat, int32_t* best_buddy,
+                                  void* stream);
+
 /* ---- single-kernel entry points (used by tests/ and profiles/ to check and time each kernel in isolation) ---- */
 /* ("h16" = the 16-bit type vited_act_dtype() names) C[M,N] h16 = act(A[M,K] h16 * W[N,K]^T h16 + bias[N] f32); act: 0 none, 1 exact-erf GELU; impl as GEMM_IMPL */
 VITED_API int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,

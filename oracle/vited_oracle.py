@@ -249,3 +249,97 @@ def wi19_metrics(distance_matrix, labels):
         return v.sum() / len(v)
 
     return float(m_ap), float(top_1), float(pr_at(10)), float(pr_at(100))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# distance tables of the puzzle solver: what InterPieceDistance.__init__ computes from the
+# distance_function callback of evaluation.py:116-131 (paikin_tal_solver/inter_piece_distance.py:437-475). Pinned to
+# the reference's own class by tests/golden/solver_tables.npz (tests/golden/make_golden_tables.py).
+# ---------------------------------------------------------------------------------------------------------------
+SIDE_BIN = (3, 0, 1, 2)   # PuzzlePieceSide value (top 0, right 1, bottom 2, left 3) -> score bin (evaluation.py:118-129)
+_MAXSIZE = 2 ** 63 - 1    # sys.maxsize on the 64-bit CPython the reference runs on
+
+
+def solver_tables(distance, order):
+    """distance [N, N, 4] fp32 = 1 - sigmoid(logits), indexed by origin piece id; order[k] = origin id of the piece at
+    list position k (evaluation.py:87 shuffles the list; InterPieceDistance numbers pieces by position, :437-441).
+    Type-1 puzzles: the only valid neighbour side is the complementary one (:816-819), so tables are [N, 4, N].
+    Returns the dict of arrays tests/golden/make_golden_tables.py stores."""
+    import numpy as np
+    d = np.asarray(distance, dtype=np.float32)
+    order = np.asarray(order)
+    n = len(order)
+    asym = np.full((n, 4, n), 2 ** 31 - 1, dtype=np.uint32)                   # :204-207
+    compat = np.full((n, 4, n), np.inf, dtype=np.float32)                     # :340-343
+    mutual = np.full((n, 4, n), np.inf, dtype=np.float32)                     # :369-372
+    min_d = np.zeros((n, 4), dtype=np.int64)
+    second_d = np.zeros((n, 4), dtype=np.int64)
+    cand = np.zeros((n, 4, n), dtype=bool)
+    for i in range(n):
+        for s in range(4):
+            mn, sec = _MAXSIZE - 1, _MAXSIZE                                   # :283-288
+            cands = []
+            for j in range(n):
+                if j == i:
+                    continue
+                # evaluation.py:118-129: float32 element * python float (float32 under NumPy >= 2), then the uint32
+                # store of :229 truncates
+                dist = int(np.uint32(np.float32(d[order[i], order[j], SIDE_BIN[s]]) * np.float32(1000.)))
+                asym[i, s, j] = dist
+                if dist < mn:                                                  # :256-272
+                    sec, mn, cands = mn, dist, [j]
+                elif dist == mn:
+                    sec = dist
+                    cands.append(j)
+                elif dist < sec:
+                    sec = dist
+            min_d[i, s], second_d[i, s] = mn, sec
+            cand[i, s, cands] = True
+            for j in range(n):                                                 # :345-367
+                if j == i:
+                    continue
+                if asym[i, s, j] == 0:
+                    c = 1
+                elif sec == 0:
+                    c = -_MAXSIZE
+                else:
+                    c = 1 - 1.0 * float(asym[i, s, j]) / sec
+                compat[i, s, j] = c
+    for i in range(n):                                                         # :489-524
+        for s in range(4):
+            cs = (s + 2) % 4
+            for j in range(i + 1, n):
+                m = np.float32(compat[i, s, j] + compat[j, cs, i]) / np.float32(2)
+                mutual[i, s, j] = m
+                mutual[j, cs, i] = m
+    # best buddies (:626-648) with _ALLOW_MULTIPLE_BEST_BUDDIES = False (:21, :76-84): a tied minimum has no candidate
+    single = cand.sum(-1) == 1
+    first = cand.argmax(-1)
+    bb = np.full((n, 4), -1, dtype=np.int32)
+    for i in range(n):
+        for s in range(4):
+            cs = (s + 2) % 4
+            if single[i, s]:
+                j = int(first[i, s])
+                if single[j, cs] and first[j, cs] == i:
+                    bb[i, s] = j
+    # starter piece ordering (:650-719): 4 x own best buddies + best buddies of those, then summed mutual compatibility
+    info = []
+    for i in range(n):
+        ids, total = [], 0
+        for s in range(4):
+            if bb[i, s] >= 0:
+                ids.append(int(bb[i, s]))
+                total = total + mutual[i, s, bb[i, s]]
+        info.append((ids, total))
+    ordering = []
+    for i in range(n):
+        numb = 4 * len(info[i][0]) + sum(len(info[b][0]) for b in info[i][0])
+        ordering.append((i, numb, info[i][1]))
+    ordering.sort(key=lambda t: (t[1], t[2]), reverse=True)
+    return {
+        'asym_dist': asym, 'asym_compat': compat, 'mutual_compat': mutual, 'min_dist': min_d, 'second_dist': second_d,
+        'candidates': cand, 'best_buddy': bb,
+        'start_order': np.array([(a, b) for (a, b, _) in ordering], dtype=np.int64).reshape(-1, 2),
+        'start_compat': np.array([float(c) for (_, _, c) in ordering], dtype=np.float64),
+    }

@@ -852,4 +852,12 @@ int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, 
   return im2col_patches(images, (act_t*)out, B, C, S, p, (cudaStream_t)stream);
 }
 
+int vited_puzzle_tables(const float* scores, int scores_are_logits, const int32_t* order, int N, uint32_t* asym_dist,
+                        int64_t* min_dist, int64_t* second_dist, int32_t* n_candidates, int32_t* candidate,
+                        float* asym_compat, float* mutual_compat, int32_t* best_buddy, void* stream) {
+  return puzzle_tables(scores, scores_are_logits, order, N, asym_dist, reinterpret_cast<long long*>(min_dist),
+                       reinterpret_cast<long long*>(second_dist), n_candidates, candidate, asym_compat, mutual_compat,
+                       best_buddy, (cudaStream_t)stream);
+}
+
 }  // extern "C"
