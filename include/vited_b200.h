@@ -121,6 +121,18 @@ VITED_API int vited_act_dtype(void);
 /* bytes of device workspace currently held */
 VITED_API int64_t vited_workspace_bytes(vited_engine* e);
 
+/* ---- producer side of the puzzle grid ----
+ * replaces: the per-piece preparation PiecesDataset.__getitem__ + TwoImgSyncEval run 2*N*(N-1) times in DataLoader
+ * workers (data/datasets/pieces_dataset.py:34-56, data/transforms.py:12-26): cv2.cvtColor(LAB2RGB) on the eroded
+ * piece, PIL bilinear Resize(out_size), ToTensor, Normalize(.5, .5) -- and the crop of Puzzle.make_pieces
+ * (paikin_tal_solver/puzzle_importer.py:196-232, :430-446). Once per piece, on the device, bit-identical floats.
+ * lab_image [H, W, 3] u8 (device): the puzzle image after cv2.COLOR_BGR2LAB (puzzle_importer.py:136-156);
+ * piece_width: grid = floor(H / w) x floor(W / w), centred; side / off: eroded piece side and crop offset
+ * (ceil(w * (1 - erosion)) and Python round((w - side) / 2): computed by the caller, vit-ed_b200/pieces.py);
+ * out [rows * cols, 3, out_size, out_size] f32 in piece-id (row-major) order; *n_pieces (host, may be NULL) = rows * cols. */
+VITED_API int vited_prepare_pieces(const uint8_t* lab_image, int H, int W, int piece_width, int side, int off, int out_size,
+                                   float* out, int* n_pieces, void* stream);
+
 /* ---- consumer side of the puzzle grid ----
  * replaces: the tables InterPieceDistance.__init__ fills through 4*N*(N-1) callbacks into evaluation.py:116-131's
  * distance_function -- PieceDistanceInformation.calculate_inter_piece_distances (paikin_tal_solver/

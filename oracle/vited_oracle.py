@@ -343,3 +343,111 @@ def solver_tables(distance, order):
         'start_order': np.array([(a, b) for (a, b, _) in ordering], dtype=np.int64).reshape(-1, 2),
         'start_compat': np.array([float(c) for (_, _, c) in ordering], dtype=np.float64),
     }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# piece preparation: what PiecesDataset.__getitem__ + TwoImgSyncEval do to each piece
+# (data/datasets/pieces_dataset.py:34-56, data/transforms.py:12-26). `prepare_pieces` makes the reference's own
+# library calls (cv2, PIL via torchvision -- all present on the GPU box too); `lab2rgb_u8` / `pil_resize_bilinear_u8`
+# restate the integer arithmetic of those libraries in numpy and are pinned to them by tests/test_piece_prep.py.
+# ---------------------------------------------------------------------------------------------------------------
+def prepare_pieces(img_bgr, piece_width, erosion, img_size):
+    """BGR uint8 [H, W, 3] -> fp32 [N, 3, S, S] in piece-id order, through the calls the reference makes:
+    cv2 BGR2LAB on the image (puzzle_importer.py:136-156), centred grid + eroded centre crop (:196-232, :430-446),
+    then per piece cv2 LAB2RGB -> ToPILImage -> Resize(S) (PIL bilinear) -> ToTensor -> Normalize(.5, .5)."""
+    import cv2
+    from torchvision import transforms
+    lab = cv2.cvtColor(img_bgr, cv2.COLOR_BGR2LAB)
+    rows, cols, top, left, side, off = crop_geometry(img_bgr.shape[0], img_bgr.shape[1], piece_width, erosion)
+    tf = transforms.Compose([transforms.ToPILImage(), transforms.Resize(img_size), transforms.ToTensor(),
+                             transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+    out = []
+    for r in range(rows):
+        for c in range(cols):
+            y0, x0 = top + r * piece_width + off, left + c * piece_width + off
+            piece = np.ascontiguousarray(lab[y0:y0 + side, x0:x0 + side])
+            out.append(tf(cv2.cvtColor(piece, cv2.COLOR_LAB2RGB)))
+    return torch.stack(out)
+
+
+def lab2rgb_u8(lab):
+    """OpenCV's bit-exact 8-bit Lab -> sRGB (imgproc color_lab.cpp, Lab2RGBinteger): L -> (Y, f(Y)) tables in 2^14
+    fixed point, a / b offsets by multiply-shift, f^-1 by integer division (toward zero) or integer cube, 3x3 integer
+    matrix descaled to a 12-bit index into the inverse-gamma table. Tables: tools/gen_lab_tables.py."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('gen_lab_tables', os.path.join(here, 'tools', 'gen_lab_tables.py'))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    y_tab, fy_tab = gen.lab_to_y_fy()
+    gamma = _inv_gamma_table(os.path.join(here, 'vit-ed_b200', 'csrc', 'lab_tables.inc'))
+    lab = np.asarray(lab).astype(np.int64)
+    L, a, b = lab[..., 0], lab[..., 1], lab[..., 2]
+    base = 1 << 14
+    adiv = ((5 * a * 53687 + (1 << 7)) >> 13) - 128 * base // 500
+    bdiv = ((b * 41943 + (1 << 4)) >> 9) - 128 * base // 200 + 1
+    x, z, y = gen.ab_to_xz(fy_tab[L] + adiv), gen.ab_to_xz(fy_tab[L] - bdiv), y_tab[L]
+    out = [gamma[np.clip((gen.COEFFS[c, 0] * x + gen.COEFFS[c, 1] * y + gen.COEFFS[c, 2] * z + (1 << 13)) >> 14, 0, 4095)]
+           for c in range(3)]
+    return np.stack(out, -1).astype(np.uint8)
+
+
+def _inv_gamma_table(path):
+    text = open(path).read()
+    body = text[text.index('kInvGamma[4096]'):]
+    body = body[body.index('{') + 1:body.index('}')]
+    return np.array([int(v) for v in body.replace('\n', ' ').split(',') if v.strip()], dtype=np.int64)
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """Pillow Resample.c precompute_coeffs + normalize_coeffs_8bpc, bilinear filter (support 1), whole-axis box."""
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    bounds, coefs = [], []
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [max(0.0, 1.0 - abs((x + xmin - center + 0.5) * ss)) for x in range(xmax)]
+        ww = sum(k)
+        k = [v / ww if ww != 0.0 else v for v in k]
+        coefs.append([int(0.5 + v * (1 << 22)) for v in k])
+        bounds.append((xmin, xmax))
+    return bounds, coefs
+
+
+def pil_resize_bilinear_u8(img, out_size):
+    """Pillow's 8-bit two-pass resize of a square [s, s, C] uint8 image to [S, S, C]: horizontal pass, uint8 rounding
+    (clip8 of the 22-bit fixed-point sum), vertical pass (ImagingResampleHorizontal_8bpc / Vertical_8bpc)."""
+    img = np.asarray(img).astype(np.int64)
+    s = img.shape[0]
+    bounds, coefs = pil_bilinear_coeffs(s, out_size)
+
+    def one_pass(a):   # along axis 1
+        out = np.zeros((a.shape[0], out_size, a.shape[2]), dtype=np.int64)
+        for xx, ((xmin, n), k) in enumerate(zip(bounds, coefs)):
+            acc = np.full((a.shape[0], a.shape[2]), 1 << 21, dtype=np.int64)
+            for t in range(n):
+                acc += a[:, xmin + t] * k[t]
+            out[:, xx] = np.clip(acc >> 22, 0, 255)
+        return out
+
+    h = one_pass(img)
+    return one_pass(h.transpose(1, 0, 2)).transpose(1, 0, 2).astype(np.uint8)
+
+
+def prepare_pieces_restated(img_lab, piece_width, erosion, img_size):
+    """The same result as `prepare_pieces` from the LAB image, through the numpy restatements only (fp32 division by
+    255, then (x - 0.5) / 0.5 as torch does)."""
+    rows, cols, top, left, side, off = crop_geometry(img_lab.shape[0], img_lab.shape[1], piece_width, erosion)
+    out = []
+    for r in range(rows):
+        for c in range(cols):
+            y0, x0 = top + r * piece_width + off, left + c * piece_width + off
+            rgb = pil_resize_bilinear_u8(lab2rgb_u8(img_lab[y0:y0 + side, x0:x0 + side]), img_size)
+            v = rgb.astype(np.float32) / np.float32(255)
+            out.append(((v - np.float32(0.5)) / np.float32(0.5)).transpose(2, 0, 1))
+    return torch.from_numpy(np.stack(out))

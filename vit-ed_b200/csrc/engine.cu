@@ -852,6 +852,11 @@ int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, 
   return im2col_patches(images, (act_t*)out, B, C, S, p, (cudaStream_t)stream);
 }
 
+int vited_prepare_pieces(const uint8_t* lab_image, int H, int W, int piece_width, int side, int off, int out_size,
+                         float* out, int* n_pieces, void* stream) {
+  return prepare_pieces(lab_image, H, W, piece_width, side, off, out_size, out, n_pieces, (cudaStream_t)stream);
+}
+
 int vited_puzzle_tables(const float* scores, int scores_are_logits, const int32_t* order, int N, uint32_t* asym_dist,
                         int64_t* min_dist, int64_t* second_dist, int32_t* n_candidates, int32_t* candidate,
                         float* asym_compat, float* mutual_compat, int32_t* best_buddy, void* stream) {

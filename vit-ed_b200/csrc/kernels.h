@@ -75,6 +75,10 @@ int head_logits(const HeadArgs& a, cudaStream_t stream);
 int f32_to_act(const float* in, act_t* out, size_t n, cudaStream_t stream);
 int add_delta_out(const float* x, const act_t* delta, float* out, size_t rows, int D, cudaStream_t stream);
 
+// ---- on-device piece preparation (piece_prep.cu): see include/vited_b200.h vited_prepare_pieces ----
+int prepare_pieces(const uint8_t* lab, int H, int W, int piece_width, int side, int off, int out_size, float* dst,
+                   int* n_pieces, cudaStream_t stream);
+
 // ---- solver distance tables (solver_tables.cu): see include/vited_b200.h vited_puzzle_tables ----
 int puzzle_tables(const float* scores, int scores_are_logits, const int* order, int N, uint32_t* asym, long long* min_d,
                   long long* second_d, int* n_cand, int* cand, float* compat, float* mutual, int* best_buddy,

@@ -76,3 +76,31 @@ def fragment_to_tensor(pil_image, img_size=512):
         transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
     ])
     return tf(pil_image)
+
+
+def prepare_pieces_device(img_bgr, piece_width, erosion, img_size, device='cuda'):
+    """BGR uint8 image [H, W, 3] -> (CUDA fp32 [N, 3, S, S] in piece-id order, (rows, cols)).
+
+    The device replacement of ``make_pieces_lab`` + ``pieces_to_batch``: the image is converted to
+    LAB once on the host as Puzzle._load_puzzle_image does (puzzle_importer.py:136-156) and uploaded as bytes; crop,
+    Lab -> sRGB, the PIL bilinear resize and the normalisation run in one kernel (C-ABI ``vited_prepare_pieces``) and
+    give bit-identical floats to the per-piece cv2 / PIL / torchvision calls of pieces_dataset.py:35-46."""
+    import ctypes
+
+    import cv2
+    from . import _lib
+    lab = cv2.cvtColor(np.ascontiguousarray(img_bgr), cv2.COLOR_BGR2LAB)
+    h, w = lab.shape[:2]
+    rows, cols, _, _ = grid_geometry(h, w, piece_width)
+    side, off = erosion_crop(piece_width, erosion)
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        lab_d = torch.from_numpy(lab).to(dev)
+        out = torch.empty((rows * cols, 3, img_size, img_size), dtype=torch.float32, device=dev)
+        n = ctypes.c_int(0)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(_lib.lib.vited_prepare_pieces(ctypes.c_void_p(lab_d.data_ptr()), h, w, piece_width, side, off, img_size,
+                                                 ctypes.c_void_p(out.data_ptr()), ctypes.byref(n), stream),
+                   'vited_prepare_pieces')
+    assert n.value == rows * cols
+    return out, (rows, cols)
