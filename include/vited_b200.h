@@ -152,6 +152,19 @@ VITED_API int vited_puzzle_tables(const float* scores, int scores_are_logits, co
                                   int32_t* candidate, float* asym_compat, float* mutual_compat, int32_t* best_buddy,
                                   void* stream);
 
+/* ---- consumer side of the fragment grid ----
+ * replaces: wi19_evaluate.get_metrics(distance_matrix, labels) (misc/wi19_evaluate.py:12-56) as hisfrag.py:306-309 calls
+ * it on distance = 1 - fp16(similarity) (hisfrag.py:283-296): per query row i, with the first sorted column dropped
+ * (:29-30) and relevance = same label (:26-27, self included),
+ *   n_relevant[i]  relevant items left,           ap_sum[i]  sum of precision-at-rank over them (f64),
+ *   top1[i]        1 if the nearest remaining item is relevant,   hits10 / hits100[i]  relevant items within rank 10 / 100.
+ * mAP = mean over rows with n_relevant > 0 of ap_sum / n_relevant; top-1 = mean(top1); Pr@k = mean(hits_k /
+ * min(n_relevant, k)) (0 / 0 = nan for singleton queries, as in the reference). Equal distances are ordered by
+ * ascending index (numpy's argsort leaves the order of ties to its implementation).
+ * sim [N, N] f32 (device): the logits of vited_score_grid mode UPPER_TRI_DIAG after mirroring; labels [N] i32. */
+VITED_API int vited_retrieval_rows(const float* sim, const int32_t* labels, int N, int32_t* n_relevant, double* ap_sum,
+                                   int32_t* top1, int32_t* hits10, int32_t* hits100, void* stream);
+
 /* ---- single-kernel entry points (used by tests/ and profiles/ to check and time each kernel in isolation) ---- */
 /* ("h16" = the 16-bit type vited_act_dtype() names) C[M,N] h16 = act(A[M,K] h16 * W[N,K]^T h16 + bias[N] f32); act: 0 none, 1 exact-erf GELU; impl as GEMM_IMPL */
 VITED_API int vited_op_gemm(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, int act, int impl,

@@ -226,8 +226,10 @@ def puzzle_distance_lookup(logits, i, j, side_i, side_j):
 # retrieval metrics of the Hisfrag consumer (misc/wi19_evaluate.py:12-56) -- used to check the north-star criterion
 # "identical retrieval top-1 / mAP to 3 decimals" on score matrices produced by the CUDA path and by this oracle
 # ---------------------------------------------------------------------------------------------------------------
-def wi19_metrics(distance_matrix, labels):
-    """get_metrics(distance_matrix, labels, remove_self_column=True) of misc/wi19_evaluate.py:12-22:
+def wi19_metrics(distance_matrix, labels, kind=None):
+    """get_metrics(distance_matrix, labels, remove_self_column=True) of misc/wi19_evaluate.py:12-22 (``kind`` is passed
+    to argsort: None = numpy's default as the reference calls it -- its order among TIED distances is implementation
+    defined; 'stable' = ties by ascending index, the convention of the device evaluator):
     rows sorted by ascending distance (numpy argsort, :28), the first column (self) dropped (:29-30), relevance =
     same label (:26-27); mAP over non-singleton queries of mean(precision@rank over relevant ranks) (:49-56),
     top-1 (:18), Pr@10 / Pr@100 (:7-9). Returns (mAP, top_1, pr_a_k10, pr_a_k100)."""
@@ -235,7 +237,7 @@ def wi19_metrics(distance_matrix, labels):
     D = np.asarray(distance_matrix)
     classes = np.asarray(labels)
     correct = classes[None, :] == classes[:, None]
-    order = np.argsort(D, axis=1)[:, 1:]
+    order = np.argsort(D, axis=1, kind=kind)[:, 1:]
     rel = correct[np.arange(order.shape[0], dtype='int64')[:, None], order]
     ranks = np.cumsum(np.ones_like(rel), axis=1)
     precision_at = np.cumsum(rel, axis=1).astype('float') / ranks
@@ -245,10 +247,30 @@ def wi19_metrics(distance_matrix, labels):
     top_1 = rel[:, 0].sum() / len(rel)
 
     def pr_at(k):
-        v = rel[:, :k].sum(axis=1) / np.minimum(rel.sum(axis=1), k)
+        with np.errstate(invalid='ignore', divide='ignore'):   # a singleton query gives 0 / 0 = nan, as in the reference
+            v = rel[:, :k].sum(axis=1) / np.minimum(rel.sum(axis=1), k)
         return v.sum() / len(v)
 
     return float(m_ap), float(top_1), float(pr_at(10)), float(pr_at(100))
+
+
+def sim_to_distance(sim):
+    """hisfrag.py:283-296: the similarity logits stored as fp16, then ``1 - similarity`` in fp16."""
+    return (1 - torch.as_tensor(sim, dtype=torch.float32).type(torch.float16)).numpy()
+
+
+def wi19_rows(distance_matrix, labels):
+    """Per query row, with ties by ascending index: (relevant items left after the first sorted column is dropped,
+    sum over them of precision at their rank, top-1 hit, hits within 10, hits within 100) -- the integers / sums the
+    device evaluator returns, from which get_metrics' four numbers follow."""
+    import numpy as np
+    D = np.asarray(distance_matrix)
+    classes = np.asarray(labels)
+    order = np.argsort(D, axis=1, kind='stable')[:, 1:]
+    rel = (classes[None, :] == classes[:, None])[np.arange(len(D))[:, None], order]
+    prec = np.cumsum(rel, axis=1) / np.arange(1, rel.shape[1] + 1)
+    return (rel.sum(1).astype(np.int32), (prec * rel).sum(1), rel[:, 0].astype(np.int32),
+            rel[:, :10].sum(1).astype(np.int32), rel[:, :100].sum(1).astype(np.int32))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -79,6 +79,10 @@ int add_delta_out(const float* x, const act_t* delta, float* out, size_t rows, i
 int prepare_pieces(const uint8_t* lab, int H, int W, int piece_width, int side, int off, int out_size, float* dst,
                    int* n_pieces, cudaStream_t stream);
 
+// ---- retrieval metrics (retrieval_metrics.cu): see include/vited_b200.h vited_retrieval_rows ----
+int retrieval_rows(const float* sim, const int* labels, int N, int* n_rel, double* ap_sum, int* top1, int* hits10,
+                   int* hits100, cudaStream_t stream);
+
 // ---- solver distance tables (solver_tables.cu): see include/vited_b200.h vited_puzzle_tables ----
 int puzzle_tables(const float* scores, int scores_are_logits, const int* order, int N, uint32_t* asym, long long* min_d,
                   long long* second_d, int* n_cand, int* cand, float* compat, float* mutual, int* best_buddy,

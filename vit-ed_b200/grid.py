@@ -163,3 +163,41 @@ def similarity_to_distance(sim):
     """fp16 similarity matrix then ``1 - sim`` (hisfrag.py:281-296) -> numpy fp16 [N, N]."""
     sim16 = sim.detach().to('cpu').type(torch.float16)
     return (1 - sim16).numpy()
+
+
+def retrieval_metrics(similarity, labels):
+    """(mAP, top-1, Pr@10, Pr@100) of ``wi19_evaluate.get_metrics(1 - fp16(similarity), labels)`` (hisfrag.py:283-309,
+    misc/wi19_evaluate.py:12-56), evaluated on the device from the fp32 similarity matrix that ``score_fragments``
+    returns (C-ABI ``vited_retrieval_rows``: ranks of the relevant items by counting, no sort, no N x N host copy).
+    labels: integer writer ids (``utils.list_to_idx`` output). Ties in distance are ordered by ascending index."""
+    import ctypes
+
+    import numpy as np
+    from . import _lib
+    if not (isinstance(similarity, torch.Tensor) and similarity.is_cuda and similarity.dtype == torch.float32
+            and similarity.dim() == 2 and similarity.shape[0] == similarity.shape[1]):
+        raise _lib.VitedError('retrieval_metrics: similarity must be a square CUDA fp32 tensor (there is no CPU path)')
+    n = similarity.shape[0]
+    dev = similarity.device
+    labels_np = np.asarray(labels)
+    if labels_np.shape != (n,):
+        raise _lib.VitedError(f'retrieval_metrics: {labels_np.shape} labels for {n} items')
+    similarity = similarity.contiguous()
+    with torch.cuda.device(dev):
+        lab = torch.from_numpy(labels_np.astype(np.int32)).to(dev)
+        n_rel = torch.empty(n, dtype=torch.int32, device=dev)
+        ap_sum = torch.empty(n, dtype=torch.float64, device=dev)
+        top1 = torch.empty(n, dtype=torch.int32, device=dev)
+        h10 = torch.empty(n, dtype=torch.int32, device=dev)
+        h100 = torch.empty(n, dtype=torch.int32, device=dev)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        _lib.check(_lib.lib.vited_retrieval_rows(p(similarity), p(lab), n, p(n_rel), p(ap_sum), p(top1), p(h10), p(h100),
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   'vited_retrieval_rows')
+        n_rel, ap_sum, top1, h10, h100 = [t.cpu().numpy() for t in (n_rel, ap_sum, top1, h10, h100)]
+    keep = n_rel > 0
+    m_ap = (ap_sum[keep] / n_rel[keep]).mean()
+    with np.errstate(invalid='ignore', divide='ignore'):       # singleton queries: 0 / 0 = nan, as in the reference
+        pr10 = (h10 / np.minimum(n_rel, 10)).sum() / n
+        pr100 = (h100 / np.minimum(n_rel, 100)).sum() / n
+    return float(m_ap), float(top1.sum() / n), float(pr10), float(pr100)
