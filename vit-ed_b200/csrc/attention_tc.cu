@@ -95,6 +95,8 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();           // the prologue above overlapped the previous kernel's tail; global memory only from here on
 
   if (quarter == 3) {
     if (group == 0) {
@@ -381,6 +383,8 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();           // the prologue above overlapped the previous kernel's tail; global memory only from here on
   auto is_cls_item = [&](int i) { return (((int)blockIdx.x + i * (int)gridDim.x) % per_bh) == n_qp; };
 
   if (warp == 8) {
@@ -673,7 +677,7 @@ static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 128, 128)) return 1;
   if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 1, 128)) return 1;
   const unsigned grid = (unsigned)(items < (size_t)sms ? items : (size_t)sms);
-  attn_l64_kernel<<<grid, L64::THREADS, L64::BYTES, stream>>>(a, maps, (int)items);
+  VITED_CUDA_OK(launch_pdl(attn_l64_kernel, dim3(grid), dim3(L64::THREADS), L64::BYTES, stream, a, maps, (int)items));
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -714,7 +718,7 @@ static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream
   if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 64, 64)) return 1;
   if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 1, 64)) return 1;
   const unsigned grid = (unsigned)(units < (size_t)sms ? units : (size_t)sms);
-  attn_p64_kernel<<<grid, P64::THREADS, P64::BYTES, stream>>>(a, maps, (int)units, cls_only);
+  VITED_CUDA_OK(launch_pdl(attn_p64_kernel, dim3(grid), dim3(P64::THREADS), P64::BYTES, stream, a, maps, (int)units, cls_only));
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -2,6 +2,7 @@
 // PTX wrappers: mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld), ldmatrix, mma.sync.
 #pragma once
 #include <cuda_runtime.h>
+#include <utility>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda.h>
@@ -29,6 +30,7 @@ typedef __half act_t;
 // host side error plumbing (no exceptions cross the C-ABI; see include/vited_b200.h)
 // ---------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
+bool pdl_enabled();   // VITED_PDL=1 (default off: measured neutral, see profiles/README.md); engine.cu
 const char* get_error();
 
 #define VITED_CUDA_OK(expr)                                                                     \
@@ -49,6 +51,24 @@ const char* get_error();
   } while (0)
 
 #ifdef __CUDACC__
+// Launch `kernel` so that it may overlap the tail of the previous kernel in `stream` (see pdl_wait below). Only for
+// kernels that call pdl_wait() before their first global-memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
@@ -91,6 +111,15 @@ __device__ __forceinline__ act_t f2act(float v) {
   return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
 #endif
 }
+
+// Programmatic dependent launch (PDL). A kernel launched through launch_pdl() may become resident while the previous
+// kernel of the stream is still draining: its prologue (barrier init, TMEM allocation, descriptor prefetch) then
+// overlaps the predecessor's tail and the launch latency. pdl_wait() blocks until every earlier kernel has completed
+// and its writes are visible; NOTHING may touch global memory before it. pdl_launch_dependents() lets the NEXT
+// kernel do the same with respect to this one (it still cannot pass its own pdl_wait() before this grid is done).
+// Both are no-ops in a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // one lane of a converged warp (always the same one: lane 0 for a full mask). Issuing tcgen05.mma / commit under this
 // predicate from WARP-UNIFORM code lets the compiler keep descriptors in uniform registers; issuing from a divergent
@@ -180,6 +209,15 @@ __device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parit
 }
 // Bounded wait: a protocol bug must trap (launch error on the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+#ifdef VITED_JITTER
+  // Timing fuzzer for the barrier protocols (-DVITED_JITTER): roughly one wait in four first sleeps 0..4 us, so
+  // warps reach their waits in orders the production timing never produces. A protocol that relies on "the producer
+  // cannot be that far ahead" shows up as a bounded-wait timeout or a wrong result in the kernel tests.
+  {
+    const uint32_t c = (uint32_t)clock64() * 2654435761u + (threadIdx.x >> 5) * 40503u + blockIdx.x * 9176u;
+    if (((c >> 13) & 3u) == 0u) __nanosleep((c >> 17) & 4095u);
+  }
+#endif
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {

@@ -554,6 +554,13 @@ static int upload_ints(DevBuf& buf, const std::vector<int>& v, cudaStream_t s) {
 // =====================================================================================================================
 // C-ABI
 // =====================================================================================================================
+namespace vited {
+bool pdl_enabled() {
+  static const int on = [] { const char* v = getenv("VITED_PDL"); return v == nullptr ? 0 : atoi(v); }();
+  return on != 0;
+}
+}  // namespace vited
+
 extern "C" {
 
 const char* vited_last_error(void) { return get_error(); }

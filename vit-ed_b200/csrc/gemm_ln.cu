@@ -106,6 +106,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();           // the prologue above overlapped the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs): own 128 activation rows + 2 x 96 weight rows per k-block ========
@@ -327,8 +329,8 @@ int gemm_resid_ln(const act_t* A, const act_t* W, const float* bias, float* x, c
   const int tiles = (M + 2 * BM - 1) / (2 * BM);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  gemm_ln_pair_kernel<<<2 * pairs, LnCfg::kThreads, LnCfg::SMEM_BYTES, stream>>>(tA, tB, tX, tH, bias, ln_w, ln_b, M, K, eps);
-  VITED_CUDA_OK(cudaGetLastError());
+  VITED_CUDA_OK(launch_pdl(gemm_ln_pair_kernel, dim3(2 * pairs), dim3(LnCfg::kThreads), LnCfg::SMEM_BYTES, stream, tA, tB, tX, tH,
+                           bias, ln_w, ln_b, M, K, eps));
   return 0;
 }
 

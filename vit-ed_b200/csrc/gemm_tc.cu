@@ -440,6 +440,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();           // everything above overlapped the previous kernel's tail; global memory only from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -741,8 +743,8 @@ static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   int pairs = g_num_sms / 2;
   if (pairs > tiles) pairs = tiles;
-  gemm_tc_pair_kernel<BN, ACT><<<2 * pairs, Cfg::kThreads, Cfg::SMEM_BYTES, stream>>>(tA, tB, tC, bias, M, N, K);
-  VITED_CUDA_OK(cudaGetLastError());
+  VITED_CUDA_OK(launch_pdl(gemm_tc_pair_kernel<BN, ACT>, dim3(2 * pairs), dim3(Cfg::kThreads), Cfg::SMEM_BYTES, stream, tA, tB,
+                           tC, bias, M, N, K));
   return 0;
 }
 
