@@ -22,4 +22,4 @@ for r in rd:
 total = sum(tot.values())
 print('kernel,launches,total_us,share,avg_us')
 for k in sorted(tot, key=lambda k: -tot[k]):
-    print(f'{k},{cnt[k]},{tot[k]:.1f},{tot[k] / total:.4f},{tot[k] / cnt[k]:.2f}')
+    print(f'"{k}",{cnt[k]},{tot[k]:.1f},{tot[k] / total:.4f},{tot[k] / cnt[k]:.2f}')
