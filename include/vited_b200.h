@@ -133,6 +133,11 @@ VITED_API int64_t vited_workspace_bytes(vited_engine* e);
 VITED_API int vited_prepare_pieces(const uint8_t* lab_image, int H, int W, int piece_width, int side, int off, int out_size,
                                    float* out, int* n_pieces, void* stream);
 
+/* replaces: ToTensor + Normalize(.5, .5) of the Hisfrag test transform (hisfrag.py:89-93, applied by
+ * HisFrag20Test.__getitem__, hisfrag_dataset.py:181-191) after its CenterCrop, which the caller does on the bytes.
+ * images [N, S, S, 3] u8 (device) -> out [N, 3, S, S] f32 = (v / 255 - 0.5) / 0.5, bit-identical to torch's fp32 ops. */
+VITED_API int vited_normalize_u8(const uint8_t* images, int N, int S, float* out, void* stream);
+
 /* ---- consumer side of the puzzle grid ----
  * replaces: the tables InterPieceDistance.__init__ fills through 4*N*(N-1) callbacks into evaluation.py:116-131's
  * distance_function -- PieceDistanceInformation.calculate_inter_piece_distances (paikin_tal_solver/

@@ -64,3 +64,18 @@ def test_bad_arguments_fail_loudly():
         pieces.prepare_pieces_device(np.zeros((32, 32, 3), np.uint8), 64, 0.07, 64)
     with pytest.raises(vited_b200.VitedError):
         pieces.prepare_pieces_device(np.zeros((256, 256, 3), np.uint8), 128, 0.0, 64)    # side 128 > kernel limit
+
+
+def test_fragment_batch_on_device_equals_reference_transform():
+    """Hisfrag test transform (hisfrag.py:89-93): CenterCrop(512) -> ToTensor -> Normalize, images of different sizes
+    (one smaller than the crop), against torchvision on the PIL images."""
+    from PIL import Image
+    from vited_b200 import pieces
+    rng = np.random.default_rng(12)
+    imgs = [Image.fromarray(rng.integers(0, 256, size=s + (3,), dtype=np.uint8))
+            for s in [(600, 700), (512, 512), (777, 513), (300, 900)]]
+    got = pieces.fragments_to_batch_device(imgs, 512)
+    want = torch.stack([pieces.fragment_to_tensor(im, 512) for im in imgs])
+    assert got.shape == (4, 3, 512, 512) and torch.equal(got.cpu(), want)
+    small = pieces.fragments_to_batch_device([np.asarray(imgs[0])[:70, :90]], 64)
+    assert torch.equal(small.cpu(), pieces.fragment_to_tensor(Image.fromarray(np.asarray(imgs[0])[:70, :90]), 64)[None])

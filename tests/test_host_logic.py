@@ -175,3 +175,15 @@ def test_row_sharding_and_gather_world2_gloo():
     for rank, puzzle, frag in results:
         assert np.array_equal(puzzle, want_puzzle.numpy()), f'rank {rank} puzzle grid differs'
         assert np.array_equal(frag, want_frag.numpy()), f'rank {rank} fragment grid differs'
+
+
+@pytest.mark.parametrize('shape', [(600, 700), (512, 512), (513, 515), (400, 700), (300, 200), (511, 1024)])
+def test_center_crop_u8_matches_torchvision(shape):
+    """pieces.center_crop_u8 (the byte-level crop in front of the device normalisation) against torchvision's
+    CenterCrop on the PIL image, including zero padding of images smaller than the crop and odd margins."""
+    from PIL import Image
+    from torchvision import transforms
+    rng = np.random.default_rng(shape[0] * 7 + shape[1])
+    arr = rng.integers(0, 256, size=(shape[0], shape[1], 3), dtype=np.uint8)
+    want = np.asarray(transforms.CenterCrop(512)(Image.fromarray(arr)))
+    assert np.array_equal(pieces.center_crop_u8(arr, 512), want)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vited_launch_count": (_i64, [_vp]),
     "vited_act_dtype": (_i, []),
     "vited_prepare_pieces": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "vited_normalize_u8": (_i, [_vp, _i, _i, _vp, _vp]),
     "vited_retrieval_rows": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vited_puzzle_tables": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vited_workspace_bytes": (_i64, [_vp]),

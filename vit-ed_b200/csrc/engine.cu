@@ -864,6 +864,10 @@ int vited_prepare_pieces(const uint8_t* lab_image, int H, int W, int piece_width
   return prepare_pieces(lab_image, H, W, piece_width, side, off, out_size, out, n_pieces, (cudaStream_t)stream);
 }
 
+int vited_normalize_u8(const uint8_t* images, int N, int S, float* out, void* stream) {
+  return normalize_u8(images, N, S, out, (cudaStream_t)stream);
+}
+
 int vited_retrieval_rows(const float* sim, const int32_t* labels, int N, int32_t* n_relevant, double* ap_sum,
                          int32_t* top1, int32_t* hits10, int32_t* hits100, void* stream) {
   return retrieval_rows(sim, labels, N, n_relevant, ap_sum, top1, hits10, hits100, (cudaStream_t)stream);

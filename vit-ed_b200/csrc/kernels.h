@@ -79,6 +79,8 @@ int add_delta_out(const float* x, const act_t* delta, float* out, size_t rows, i
 int prepare_pieces(const uint8_t* lab, int H, int W, int piece_width, int side, int off, int out_size, float* dst,
                    int* n_pieces, cudaStream_t stream);
 
+int normalize_u8(const uint8_t* in, int N, int S, float* out, cudaStream_t stream);   // [N,S,S,3] u8 -> [N,3,S,S] f32 in [-1,1]
+
 // ---- retrieval metrics (retrieval_metrics.cu): see include/vited_b200.h vited_retrieval_rows ----
 int retrieval_rows(const float* sim, const int* labels, int N, int* n_rel, double* ap_sum, int* top1, int* hits10,
                    int* hits100, cudaStream_t stream);

@@ -11,6 +11,7 @@
 //      in double on the host exactly as precompute_coeffs does, uint8 rounding between the passes);
 //   4. fp32: v / 255 (IEEE division), (x - 0.5) / 0.5.
 // HBM-bound byte work: reads s*s*3 bytes and writes 3*S*S*4 bytes per piece.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -153,7 +154,33 @@ int upload_tables() {
   return 0;
 }
 
+// [N, S, S, 3] uint8 -> [N, 3, S, S] fp32: ToTensor (v / 255) + Normalize((x - .5) / .5), the arithmetic of
+// hisfrag.py:89-93 after its CenterCrop; four pixels of one channel per thread, float4 stores
+__global__ void normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, size_t n_quads, int plane) {
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads; q += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = q * 4;                       // first output element of this quad: ((n * 3 + c) * plane + pix)
+    const size_t pix = e % plane, nc = e / plane, c = nc % 3, n = nc / 3;
+    const uint8_t* src = in + (n * plane + pix) * 3 + c;
+    float4 v;
+    v.x = __fdiv_rn(__fsub_rn(__fdiv_rn((float)src[0], 255.0f), 0.5f), 0.5f);
+    v.y = __fdiv_rn(__fsub_rn(__fdiv_rn((float)src[3], 255.0f), 0.5f), 0.5f);
+    v.z = __fdiv_rn(__fsub_rn(__fdiv_rn((float)src[6], 255.0f), 0.5f), 0.5f);
+    v.w = __fdiv_rn(__fsub_rn(__fdiv_rn((float)src[9], 255.0f), 0.5f), 0.5f);
+    *reinterpret_cast<float4*>(out + e) = v;
+  }
+}
+
 }  // namespace
+
+int normalize_u8(const uint8_t* in, int N, int S, float* out, cudaStream_t stream) {
+  VITED_CHECK(in != nullptr && out != nullptr && N >= 1 && S >= 1, "normalize_u8: bad arguments N=%d S=%d", N, S);
+  VITED_CHECK((S * S) % 4 == 0, "normalize_u8: S*S must be a multiple of 4, got S=%d", S);
+  const size_t n_quads = (size_t)N * 3 * S * S / 4;
+  const int blocks = (int)std::min<size_t>((n_quads + 255) / 256, (size_t)148 * 16);
+  normalize_u8_kernel<<<blocks, 256, 0, stream>>>(in, out, n_quads, S * S);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int prepare_pieces(const uint8_t* lab, int H, int W, int piece_width, int side, int off, int out_size, float* dst,
                    int* n_pieces, cudaStream_t stream) {

@@ -104,3 +104,41 @@ def prepare_pieces_device(img_bgr, piece_width, erosion, img_size, device='cuda'
                    'vited_prepare_pieces')
     assert n.value == rows * cols
     return out, (rows, cols)
+
+
+def center_crop_u8(img, size):
+    """torchvision CenterCrop(size) on an [H, W, 3] uint8 array (transforms/functional.py center_crop): zero padding
+    when the image is smaller than the crop, then offsets ``int(round((dim - size) / 2.0))`` (Python banker's round)."""
+    img = np.asarray(img)
+    h, w = img.shape[:2]
+    if size > w or size > h:
+        pl = (size - w) // 2 if size > w else 0
+        pt = (size - h) // 2 if size > h else 0
+        pr = (size - w + 1) // 2 if size > w else 0
+        pb = (size - h + 1) // 2 if size > h else 0
+        img = np.pad(img, ((pt, pb), (pl, pr), (0, 0)))
+        h, w = img.shape[:2]
+    top = int(round((h - size) / 2.0))
+    left = int(round((w - size) / 2.0))
+    return img[top:top + size, left:left + size]
+
+
+def fragments_to_batch_device(images, img_size=512, device='cuda'):
+    """List of PIL images / [H, W, 3] uint8 arrays -> CUDA fp32 [N, 3, S, S]: the Hisfrag20 test-time preparation
+    (``fragment_to_tensor`` is the per-image host version) with the crop done on the bytes and
+    ToTensor + Normalize on the device (C-ABI ``vited_normalize_u8``): a quarter of the upload, identical floats."""
+    import ctypes
+
+    from . import _lib
+    crops = np.stack([center_crop_u8(np.asarray(im), img_size) for im in images])
+    if crops.dtype != np.uint8 or crops.shape[1:] != (img_size, img_size, 3):
+        raise _lib.VitedError(f'fragments_to_batch_device: expected uint8 RGB images, got {crops.dtype} {crops.shape}')
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        src = torch.from_numpy(np.ascontiguousarray(crops)).to(dev)
+        out = torch.empty((len(crops), 3, img_size, img_size), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib.vited_normalize_u8(ctypes.c_void_p(src.data_ptr()), len(crops), img_size,
+                                               ctypes.c_void_p(out.data_ptr()),
+                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                   'vited_normalize_u8')
+    return out
