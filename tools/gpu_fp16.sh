@@ -2,7 +2,7 @@
 # fp16-vs-bf16 operand A/B on one box: tests, error against the fixtures / oracle, bench of both builds
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-BF=$PWD/tools/bin/bf16/libvited_b200.so
+BF=$PWD/tools/bin/bf16/libvited_b200.so   # tools/build_variants.sh
 timeout 1200 python -m pytest tests -m gpu -x -q --timeout 900 -p no:cacheprovider -rP 2>&1 | grep -v "^$" | grep "passed\|failed\|Error\|error\|argmax agreement\|assert" | head -20
 timeout 300 python tests/analysis/fixture_err.py 2>&1 | grep "^\["
 VITED_LIB=$BF timeout 300 python tests/analysis/fixture_err.py 2>&1 | grep "^\["

@@ -1,12 +1,12 @@
-"""Debug: clock trace of the long-sequence attention kernel, block 0. Needs tools/bin/libvited_trace.so = the library
-built with -DVITED_ATTN_TRACE (the nvcc line of vit-ed_b200/csrc/build.sh plus that define, -o tools/bin/libvited_trace.so);
+"""Debug: clock trace of the long-sequence attention kernel, block 0. Needs tools/bin/trace/libvited_b200.so = the library
+built with -DVITED_ATTN_TRACE (the nvcc line of vit-ed_b200/csrc/build.sh plus that define, -o tools/bin/trace/libvited_b200.so);
 the current kernel keeps the softmax-side trace points only: MMA warp per group (wait P start / end, PV issued, QK issued) and softmax warp 0 per group
 (wait S start / end, P stored)."""
 import ctypes, os
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'libvited_trace.so'))
+lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'trace', 'libvited_b200.so'))
 vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 lib.vited_op_attention.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, cf, ci, vp]
 lib.vited_op_attention.restype = ci

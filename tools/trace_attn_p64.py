@@ -1,10 +1,10 @@
 """Debug: clock trace of the puzzle attention kernel, block 0, first warp of every softmax group (needs
-tools/bin/libvited_trace.so = the library built with -DVITED_ATTN_TRACE)."""
+tools/bin/trace/libvited_b200.so = the library built with -DVITED_ATTN_TRACE)."""
 import ctypes, os
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'libvited_trace.so'))
+lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'trace', 'libvited_b200.so'))
 vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 lib.vited_op_attention.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp, cf, ci, vp]
 lib.vited_op_attention.restype = ci

@@ -1,10 +1,10 @@
-"""Debug: clock trace of the fused GEMM + residual + LayerNorm kernel, CTA 0 (needs tools/bin/libvited_trace.so = the
+"""Debug: clock trace of the fused GEMM + residual + LayerNorm kernel, CTA 0 (needs tools/bin/trace/libvited_b200.so = the
 library built with -DVITED_LN_TRACE: the nvcc line of vit-ed_b200/csrc/build.sh plus that define)."""
 import ctypes, math, os, sys
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'libvited_trace.so'))
+lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'trace', 'libvited_b200.so'))
 vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 lib.vited_op_gemm_resid_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, cf, vp]
 lib.vited_op_gemm_resid_ln.restype = ci
