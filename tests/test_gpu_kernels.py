@@ -299,3 +299,27 @@ def test_im2col_patch_indexing_is_exact(cfg):
     torch.cuda.synchronize()
     ref = img.reshape(B, C, G, p, G, p).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, C * p * p).to(_act())
     assert torch.equal(out, ref), 'patch indexing must be bit-exact (SURVEY 8b)'
+
+
+def test_fp16_results_saturate_instead_of_overflowing():
+    """A 16-bit result beyond the fp16 range is stored as +-65504, not inf (the reference under autocast would carry
+    inf / nan on); bf16 builds have the fp32 range and are not affected."""
+    if _act() != torch.float16:
+        pytest.skip('bf16 build')
+    M, N, K = 512, 384, 64
+    A = torch.full((M, K), 200.0, device='cuda').to(_act())
+    W = torch.full((N, K), 200.0, device='cuda').to(_act())
+    W[N // 2:] = -200.0
+    C = _gemm(A, W, torch.zeros(N, device='cuda'), 0, 0)          # +-2.56e6 per element
+    assert torch.isfinite(C.float()).all()
+    assert (C[:, :N // 2].float() == 65504.0).all() and (C[:, N // 2:].float() == -65504.0).all()
+    # fused Linear + residual + LayerNorm: the fp32 residual takes the full value, the normalised row stays finite
+    L = _lib()
+    x = torch.zeros(M, N, device='cuda')
+    h = torch.full((M, N), float('nan'), dtype=_act(), device='cuda')
+    lw, lb = torch.full((N,), 1e6, device='cuda'), torch.zeros(N, device='cuda')
+    L.check(L.lib.vited_op_gemm_resid_ln(_ptr(A), _ptr(W), _ptr(torch.zeros(N, device='cuda')), _ptr(x), _ptr(lw),
+                                         _ptr(lb), _ptr(h), M, N, K, 1e-6, _stream()), 'op_gemm_resid_ln')
+    torch.cuda.synchronize()
+    assert (x[:, 0] == 200.0 * 200.0 * K).all()
+    assert torch.isfinite(h.float()).all() and (h.float().abs() == 65504.0).all()
