@@ -64,8 +64,10 @@ enum {
   VITED_OPT_PROFILE = 4,        /* 1 = record a CUDA event before every launch (see vited_profile_json); default 0   */
   VITED_OPT_PRUNE_TAIL = 5,     /* 1 (default) = in the last decoder layer run everything after the K/V projection of
                                    its self-attention on the class-token rows only (only row 0 reaches the head)   */
-  VITED_OPT_FUSE_LN = 6         /* 1 (default) = residual add + LayerNorm run in the epilogue of the producing GEMM
+  VITED_OPT_FUSE_LN = 6,        /* 1 (default) = residual add + LayerNorm run in the epilogue of the producing GEMM
                                    (embed_dim 384, large row counts); 0 = separate resid_ln kernel                  */
+  VITED_OPT_KV_BUDGET_MB = 7    /* vited_score_grid processes context rows in blocks whose K/V cache (all decoder
+                                   layers) fits this many MB (default 8000; Hisfrag: 18.9 MB per fragment)          */
 };
 
 /* Library-wide last error message (thread-local). */

@@ -196,3 +196,28 @@ def test_errors_are_loud():
         model.score_grid(torch.zeros(4, 3, kw['img_size'], kw['img_size'], device='cuda'), 0, 3, 2)
     out = model.score_grid(torch.zeros(0, 3, kw['img_size'], kw['img_size'], device='cuda'), 0)
     assert out.shape == (0, 0, kw['num_classes'])
+
+
+@pytest.mark.parametrize('name,mode,n', [('small_hd32', 'puzzle', 80), ('small_hd64', 'fragments', 90),
+                                         ('puzzle_patch8_64', 'puzzle', 23)])
+def test_context_rows_in_several_kv_blocks(name, mode, n):
+    """vited_score_grid walks the context rows in blocks whose K/V cache fits a budget (8 GB by default: more than 423
+    Hisfrag fragments per GPU take several blocks). With a 1 MB budget a small grid takes many blocks and must give
+    the same scores, for full grids and for a row range (2 blocks for the small models, 23 one-row blocks for the
+    puzzle model)."""
+    import vited_b200
+    from vited_b200 import grid
+    model, sd, kw, images = _grid_case(name, n)
+    images = images.cuda()
+    score = grid.score_puzzle if mode == 'puzzle' else grid.score_fragments
+    gmode = vited_b200.GRID_ORDERED_OFFDIAG if mode == 'puzzle' else vited_b200.GRID_UPPER_TRI_DIAG
+    one_block = score(model, images)
+    part_one = model.score_grid(images, gmode, 5, 19)
+    model.set_option(vited_b200.OPT_KV_BUDGET_MB, 1)
+    many_blocks = score(model, images)
+    part_many = model.score_grid(images, gmode, 5, 19)
+    np.testing.assert_allclose(many_blocks.cpu().numpy(), one_block.cpu().numpy(), rtol=0, atol=1e-2)
+    np.testing.assert_allclose(part_many.cpu().numpy(), part_one.cpu().numpy(), rtol=0, atol=1e-2)
+    # the blocks really were smaller than the grid: K/V bytes per item x n exceeds the budget
+    ne = (kw['img_size'] // kw['patch_size']) ** 2
+    assert kw['c_depth'] * ne * 2 * kw['embed_dim'] * 2 * n > 1_000_000

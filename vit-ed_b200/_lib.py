@@ -41,6 +41,7 @@ OPT_CACHE_LAYER0 = 3
 OPT_PROFILE = 4
 OPT_PRUNE_TAIL = 5
 OPT_FUSE_LN = 6
+OPT_KV_BUDGET_MB = 7
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

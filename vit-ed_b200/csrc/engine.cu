@@ -94,6 +94,7 @@ struct vited_engine {
   int cache_layer0 = 1;
   int prune_tail = 1;   // last decoder layer: only the class-token row continues past self-attention
   int fuse_ln = 1;      // residual + LayerNorm in the epilogue of the N = 384 GEMMs (gemm_ln.cu)
+  int kv_budget_mb = 8000;  // K/V cache budget of one block of context rows in vited_score_grid
   int64_t launches = 0;
   // optional per-kernel timing (bench.py's roofline): one event before every launch, intervals summed per class
   int profile = 0;
@@ -614,6 +615,10 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
     case VITED_OPT_CACHE_LAYER0: e->cache_layer0 = value ? 1 : 0; return 0;
     case VITED_OPT_PRUNE_TAIL: e->prune_tail = value ? 1 : 0; return 0;
     case VITED_OPT_FUSE_LN: e->fuse_ln = value ? 1 : 0; return 0;
+    case VITED_OPT_KV_BUDGET_MB:
+      VITED_CHECK(value >= 1, "kv budget must be positive");
+      e->kv_budget_mb = value;
+      return 0;
     case VITED_OPT_PROFILE:
       e->profile = value ? 1 : 0;
       e->recs.clear();
@@ -735,9 +740,9 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
     TRY(scatter_split(e, e->xsrc.as<float>(), N, i0, n, s));
   }
 
-  // 2) context rows in blocks whose per-layer K/V cache stays within ~8 GB
+  // 2) context rows in blocks whose K/V cache stays within the budget (default 8 GB)
   const size_t kv_bytes_per_item = e->dec.size() * Ne * 2 * D * 2;
-  int rb = (int)((size_t)8e9 / kv_bytes_per_item);
+  int rb = (int)((size_t)e->kv_budget_mb * 1000000 / kv_bytes_per_item);
   if (rb < 1) rb = 1;
   const int pairs_per_chunk = items_per_batch(e);
   for (int r0 = row_begin; r0 < row_end; r0 += rb) {
