@@ -473,3 +473,41 @@ def prepare_pieces_restated(img_lab, piece_width, erosion, img_size):
             v = rgb.astype(np.float32) / np.float32(255)
             out.append(((v - np.float32(0.5)) / np.float32(0.5)).transpose(2, 0, 1))
     return torch.from_numpy(np.stack(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Hisfrag training step (product side not built): pair construction of prepare_data
+# (hisfrag.py:117-155) and loss / parameter gradients of one step (train_step :157-159, BCEWithLogitsLoss :60-61) by
+# autograd over the functional model above. Pinned by tests/golden/train_step.npz, which the reference's own
+# prepare_data and model file wrote (tests/golden/make_golden_train.py).
+# ---------------------------------------------------------------------------------------------------------------
+def train_pairs(targets, perm_seed):
+    """(groups [P, 2], labels [P, 1]): for every i the later items j > i with the same target are positive pairs
+    (i, j), those with another target negative pairs (hisfrag.py:121-137); at most twice as many negatives as
+    positives are kept, drawn by ``torch.randperm`` (:142-143; seeded here), positives first (:145-147)."""
+    t = torch.as_tensor(targets)
+    n = len(t)
+    pos = [(i, j) for i in range(n) for j in range(i, n) if j != i and t[j] == t[i]]
+    neg = [(i, j) for i in range(n) for j in range(i, n) if t[j] != t[i]]
+    pos_g = torch.tensor(pos, dtype=torch.long).view(-1, 2)
+    neg_g = torch.tensor(neg, dtype=torch.long).view(-1, 2)
+    neg_length = min(len(neg_g), int(2 * len(pos_g)))
+    torch.manual_seed(perm_seed)
+    neg_g = neg_g[torch.randperm(len(neg_g))[:neg_length]]
+    labels = torch.tensor([1.] * len(pos_g) + [0.] * len(neg_g), dtype=torch.float32).view(-1, 1)
+    return torch.cat([pos_g, neg_g], dim=0), labels
+
+
+def train_step(sd, num_heads, samples, targets, perm_seed):
+    """One training step without dropout / stochastic depth: encode the batch (with gradient, :149-150), decode
+    ``model(tokens[groups[:, 1]], samples[groups[:, 0]])`` (:152-154, :157-159), BCE-with-logits against the pair
+    labels. Returns (loss, logits, {parameter name: gradient})."""
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    groups, labels = train_pairs(targets, perm_seed)
+    with torch.enable_grad():
+        tokens = forward_first_part(samples, params, num_heads)
+        x2 = forward_second_part(tokens[groups[:, 1]], samples[groups[:, 0]], params, num_heads)
+        logits = forward_head(x2, params)
+        loss = F.binary_cross_entropy_with_logits(logits, labels)
+        loss.backward()
+    return loss.detach(), logits.detach(), groups, labels, {k: p.grad for k, p in params.items()}
