@@ -344,7 +344,7 @@ def run_ours(args):
             ach = sum(v['bytes'] for v in sel.values()) / (ms / 1e3) / 1e9
             peak, unit = peaks['hbm_gbs'], 'GB/s'
         return {'bound': f['bound'], 'kernel': f['kernel'], 'achieved': ach, 'peak': peak, 'unit': unit, 'frac': ach / peak,
-                'peak_source': peaks['source'] + (', sustained figure (kernel timed inside a long step)' if f['bound'] == 'tensor' else ''),
+                'peak_source': peaks['source'] + (', sustained dense 16-bit figure (measured by the driver with bf16; fp16 operands run at the same rate; kernel timed inside a long step)' if f['bound'] == 'tensor' else ''),
                 'traffic': f['traffic_ratio'] * sum(v['bytes'] for v in sel.values()) / max(n, 1) if world == 1 else None,
                 'launches_per_step': n, 'avg_launch_ms': ms / max(n, 1),
                 'algorithmic_per_launch': (sum(v['flops'] for v in sel.values()) if f['bound'] == 'tensor'
