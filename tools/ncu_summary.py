@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (read on the CPU box): key pipe/throughput metrics per captured launch and the top stall
-instructions of the first launch. usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [n_top]"""
+instructions of one launch. usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [n_top] [launch index, default 0]"""
 import csv
 import io
 import subprocess
@@ -7,6 +7,7 @@ import sys
 
 rep = sys.argv[1]
 ntop = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+launch = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
@@ -22,7 +23,7 @@ for w in want:
         print(f'{w} [{units[i]}]:', [r[i][:60] for r in data])
 for i, h in enumerate(hdr):
     if 'smsp__average_warps_issue_stalled' in h and h.endswith('_per_issue_active.ratio'):
-        v = float(data[0][i] or 0)
+        v = float(data[launch][i] or 0)
         if v > 0.2:
             print('  stall', h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''), round(v, 2))
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
@@ -35,7 +36,8 @@ for r in rows:
         continue
     if cur is not None:
         cur.append(r)
-b = blocks[0]
+b = blocks[launch]
+print('launch', launch, data[launch][hdr.index('Kernel Name')][:70])
 h, d = b[0], b[1:]
 iS, iSrc, iEx = h.index('Warp Stall Sampling (All Samples)'), h.index('Source'), h.index('Instructions Executed')
 tot = sum(int(r[iS]) for r in d if len(r) > iS and r[iS].isdigit())
