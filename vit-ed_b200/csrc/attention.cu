@@ -394,11 +394,114 @@ __global__ void __launch_bounds__(128) attn_simt_kernel(AttnArgs a) {
 
 static int attention_launch(const AttnArgs& a, int cls_only, cudaStream_t stream);
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Class-token query only, puzzle shape (head_dim 32, 64 patch keys [+ class-token key]): the pruned last decoder layer.
+// One query row per (sequence, head) is 4 KB of K and 4 KB of V against 8 KFLOP -- pure streaming, and the tile
+// kernels keep only four such units in flight per SM (0.36 ms per chunk at 2.2 TB/s). Here: one warp per unit, every
+// lane owns 8 dims of 8(+1) key rows (row 8 i + lane / 4, dims 8 (lane % 4) ..), all 18 16-byte loads of a unit are
+// independent, scores are reduced over the 4 lanes of a row, the softmax runs in fp32 registers, and P.V needs no
+// shuffles for P (a lane multiplies the V chunk of the rows whose probability it already holds).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const float2 a = unpack_act(u.x), b = unpack_act(u.y), c = unpack_act(u.z), d = unpack_act(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+__global__ void __launch_bounds__(256) attn_cls_warp_kernel(AttnArgs a) {
+  const int lane = threadIdx.x & 31, sub = lane & 3, rsub = lane >> 2;
+  const int n_units = a.n_seq * a.n_heads;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const float sl2 = a.scale * 1.4426950408889634f;
+  for (int unit = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < n_units; unit += warps) {
+    const int b = unit / a.n_heads, h = unit - b * a.n_heads;
+    const int kvb = a.kv_index != nullptr ? __ldg(a.kv_index + b) : b;
+    const size_t col = (size_t)h * 32 + 8 * sub;
+    const uint4 qv = __ldg(reinterpret_cast<const uint4*>(a.q + ((size_t)a.n_seq * 64 + b) * a.q_ld + col));
+    uint4 kk[9], vv[9];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const size_t r = (size_t)kvb * 64 + 8 * i + rsub;
+      kk[i] = __ldg(reinterpret_cast<const uint4*>(a.k + r * a.k_ld + col));
+      vv[i] = __ldg(reinterpret_cast<const uint4*>(a.v + r * a.v_ld + col));
+    }
+    const bool has_c = a.k_has_cls && rsub == 0;               // the class-token key: lanes 0..3
+    kk[8] = vv[8] = make_uint4(0, 0, 0, 0);
+    if (has_c) {
+      const size_t r = (size_t)a.n_kv_seq * 64 + kvb;
+      kk[8] = __ldg(reinterpret_cast<const uint4*>(a.k + r * a.k_ld + col));
+      vv[8] = __ldg(reinterpret_cast<const uint4*>(a.v + r * a.v_ld + col));
+    }
+    float q[8];
+    unpack8(qv, q);
+    float sc[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      float k8[8];
+      unpack8(kk[i], k8);
+      float d = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(q[e], k8[e], d);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      sc[i] = (i < 8 || has_c) ? d * sl2 : -INFINITY;
+      mx = fmaxf(mx, sc[i]);
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float p = exp2f(sc[i] - mx);                        // exp2f(-inf) = 0 for the rows that do not exist
+      l += p;
+      float v8[8];
+      unpack8(vv[i], v8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, v8[e], acc[e]);
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (rsub == 0) {                                            // lanes 0..3 hold the 32 output dims
+      const float inv = 1.f / l;
+      uint4 w;
+      w.x = pack_act(acc[0] * inv, acc[1] * inv);
+      w.y = pack_act(acc[2] * inv, acc[3] * inv);
+      w.z = pack_act(acc[4] * inv, acc[5] * inv);
+      w.w = pack_act(acc[6] * inv, acc[7] * inv);
+      *reinterpret_cast<uint4*>(a.o + ((size_t)a.n_seq * 64 + b) * a.o_ld + col) = w;
+    }
+  }
+}
+
+static bool attn_cls_warp_supported(const AttnArgs& a) {
+  return a.head_dim == 32 && a.nq_patch == 64 && a.nk_patch == 64 && a.q_has_cls &&
+         a.q_ld % 8 == 0 && a.k_ld % 8 == 0 && a.v_ld % 8 == 0 && a.o_ld % 8 == 0;
+}
+
 // class-token query only (last decoder layer): same kernel, only the fifth warp computes.
 int attention_cls(const AttnArgs& a, cudaStream_t stream) {
   VITED_CHECK(a.head_dim == 32 || a.head_dim == 64, "attention_cls: head_dim %d not supported (32 or 64)", a.head_dim);
   VITED_CHECK(a.q_has_cls, "attention_cls: the query sequences have no class token");
   if (a.n_seq == 0) return 0;
+  {
+    static int use_warp = -1;   // VITED_ATTN_CLS_WARP=0: back to the tile kernels (A/B measurements)
+    if (use_warp < 0) {
+      const char* e = getenv("VITED_ATTN_CLS_WARP");
+      use_warp = e ? atoi(e) : 1;
+    }
+    if (use_warp && attn_cls_warp_supported(a)) {
+      const int units = a.n_seq * a.n_heads;
+      int blocks = (units + 7) / 8;
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      attn_cls_warp_kernel<<<blocks, 256, 0, stream>>>(a);
+      VITED_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
   {
     const char* e = getenv("VITED_ATTN_TC");
     if ((!e || atoi(e) != 0) && attention_tc_cls_supported(a)) return attention_tc_cls(a, stream);
