@@ -187,3 +187,20 @@ def test_center_crop_u8_matches_torchvision(shape):
     arr = rng.integers(0, 256, size=(shape[0], shape[1], 3), dtype=np.uint8)
     want = np.asarray(transforms.CenterCrop(512)(Image.fromarray(arr)))
     assert np.array_equal(pieces.center_crop_u8(arr, 512), want)
+
+
+@pytest.mark.parametrize('name', ['test_patch32_64', 'small_hd64'])
+def test_training_pair_construction_matches_reference(name):
+    """train.prepare_pairs against the pair list the reference's own prepare_data produced (fixture
+    tests/golden/train_step.npz; same seeded randperm draw over the negatives)."""
+    from vited_b200 import train
+    z = np.load(os.path.join(GOLDEN, 'train_step.npz'))
+    torch.manual_seed(int(z[f'{name}_perm_seed']))
+    groups, labels = train.prepare_pairs(z[f'{name}_targets'])
+    assert np.array_equal(labels.numpy(), z[f'{name}_labels'])
+    assert np.array_equal(groups[:, 0].numpy(), z[f'{name}_first'])
+    from oracle import vited_oracle as orc
+    og, ol = orc.train_pairs(z[f'{name}_targets'], int(z[f'{name}_perm_seed']))
+    assert torch.equal(groups, og) and torch.equal(labels, ol)
+    with pytest.raises(vited_b200.VitedError):
+        train.train_step()
