@@ -204,3 +204,36 @@ def test_training_pair_construction_matches_reference(name):
     assert torch.equal(groups, og) and torch.equal(labels, ol)
     with pytest.raises(vited_b200.VitedError):
         train.train_step()
+
+
+def test_row_split_and_crop_geometry_properties():
+    """Property tests (hypothesis) of the integer bookkeeping against the oracle restatements: the sampler's row
+    boundaries for random grid sizes / world sizes, and the crop geometry for random image sizes, piece widths and
+    erosion ratios (Python's banker's rounding of the crop offset included)."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import vited_oracle as orc
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 160), world=st.integers(1, 9))
+    def sampler(n, world):
+        first_col = grid.upper_tri_pairs(n)[:, 0]
+        sizes = grid.indicates_row_ranges(first_col, world)
+        assert sizes == orc.sampler_sizes(first_col, world)
+        assert sizes[0] == 0 and sizes[-1] == n
+        ranges = [grid.hisfrag_row_range(n, world, r) for r in range(world)]
+        if all(sizes[i] <= sizes[i + 1] for i in range(len(sizes) - 1)):     # the reference can produce a backward
+            rows = [x for lo, hi in ranges for x in range(lo, hi)]           # boundary for tiny grids; kept as is
+            assert sorted(set(rows)) == sorted(rows) and set(rows) <= set(range(n))
+
+    @settings(max_examples=100, deadline=None)
+    @given(h=st.integers(64, 700), w=st.integers(64, 700), pw=st.sampled_from([32, 48, 64]),
+           erosion=st.sampled_from([0.0, 0.03, 0.07, 0.1, 0.14, 0.2, 0.25, 0.33]))
+    def geometry(h, w, pw, erosion):
+        rows, cols, top, left = pieces.grid_geometry(h, w, pw)
+        side, off = pieces.erosion_crop(pw, erosion)
+        assert (rows, cols, top, left, side, off) == orc.crop_geometry(h, w, pw, erosion)
+        assert rows >= 1 and cols >= 1 and top >= 0 and left >= 0
+        assert top + rows * pw <= h and left + cols * pw <= w and 0 <= off and off + side <= pw
+
+    sampler()
+    geometry()
