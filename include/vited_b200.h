@@ -66,8 +66,11 @@ enum {
                                    its self-attention on the class-token rows only (only row 0 reaches the head)   */
   VITED_OPT_FUSE_LN = 6,        /* 1 (default) = residual add + LayerNorm run in the epilogue of the producing GEMM
                                    (embed_dim 384, large row counts); 0 = separate resid_ln kernel                  */
-  VITED_OPT_KV_BUDGET_MB = 7    /* vited_score_grid processes context rows in blocks whose K/V cache (all decoder
+  VITED_OPT_KV_BUDGET_MB = 7,   /* vited_score_grid processes context rows in blocks whose K/V cache (all decoder
                                    layers) fits this many MB (default 8000; Hisfrag: 18.9 MB per fragment)          */
+  VITED_OPT_FUSE_MLP = 8        /* 1 (default) = the MLP sub-block (fc1, GELU, fc2), its residual add and the next
+                                   layer's LayerNorm run in one kernel, hidden activations never written (needs
+                                   FUSE_LN; embed_dim 384, large row counts); 0 = fc1 GEMM + fused fc2 GEMM          */
 };
 
 /* Library-wide last error message (thread-local). */
@@ -146,15 +149,22 @@ VITED_API int vited_normalize_u8(const uint8_t* images, int N, int S, float* out
  * inter_piece_distance.py:189-240: uint32 distances, minimum / second best, best-buddy candidates),
  * calculate_asymmetric_compatibility (:325-372), InterPieceDistance.calculate_mutual_compatibility (:489-524) and the
  * candidate matching of find_best_buddies (:626-648), for a type-1 puzzle (neighbour side = complementary side).
- * scores  [N, N, 4] f32 indexed by origin piece id: logits (scores_are_logits = 1: 1 - sigmoid is applied, as
- *         evaluation.py:109-114 does) or distances 1 - sigmoid(logit) (0);
+ * scores  [N, N, 4] f32 indexed by origin piece id;
+ * flags   bit 0 (VITED_TABLES_LOGITS): scores are logits and 1 - sigmoid is applied as evaluation.py:109-114 does
+ *         (clear: scores already are the distances 1 - sigmoid(logit));
+ *         bit 1 (VITED_TABLES_F32_PRODUCT): `pred[k] * 1000.` (evaluation.py:118-129, np.float32 scalar x Python float)
+ *         is evaluated in float32 as NumPy >= 2 does. Clear (default): in float64, as the NumPy 1.x of the reference's
+ *         pinned stack (requirements.txt: torch~=2.1, scipy~=1.9.1) does -- the truncated uint32 distance differs by one
+ *         on ~1e-5 of the entries between the two;
  * order   [N] i32 origin id of the piece at list position k (evaluation.py:87 shuffles the list), NULL = identity;
  * All outputs are indexed by list position, rows (i, side) with side = PuzzlePieceSide value (top 0, right 1,
  * bottom 2, left 3):  asym_dist [N,4,N] u32 (diagonal 2^31-1), min_dist / second_dist [N,4] i64 (sys.maxsize - 1 /
  * sys.maxsize where the reference leaves its initial values), n_candidates [N,4] i32 = pieces at the minimum,
  * candidate [N,4] i32 = the lowest such j (-1 if none), asym_compat / mutual_compat [N,4,N] f32 (diagonal +inf),
- * best_buddy [N,4] i32 = j or -1. Every value is bit-identical to the reference's (NumPy >= 2 scalar rules). */
-VITED_API int vited_puzzle_tables(const float* scores, int scores_are_logits, const int32_t* order, int N,
+ * best_buddy [N,4] i32 = j or -1. Every value is bit-identical to the reference's under the selected scalar rules. */
+#define VITED_TABLES_LOGITS 1
+#define VITED_TABLES_F32_PRODUCT 2
+VITED_API int vited_puzzle_tables(const float* scores, int flags, const int32_t* order, int N,
                                   uint32_t* asym_dist, int64_t* min_dist, int64_t* second_dist, int32_t* n_candidates,
                                   int32_t* candidate, float* asym_compat, float* mutual_compat, int32_t* best_buddy,
                                   void* stream);
@@ -180,6 +190,12 @@ VITED_API int vited_op_gemm(const void* A, const void* W, const float* bias, voi
  * h[M,384] h16 = LayerNorm(x) * ln_w + ln_b */
 VITED_API int vited_op_gemm_resid_ln(const void* A, const void* W, const float* bias, float* x, const float* ln_w,
                            const float* ln_b, void* h, int M, int N, int K, float eps, void* stream);
+/* fused MLP sub-block + residual + LayerNorm (D must be 384, hidden a multiple of 64): x[M,384] f32 +=
+ * GELU(h_in[M,384] h16 * W1[hidden,384]^T + b1) * W2[384,hidden]^T + b2; h_out[M,384] h16 = LayerNorm(x) * ln_w + ln_b
+ * (timm Mlp inside Block / CrossBlock, vision_transformer.py:126, :272, + the next norm1). h_out may alias h_in. */
+VITED_API int vited_op_mlp_resid_ln(const void* h_in, const void* W1, const float* b1, const void* W2, const float* b2,
+                          float* x, const float* ln_w, const float* ln_b, void* h_out, int M, int D, int hidden,
+                          float eps, void* stream);
 /* x += delta (h16, may be NULL); h = LayerNorm(x) * w + b as h16 (w NULL => skipped). Split token layout. */
 VITED_API int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
                       int n_patch, int has_cls, int D, float eps, void* stream);

@@ -22,6 +22,10 @@ import torch
 import torch.nn.functional as F
 
 EPS = 1e-6  # VisionTransformerCustom: norm_layer = partial(nn.LayerNorm, eps=1e-6) (vision_transformer.py:348)
+# The reference takes F.scaled_dot_product_attention when timm's use_fused_attn() says so (vision_transformer.py:32,
+# :63-66); the explicit softmax below is its other branch (:68-72). Same arithmetic; bench.py's torch GPU baseline turns
+# this on so that the stock fused kernels are what gets timed.
+USE_SDPA = False
 
 
 # ------------------------------------------------------------------------------------------------ model arithmetic
@@ -50,6 +54,9 @@ def attention(x, sd, prefix, num_heads):
     hd = c // num_heads
     qkv = _linear(x, sd, prefix + '.qkv').reshape(b, n, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
     q, k, v = qkv.unbind(0)
+    if USE_SDPA:
+        y = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+        return _linear(y, sd, prefix + '.proj')
     attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
     attn = attn.softmax(dim=-1)
     y = (attn @ v).transpose(1, 2).reshape(b, n, c)
@@ -64,6 +71,9 @@ def cross_attention(x, context, sd, prefix, num_heads):
     q = _linear(x, sd, prefix + '.q').reshape(b, n, num_heads, hd).permute(0, 2, 1, 3)
     kv = _linear(context, sd, prefix + '.kv').reshape(b, nc, 2, num_heads, hd).permute(2, 0, 3, 1, 4)
     k, v = kv.unbind(0)
+    if USE_SDPA:
+        y = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+        return _linear(y, sd, prefix + '.proj')
     attn = (q * hd ** -0.5) @ k.transpose(-2, -1)
     attn = attn.softmax(dim=-1)
     y = (attn @ v).transpose(1, 2).reshape(b, n, c)
@@ -282,8 +292,10 @@ SIDE_BIN = (3, 0, 1, 2)   # PuzzlePieceSide value (top 0, right 1, bottom 2, lef
 _MAXSIZE = 2 ** 63 - 1    # sys.maxsize on the 64-bit CPython the reference runs on
 
 
-def solver_tables(distance, order):
-    """distance [N, N, 4] fp32 = 1 - sigmoid(logits), indexed by origin piece id; order[k] = origin id of the piece at
+def solver_tables(distance, order, scalar_rules='numpy1'):
+    """scalar_rules: 'numpy1' = ``pred[k] * 1000.`` promotes to float64 (NumPy 1.x, the reference's pinned stack);
+    'numpy2' = stays float32 (NEP 50; what the reference code computes in this container's NumPy 2.3).
+    distance [N, N, 4] fp32 = 1 - sigmoid(logits), indexed by origin piece id; order[k] = origin id of the piece at
     list position k (evaluation.py:87 shuffles the list; InterPieceDistance numbers pieces by position, :437-441).
     Type-1 puzzles: the only valid neighbour side is the complementary one (:816-819), so tables are [N, 4, N].
     Returns the dict of arrays tests/golden/make_golden_tables.py stores."""
@@ -304,9 +316,13 @@ def solver_tables(distance, order):
             for j in range(n):
                 if j == i:
                     continue
-                # evaluation.py:118-129: float32 element * python float (float32 under NumPy >= 2), then the uint32
-                # store of :229 truncates
-                dist = int(np.uint32(np.float32(d[order[i], order[j], SIDE_BIN[s]]) * np.float32(1000.)))
+                # evaluation.py:118-129: float32 element * python float (float64 under NumPy 1.x, float32 under
+                # NumPy >= 2), then the uint32 store of :229 truncates
+                v = d[order[i], order[j], SIDE_BIN[s]]
+                if scalar_rules == 'numpy2':
+                    dist = int(np.uint32(np.float32(v) * np.float32(1000.)))
+                else:
+                    dist = int(np.uint32(np.float64(v) * np.float64(1000.)))
                 asym[i, s, j] = dist
                 if dist < mn:                                                  # :256-272
                     sec, mn, cands = mn, dist, [j]

@@ -1,6 +1,14 @@
 """Fixture for the solver's distance tables: runs the REFERENCE's own
 paikin_tal_solver.inter_piece_distance.InterPieceDistance (imports unchanged from /root/reference) with the distance
 callback of evaluation.py:116-131 on seeded [N, N, 4] distance arrays, and stores every table its constructor fills.
+
+Scalar rules: the closure returns ``pred[k] * 1000.`` (np.float32 scalar x Python float). The reference's pinned stack
+(requirements.txt: torch~=2.1, scipy~=1.9.1, scikit-image~=0.20) runs on NumPy 1.x, where that product is float64;
+this container has NumPy 2.3 (NEP 50), where it stays float32. Both fixture sets are written by the reference's own
+class: keys ``<table>_<seed>`` with the closure evaluated natively here (NumPy >= 2 rules) and ``<table>_np1_<seed>``
+with the product spelled ``np.float64(pred[k]) * 1000.`` -- the value NumPy 1.x's promotion computes. The two sets
+differ in the quantised cases (seeds 4 and 6: hundreds of distances off by one, e.g. float32(0.02) * 1000 truncates to
+19 in float64 and to 20 in float32) and in a handful of entries of the continuous ones.
 Run in the build container: python tests/golden/make_golden_tables.py"""
 import os
 import sys
@@ -47,8 +55,9 @@ class _Piece:
         self.id_number = -1
 
 
-def reference_tables(d, order):
+def reference_tables(d, order, numpy1=False):
     sys.path.insert(0, REF)
+    times1000 = (lambda v: np.float64(v) * 1000.) if numpy1 else (lambda v: v * 1000.)
     from paikin_tal_solver.inter_piece_distance import InterPieceDistance
     from paikin_tal_solver.puzzle_piece import PuzzlePieceSide
     from paikin_tal_solver.puzzle_importer import PuzzleType
@@ -57,16 +66,16 @@ def reference_tables(d, order):
         pred = d[piece_i.origin_piece_id][piece_j.origin_piece_id]
         if piece_j_side == PuzzlePieceSide.left:
             if piece_i_side == PuzzlePieceSide.right:
-                return pred[0] * 1000.
+                return times1000(pred[0])
         if piece_j_side == PuzzlePieceSide.right:
             if piece_i_side == PuzzlePieceSide.left:
-                return pred[2] * 1000.
+                return times1000(pred[2])
         if piece_j_side == PuzzlePieceSide.top:
             if piece_i_side == PuzzlePieceSide.bottom:
-                return pred[1] * 1000.
+                return times1000(pred[1])
         if piece_j_side == PuzzlePieceSide.bottom:
             if piece_i_side == PuzzlePieceSide.top:
-                return pred[3] * 1000.
+                return times1000(pred[3])
         return float('inf')
 
     pieces = [_Piece(o) for o in order]
@@ -103,8 +112,12 @@ if __name__ == '__main__':
         seed = case[0]
         d, order = case_inputs(*case)
         ref = reference_tables(d, order)
+        ref1 = reference_tables(d, order, numpy1=True)
         for k, v in ref.items():
             blob[f'{k}_{seed}'] = v
+        for k, v in ref1.items():
+            blob[f'{k}_np1_{seed}'] = v
+        print('  entries where the NumPy 1.x / >= 2 distances differ:', int((ref['asym_dist'] != ref1['asym_dist']).sum()))
         print(case, 'ties:', int((ref['candidates'].sum(-1) > 1).sum()), 'best buddies:', int((ref['best_buddy'] >= 0).sum()),
               'zeros:', int((ref['asym_dist'] == 0).sum()), 'start[0..2]:', ref['start_order'][:3].tolist())
     np.savez_compressed(os.path.join(HERE, 'solver_tables.npz'), **blob)

@@ -25,32 +25,8 @@ def case_inputs(z, kw):
 
 def shapes_from_kwargs(kw, mlp_ratio=4.0, in_chans=3):
     """state_dict key -> shape for a ViT-ED of these constructor kwargs (independent of any model class)."""
-    d, p = kw['embed_dim'], kw['patch_size']
-    ne = (kw['img_size'] // p) ** 2
-    hid = int(d * mlp_ratio)
-    sh = {'cls_token': (1, 1, d), 'pos_embed': (1, ne + 1, d), 'patch_embed.proj.weight': (d, in_chans, p, p),
-          'patch_embed.proj.bias': (d,), 'norm.weight': (d,), 'norm.bias': (d,),
-          'head.weight': (kw['num_classes'], d), 'head.bias': (kw['num_classes'],)}
-
-    def lin(prefix, o, i):
-        sh[prefix + '.weight'] = (o, i)
-        sh[prefix + '.bias'] = (o,)
-
-    def ln(prefix):
-        sh[prefix + '.weight'] = (d,)
-        sh[prefix + '.bias'] = (d,)
-
-    for l in range(kw['depth']):
-        b = f'blocks.{l}'
-        ln(b + '.norm1'); lin(b + '.attn.qkv', 3 * d, d); lin(b + '.attn.proj', d, d)
-        ln(b + '.norm2'); lin(b + '.mlp.fc1', hid, d); lin(b + '.mlp.fc2', d, hid)
-    for l in range(kw['c_depth']):
-        b = f'cross_blocks.{l}'
-        ln(b + '.norm1'); lin(b + '.attn.qkv', 3 * d, d); lin(b + '.attn.proj', d, d)
-        ln(b + '.norm_cross'); ln(b + '.norm_context')
-        lin(b + '.cross_attn.q', d, d); lin(b + '.cross_attn.kv', 2 * d, d); lin(b + '.cross_attn.proj', d, d)
-        ln(b + '.norm2'); lin(b + '.mlp.fc1', hid, d); lin(b + '.mlp.fc2', d, hid)
-    return sh
+    from vited_b200 import synthetic
+    return synthetic.state_dict_shapes(mlp_ratio=mlp_ratio, in_chans=in_chans, **kw)
 
 
 def make_gpu_model(kw, weight_seed):

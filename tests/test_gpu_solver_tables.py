@@ -31,13 +31,20 @@ def _compare(tables, want):
     assert tables.asym_dist.shape == (n, 4, n)
 
 
+@pytest.mark.parametrize('rules', ['numpy1', 'numpy2'])
 @pytest.mark.parametrize('case', mg.CASES, ids=lambda c: f'seed{c[0]}_{c[1]}x{c[2]}')
-def test_device_tables_match_reference_fixture(case):
+def test_device_tables_match_reference_fixture(case, rules):
+    """Both scalar-rule sets the reference's own class wrote: `pred[k] * 1000.` in float64 (NumPy 1.x, the reference's
+    pinned stack; the default) and in float32 (NumPy >= 2)."""
     from vited_b200 import solver_tables
     z = np.load(os.path.join(GOLDEN, 'solver_tables.npz'))
     d, order = mg.case_inputs(*case)
-    tables = solver_tables.build_tables(torch.from_numpy(d).cuda(), order=order, scores_are_logits=False)
-    _compare(tables, {k[:-len(f'_{case[0]}')]: z[k] for k in z.files if k.endswith(f'_{case[0]}')})
+    tables = solver_tables.build_tables(torch.from_numpy(d).cuda(), order=order, scores_are_logits=False,
+                                        scalar_rules=rules)
+    infix = '_np1' if rules == 'numpy1' else ''
+    keys = ['asym_dist', 'asym_compat', 'mutual_compat', 'min_dist', 'second_dist', 'candidates', 'best_buddy',
+            'start_order', 'start_compat']
+    _compare(tables, {k: z[f'{k}{infix}_{case[0]}'] for k in keys})
 
 
 @pytest.mark.parametrize('case', [(21, 10, 13, 0, 1), (22, 12, 12, 2, 5), (23, 1, 1, 0, 0), (24, 17, 16, 0, 0)],
@@ -50,8 +57,9 @@ def test_device_tables_match_oracle(case):
     d, order = mg.case_inputs(*case)
     tables = solver_tables.build_tables(torch.from_numpy(d).cuda(), order=order, scores_are_logits=False)
     _compare(tables, orc.solver_tables(d, order))
-    ident = solver_tables.build_tables(torch.from_numpy(d).cuda(), order=None, scores_are_logits=False)
-    _compare(ident, orc.solver_tables(d, np.arange(len(order))))
+    ident = solver_tables.build_tables(torch.from_numpy(d).cuda(), order=None, scores_are_logits=False,
+                                       scalar_rules='numpy2')
+    _compare(ident, orc.solver_tables(d, np.arange(len(order)), scalar_rules='numpy2'))
 
 
 def test_logit_mode_equals_torch_sigmoid_on_device():

@@ -127,7 +127,14 @@ class _FakeModel:
     form of (i, j, c)."""
     num_classes = 4
 
-    def score_grid(self, images, mode, row_begin, row_end):
+    def score_grid(self, images, mode, row_begin, row_end, out=None):
+        res = self._score(images, mode, row_begin, row_end)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def _score(self, images, mode, row_begin, row_end):
         n = images.shape[0]
         i = torch.arange(row_begin, row_end).view(-1, 1, 1).float()
         j = torch.arange(n).view(1, -1, 1).float()
@@ -149,9 +156,18 @@ def _gloo_worker(rank, world, n, port, q):
         model = _FakeModel()
         images = torch.zeros(n, 3, 8, 8)
         puzzle = grid.score_puzzle(model, images)
+        # a batch of puzzles of different sizes, (puzzle, row) units sharded over the ranks; puzzle 1 is handed over as
+        # a callable and must only be materialised on ranks that own rows of it
+        sizes = [5, 3, 9]
+        called = []
+        batch = [torch.zeros(sizes[0], 3, 8, 8), lambda: called.append(1) or torch.zeros(sizes[1], 3, 8, 8),
+                 torch.zeros(sizes[2], 3, 8, 8)]
+        many = grid.score_puzzles(model, batch, n_pieces=sizes)
+        owns1 = any(p == 1 for p, _, _ in grid.puzzle_unit_ranges(sizes, world, rank))
+        assert len(called) == (1 if owns1 else 0)
         model.num_classes = 1
         frag = grid.score_fragments(model, images)
-        q.put((rank, puzzle.numpy(), frag.numpy()))
+        q.put((rank, puzzle.numpy(), frag.numpy(), [m.numpy() for m in many]))
     finally:
         dist.destroy_process_group()
 
@@ -169,12 +185,30 @@ def test_row_sharding_and_gather_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     single = _FakeModel()
+    single_c4 = _FakeModel()
     want_puzzle = single.score_grid(torch.zeros(n, 3, 8, 8), vited_b200.GRID_ORDERED_OFFDIAG, 0, n)
     single.num_classes = 1
     want_frag = grid.mirror_upper(single.score_grid(torch.zeros(n, 3, 8, 8), vited_b200.GRID_UPPER_TRI_DIAG, 0, n)[..., 0])
-    for rank, puzzle, frag in results:
+    sizes = [5, 3, 9]
+    want_many = [single_c4.score_grid(torch.zeros(k, 3, 8, 8), vited_b200.GRID_ORDERED_OFFDIAG, 0, k) for k in sizes]
+    for rank, puzzle, frag, many in results:
         assert np.array_equal(puzzle, want_puzzle.numpy()), f'rank {rank} puzzle grid differs'
         assert np.array_equal(frag, want_frag.numpy()), f'rank {rank} fragment grid differs'
+        for got, want in zip(many, want_many):
+            assert np.array_equal(got, want.numpy()), f'rank {rank}: a puzzle of the batch differs'
+
+
+def test_puzzle_unit_ranges_cover_configs2():
+    """BASELINE configs[2]: 20 puzzles x 1000 rows over 8 ranks -> 2,500 units each, contiguous, puzzle-major."""
+    sizes = [1000] * 20
+    seen = []
+    for r in range(8):
+        segs = grid.puzzle_unit_ranges(sizes, 8, r)
+        assert sum(hi - lo for _, lo, hi in segs) == 2500
+        seen += [(p, row) for p, lo, hi in segs for row in range(lo, hi)]
+    assert seen == [(p, row) for p in range(20) for row in range(1000)]
+    assert grid.puzzle_unit_ranges([3, 2], 4, 1) == [(0, 2, 3), (1, 0, 1)] and grid.puzzle_unit_ranges([3, 2], 4, 2) == [(1, 1, 2)]
+    assert grid.puzzle_unit_ranges([3, 2], 4, 3) == [] and grid.puzzle_unit_ranges([3], 5, 4) == []
 
 
 @pytest.mark.parametrize('shape', [(600, 700), (512, 512), (513, 515), (400, 700), (300, 200), (511, 1024)])

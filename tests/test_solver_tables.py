@@ -28,16 +28,28 @@ def test_fixture_generator_cases_match_fixture():
     assert cases == [tuple(c) for c in mg.CASES]
 
 
+RULES = {'numpy1': '_np1', 'numpy2': ''}   # scalar rules -> fixture key infix (see make_golden_tables.py)
+
+
+@pytest.mark.parametrize('rules', sorted(RULES))
 @pytest.mark.parametrize('case', mg.CASES, ids=lambda c: f'seed{c[0]}_{c[1]}x{c[2]}')
-def test_oracle_tables_match_reference_fixture(case):
+def test_oracle_tables_match_reference_fixture(case, rules):
     from oracle import vited_oracle as orc
     z, _ = _cases()
     d, order = mg.case_inputs(*case)
-    got = orc.solver_tables(d, order)
+    got = orc.solver_tables(d, order, scalar_rules=rules)
     for k in KEYS:
-        ref = z[f'{k}_{case[0]}']
+        ref = z[f'{k}{RULES[rules]}_{case[0]}']
         assert got[k].dtype == ref.dtype and got[k].shape == ref.shape, k
         assert np.array_equal(got[k], ref), k          # bit-exact: integers, and floats produced by the same operations
+
+
+def test_scalar_rules_differ_where_the_fixture_says():
+    """float32(0.02 k) * 1000: 19.99.. in float64 (NumPy 1.x, the reference's pinned stack), 20.0 in float32."""
+    case = mg.CASES[4]
+    z, _ = _cases()
+    a, b = z[f'asym_dist_np1_{case[0]}'], z[f'asym_dist_{case[0]}']
+    assert (a != b).sum() > 100 and np.abs(a.astype(np.int64) - b.astype(np.int64)).max() == 1
 
 
 @pytest.mark.parametrize('case', mg.CASES, ids=lambda c: f'seed{c[0]}_{c[1]}x{c[2]}')
@@ -50,10 +62,11 @@ def test_start_piece_ordering_host(case):
     assert np.array_equal(np.array([float(c) for (_, _, c) in got]), z[f'start_compat_{seed}'])
 
 
-def _tables_from_oracle(d, order):
+def _tables_from_oracle(d, order, rules='numpy2'):
+    """(the reference-run comparisons below execute the reference under THIS container's NumPy >= 2)"""
     from oracle import vited_oracle as orc
     from vited_b200 import solver_tables
-    t = orc.solver_tables(d, order)
+    t = orc.solver_tables(d, order, scalar_rules=rules)
     n = len(order)
     n_cand = t['candidates'].sum(-1).astype(np.int32)
     cand = np.where(n_cand > 0, t['candidates'].argmax(-1), -1).astype(np.int32)

@@ -74,6 +74,22 @@ def main():
         by = M * K * 2 + 384 * K * 2 + M * 384 * (4 + 4 + 2)
         out.append(dict(op=f'gemm_ln_{name}', M=M, N=384, K=K, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
         del A, W, xx, hh
+    # fused MLP sub-block + residual + LayerNorm (fc1 -> GELU -> fc2, hidden activations never written)
+    hin = torch.randn(M, 384, device='cuda').to(L.act_dtype())
+    W1 = (torch.randn(1536, 384, device='cuda') / math.sqrt(384)).to(L.act_dtype())
+    W2 = (torch.randn(384, 1536, device='cuda') / math.sqrt(1536)).to(L.act_dtype())
+    b1 = torch.randn(1536, device='cuda'); b2 = torch.randn(384, device='cuda')
+    xx = torch.randn(M, 384, device='cuda')
+    lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
+    hh = torch.empty(M, 384, dtype=L.act_dtype(), device='cuda')
+    ms = timeit(lambda: L.check(L.lib.vited_op_mlp_resid_ln(hin.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                                             xx.data_ptr(), lw.data_ptr(), lb.data_ptr(), hh.data_ptr(), M, 384, 1536,
+                                                             1e-6, st), 'mlp_ln'), flush=flush)
+    fl = 4.0 * M * 384 * 1536
+    by = M * 384 * (2 + 4 + 4 + 2) + 4 * 384 * 1536
+    out.append(dict(op='mlp_ln', M=M, D=384, hidden=1536, ms=ms, tflops=fl / ms / 1e9, tflops_frac=fl / ms / 1e9 / tf,
+                    gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+    del hin, xx, hh
     # resid + LN
     D = 384
     x = torch.randn(M, D, device='cuda')

@@ -42,6 +42,7 @@ OPT_PROFILE = 4
 OPT_PRUNE_TAIL = 5
 OPT_FUSE_LN = 6
 OPT_KV_BUDGET_MB = 7
+OPT_FUSE_MLP = 8
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int
@@ -72,6 +73,7 @@ SIGNATURES = {
     "vited_workspace_bytes": (_i64, [_vp]),
     "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vited_op_gemm_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "vited_op_mlp_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "vited_op_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "vited_op_attention": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _i, _vp]),
     "vited_op_im2col": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -536,11 +536,10 @@ int attention(const AttnArgs& a, int impl, cudaStream_t stream) {
 static int attention_launch(const AttnArgs& a, int cls_only, cudaStream_t stream) {
   const size_t items = (size_t)a.n_seq * a.n_heads * (cls_only ? 1 : (a.nq_patch + 63) / 64);
   VITED_CHECK(items < (size_t)1 << 31, "attention: too many work items");
-  static int sms = 0, per_sm32 = 0, per_sm64 = 0;   // resident CTAs per SM (registers / shared memory)
-  if (sms == 0) {
-    int dev = 0;
-    VITED_CUDA_OK(cudaGetDevice(&dev));
-    VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static int per_sm32 = 0, per_sm64 = 0;   // resident CTAs per SM (registers / shared memory; same on every B200)
+  static PerDeviceOnce once;
+  const int sms = device_sm_count();
+  if (once.first()) {
     VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<32>::BYTES));
     VITED_CUDA_OK(cudaFuncSetAttribute(attn_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<64>::BYTES));
     VITED_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm32, attn_mma_kernel<32>, 160, AttnSmem<32>::BYTES));

@@ -659,13 +659,10 @@ bool attention_tc_supported(const AttnArgs& a) { return a.n_heads >= 1 && (p64_s
 static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
   const size_t items = (size_t)a.n_seq * a.n_heads * (a.nq_patch / 256 + (a.q_has_cls ? 1 : 0));
   VITED_CHECK(items < ((size_t)1 << 31), "attention_tc: too many work items");
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    VITED_CUDA_OK(cudaGetDevice(&dev));
-    VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static PerDeviceOnce once;
+  const int sms = device_sm_count();
+  if (once.first())
     VITED_CUDA_OK(cudaFuncSetAttribute(attn_l64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L64::BYTES));
-  }
   const uint64_t cols = (uint64_t)a.n_heads * 64;
   const uint64_t q_rows = (uint64_t)a.n_seq * a.nq_patch + (a.q_has_cls ? a.n_seq : 0);
   const uint64_t k_rows = (uint64_t)a.n_kv_seq * a.nk_patch + (a.k_has_cls ? a.n_kv_seq : 0);
@@ -700,13 +697,10 @@ int attention_tc_cls(const AttnArgs& a, cudaStream_t stream) {
 static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream) {
   const size_t units = (size_t)a.n_seq * a.n_heads;
   VITED_CHECK(units < ((size_t)1 << 31), "attention_tc: too many work units");
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    VITED_CUDA_OK(cudaGetDevice(&dev));
-    VITED_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static PerDeviceOnce once;
+  const int sms = device_sm_count();
+  if (once.first())
     VITED_CUDA_OK(cudaFuncSetAttribute(attn_p64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P64::BYTES));
-  }
   const uint64_t cols = (uint64_t)a.n_heads * 32;
   const uint64_t q_rows = (uint64_t)a.n_seq * 64 + (a.q_has_cls ? a.n_seq : 0);
   const uint64_t k_rows = (uint64_t)a.n_kv_seq * 64 + (a.k_has_cls ? a.n_kv_seq : 0);

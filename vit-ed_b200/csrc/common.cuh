@@ -50,6 +50,22 @@ const char* get_error();
     }                                                                                           \
   } while (0)
 
+// One-time setup PER DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy / SM-count queries apply to
+// the current device only, and a process may hold engines on several GPUs (a handle is bound to one device). first()
+// is true the first time it is called with a given device current. Callers serialise per the C-ABI contract.
+struct PerDeviceOnce {
+  unsigned long long done = 0;
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
+int device_sm_count();   // SM count of the CURRENT device (cached per device); gemm_tc.cu
+
 #ifdef __CUDACC__
 // Launch `kernel` so that it may overlap the tail of the previous kernel in `stream` (see pdl_wait below). Only for
 // kernels that call pdl_wait() before their first global-memory access.
@@ -153,6 +169,21 @@ __device__ __forceinline__ float warp_max(float v) {
 // exact-erf GELU (timm Mlp default act_layer=nn.GELU, approximate='none')
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// exact-erf GELU with ONE MUFU op: gelu(v) = max(v, 0) - 0.5*|v|*erfc(|v|/sqrt(2)), and erfc(a/sqrt(2)) = 2^(-Q(a)) with a
+// cubic Q (all coefficients positive, so 2^(-Q) decays monotonically for any |v|) fitted minimax on the GELU value:
+// |error| < 9e-5 everywhere, 1/50 of the fp16 rounding step of an O(1) activation (the result is stored as fp16).
+// 6 FP32 ops + ex2.approx. The fc1 epilogue is instruction-issue bound (16 epilogue warps x 64 columns per tile), so
+// every op counts: the degree-5 fit (6e-7) cost two more FMAs per element. (fit: tools/fit_gelu.py)
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float a = fabsf(v);
+  float q = fmaf(a, -0.0275597216f, -0.488495773f);
+  q = fmaf(a, q, -1.140745f);
+  q *= a;                                   // -Q(|v|)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+  return fmaf(-0.5f * a, e, fmaxf(v, 0.0f));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -397,6 +428,18 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[tmem, packed fp16 pairs, each CTA's own 128 rows] * B[smem desc, split over the pair]
+__device__ __forceinline__ void umma_f16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // arrive on the mbarrier at this shared-memory offset in BOTH CTAs once the issued cta_group::2 MMAs have completed

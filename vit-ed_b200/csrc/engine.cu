@@ -94,6 +94,7 @@ struct vited_engine {
   int cache_layer0 = 1;
   int prune_tail = 1;   // last decoder layer: only the class-token row continues past self-attention
   int fuse_ln = 1;      // residual + LayerNorm in the epilogue of the N = 384 GEMMs (gemm_ln.cu)
+  int fuse_mlp = 1;     // fc1 + GELU + fc2 + residual + LayerNorm in one kernel (mlp_ln.cu); needs fuse_ln
   int kv_budget_mb = 8000;  // K/V cache budget of one block of context rows in vited_score_grid
   int64_t launches = 0;
   // optional per-kernel timing (bench.py's roofline): one event before every launch, intervals summed per class
@@ -265,10 +266,27 @@ static int L_gemm_ln(vited_engine* e, const act_t* A, const Linear& l, float* x,
   }
   return gemm_resid_ln(A, l.w, l.b, x, ln.w, ln.b, h, M, l.out, l.in, 1e-6f, s);
 }
+// fused x += fc2(GELU(fc1(h))) ; h = LN(x)  (mlp_ln.cu)
+static bool use_fused_mlp(vited_engine* e, size_t rows, const Linear& fc1, const Linear& fc2) {
+  return e->fuse_mlp && use_fused_ln(e, rows, fc2) && fc1.in == e->D && fc2.in == fc1.out &&
+         mlp_resid_ln_supported((int)rows, e->D, fc1.out);
+}
+static int L_mlp_ln(vited_engine* e, const act_t* h_in, const Linear& fc1, const Linear& fc2, float* x, const LNorm& ln,
+                    act_t* h_out, int M, cudaStream_t s) {
+  if (e->profile) {
+    char nm[64];
+    snprintf(nm, sizeof(nm), "mlp_ln_d%d_h%d", fc1.in, fc1.out);
+    prof_mark(e, nm, 4.0 * M * (double)fc1.out * fc1.in,
+              4.0 * (double)fc1.out * fc1.in + (double)M * fc1.in * (2.0 + 4.0 + 4.0 + 2.0), s);
+  } else {
+    e->launches++;
+  }
+  return mlp_resid_ln(h_in, fc1.w, fc1.b, fc2.w, fc2.b, x, ln.w, ln.b, h_out, M, fc1.in, fc1.out, 1e-6f, s);
+}
 static int L_resid_ln(vited_engine* e, float* x, const act_t* delta, const float* gsrc, const int* gidx, int n_src,
-                      const LNorm* ln, act_t* h, int n_seq, int has_cls, int write_x, cudaStream_t s) {
+                      const LNorm* ln, act_t* h, int n_seq, int has_cls, int write_x, cudaStream_t s, int g_off = 0) {
   ResidLnArgs a;
-  a.x = x; a.delta = delta; a.gather_src = gsrc; a.gather_idx = gidx; a.n_src_seq = n_src;
+  a.x = x; a.delta = delta; a.gather_src = gsrc; a.gather_idx = gidx; a.gather_off = g_off; a.n_src_seq = n_src;
   a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
   a.n_seq = n_seq; a.n_patch = e->Ne; a.has_cls = has_cls; a.D = e->D; a.write_x = write_x; a.eps = 1e-6f;
   {
@@ -318,9 +336,9 @@ static int L_attn_cls(vited_engine* e, const act_t* q, int q_ld, const act_t* k,
 }
 // resid_ln over a plain block of `rows` rows (no split-layout bookkeeping): used for the class-token rows alone
 static int L_resid_ln_rows(vited_engine* e, float* x, const act_t* delta, const float* gsrc_cls_rows, const int* gidx,
-                           const LNorm* ln, act_t* h, int rows, cudaStream_t s) {
+                           const LNorm* ln, act_t* h, int rows, cudaStream_t s, int g_off = 0) {
   ResidLnArgs a;
-  a.x = x; a.delta = delta; a.gather_src = gsrc_cls_rows; a.gather_idx = gidx; a.n_src_seq = 0;
+  a.x = x; a.delta = delta; a.gather_src = gsrc_cls_rows; a.gather_idx = gidx; a.gather_off = g_off; a.n_src_seq = 0;
   a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
   a.n_seq = rows; a.n_patch = 1; a.has_cls = 0; a.D = e->D; a.write_x = 1; a.eps = 1e-6f;
   prof_mark(e, "resid_ln", 0.0, (double)rows * e->D * 12.0, s);
@@ -339,11 +357,23 @@ static int ensure_rows(vited_engine* e, size_t rows) {
   return 0;
 }
 
+// Every entry point makes the engine's device current for its own duration and puts the caller's device back on return
+// (the caller -- PyTorch -- tracks its own current device and must not find it changed underneath it).
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 static int check_ready(vited_engine* e) {
   VITED_CHECK(e != nullptr, "null engine");
   VITED_CHECK(e->loaded == (int)e->names.size(), "weights not loaded: %d of %d state_dict tensors received", e->loaded,
               (int)e->names.size());
-  VITED_CUDA_OK(cudaSetDevice(e->device));
   return 0;
 }
 
@@ -446,7 +476,8 @@ static int build_kv(vited_engine* e, const float* ctx, int n, cudaStream_t s) {
 
 // cross_part + head (vision_transformer.py:397-401, :415-417) for P pairs.
 //   ci[p]: context sequence inside the current KV block; xj[p]: item whose decoder state seeds the pair.
-static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, const float* xsrc, int n_src,
+//   xsrc holds the decoder input states of items [x_off, x_off + n_src) in split layout.
+static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, const float* xsrc, int n_src, int x_off,
                         int n_kv_seq, HeadArgs head, cudaStream_t s) {
   const size_t rows = (size_t)P * e->Nd;
   TRY(ensure_rows(e, rows));
@@ -475,9 +506,9 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
     const act_t* kvl = e->kv.as<act_t>() + l * kv_per_layer;
     if (!tail) {
       if (first && e->cache_layer0) {
-        TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s));
+        TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm_cross, h, P, 1, 1, s, x_off));
       } else {
-        if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
+        if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s, x_off));
         else if (!h_is_norm1) TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
         TRY(L_gemm(e, h, b.qkv, qkv, (int)rows, ACT_NONE, s));
         TRY(L_attn_self(e, qkv, o, P, 1, s));
@@ -496,12 +527,17 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
         TRY(L_gemm(e, o, b.cproj, delta, (int)rows, ACT_NONE, s));
         TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm2, h, P, 1, 1, s));
       }
-      TRY(L_gemm(e, h, b.fc1, hid, (int)rows, ACT_GELU, s));
       h_is_norm1 = false;
-      if (fuse && l + 1 < L) {
+      if (fuse && l + 1 < L && use_fused_mlp(e, rows, b.fc1, b.fc2)) {
+        // the whole MLP sub-block, its residual add and the next layer's norm1 in one kernel: `hid` is never written
+        TRY(L_mlp_ln(e, h, b.fc1, b.fc2, x, e->dec[l + 1].norm1, h, (int)rows, s));
+        h_is_norm1 = true;
+      } else if (fuse && l + 1 < L) {
+        TRY(L_gemm(e, h, b.fc1, hid, (int)rows, ACT_GELU, s));
         TRY(L_gemm_ln(e, hid, b.fc2, x, e->dec[l + 1].norm1, h, (int)rows, s));
         h_is_norm1 = true;
       } else {
+        TRY(L_gemm(e, h, b.fc1, hid, (int)rows, ACT_GELU, s));
         TRY(L_gemm(e, hid, b.fc2, delta, (int)rows, ACT_NONE, s));
       }
     } else {
@@ -512,9 +548,9 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
       act_t* o_c = o + cls_off * D;
       if (first && e->cache_layer0) {
         // single-layer decoder with the layer-0 cache: gather the class-token rows only
-        TRY(L_resid_ln_rows(e, x_c, nullptr, xsrc + (size_t)n_src * e->Ne * D, xj, &b.norm_cross, h_c, P, s));
+        TRY(L_resid_ln_rows(e, x_c, nullptr, xsrc + (size_t)n_src * e->Ne * D, xj, &b.norm_cross, h_c, P, s, x_off));
       } else {
-        if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s));
+        if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s, x_off));
         else if (!h_is_norm1) TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
         // keys/values for every token, the query for the class token only (qkv rows: [0,D) q, [D,3D) k|v)
         Linear w_kv = b.qkv; w_kv.w = b.qkv.w + D * D; w_kv.b = b.qkv.b + D; w_kv.out = 2 * (int)D;
@@ -543,11 +579,14 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
   return 0;
 }
 
-static int upload_ints(DevBuf& buf, const std::vector<int>& v, cudaStream_t s) {
-  TRY(buf.ensure(v.size() * sizeof(int) + 16));
-  VITED_CUDA_OK(cudaMemcpyAsync(buf.p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, s));
-  VITED_CUDA_OK(cudaStreamSynchronize(s));  // the host vector may die right after this call
-  return 0;
+// pair list of grid rows [r0, r1) into e->ci / e->xj (generated on the device; nothing to upload or wait for)
+static int build_pair_list(vited_engine* e, int mode, int r0, int r1, int N, size_t* total, cudaStream_t s) {
+  *total = pair_list_count(mode, r0, r1, N);
+  if (*total == 0) return 0;
+  TRY(e->ci.ensure(*total * sizeof(int) + 16));
+  TRY(e->xj.ensure(*total * sizeof(int) + 16));
+  prof_mark(e, "pair_list", 0.0, (double)*total * 8.0, s);
+  return pair_list(mode, r0, r1, N, e->ci.as<int>(), e->xj.as<int>(), s);
 }
 
 }  // namespace vited
@@ -573,7 +612,7 @@ int vited_create(const vited_config* cfg, int device, vited_engine** out) {
   VITED_CHECK(ce == cudaSuccess && ndev > 0, "vited_create: no CUDA device available (%s); this path has no CPU fallback",
               cudaGetErrorString(ce));
   VITED_CHECK(device >= 0 && device < ndev, "vited_create: device %d out of range (%d devices)", device, ndev);
-  VITED_CUDA_OK(cudaSetDevice(device));
+  DeviceScope scope(device);
   cudaDeviceProp prop;
   VITED_CUDA_OK(cudaGetDeviceProperties(&prop, device));
   VITED_CHECK(prop.major == 10, "vited_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
@@ -583,6 +622,8 @@ int vited_create(const vited_config* cfg, int device, vited_engine** out) {
   e->device = device;
   const char* cr = getenv("VITED_CHUNK_ROWS");
   if (cr && atoll(cr) > 0) e->chunk_rows = atoll(cr);
+  const char* fm = getenv("VITED_FUSE_MLP");   // A/B runs of bench.py; vited_set_option(VITED_OPT_FUSE_MLP) is the API
+  if (fm) e->fuse_mlp = atoi(fm) ? 1 : 0;
   if (build(e) != 0) {
     vited_destroy(e);
     return 1;
@@ -593,7 +634,7 @@ int vited_create(const vited_config* cfg, int device, vited_engine** out) {
 
 void vited_destroy(vited_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceScope scope(e->device);
   cudaDeviceSynchronize();
   for (void* p : e->owned) cudaFree(p);
   DevBuf* bufs[] = {&e->x, &e->h, &e->qkv, &e->o, &e->q, &e->delta, &e->hid, &e->col, &e->tok, &e->xsrc, &e->enc_tok,
@@ -615,6 +656,7 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
     case VITED_OPT_CACHE_LAYER0: e->cache_layer0 = value ? 1 : 0; return 0;
     case VITED_OPT_PRUNE_TAIL: e->prune_tail = value ? 1 : 0; return 0;
     case VITED_OPT_FUSE_LN: e->fuse_ln = value ? 1 : 0; return 0;
+    case VITED_OPT_FUSE_MLP: e->fuse_mlp = value ? 1 : 0; return 0;
     case VITED_OPT_KV_BUDGET_MB:
       VITED_CHECK(value >= 1, "kv budget must be positive");
       e->kv_budget_mb = value;
@@ -630,7 +672,7 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
 
 int vited_load_weight(vited_engine* e, const char* name, const float* data, int64_t numel, void* stream) {
   VITED_CHECK(e != nullptr && name != nullptr && data != nullptr, "vited_load_weight: null argument");
-  VITED_CUDA_OK(cudaSetDevice(e->device));
+  DeviceScope scope(e->device);
   auto it = e->slots.find(name);
   VITED_CHECK(it != e->slots.end(), "unexpected key in state_dict: %s", name);
   Slot& sl = it->second;
@@ -659,6 +701,7 @@ const char* vited_weight_name(vited_engine* e, int i) {
 
 int vited_encode(vited_engine* e, const float* images, int B, float* out_tokens, void* stream) {
   TRY(check_ready(e));
+  DeviceScope scope(e->device);
   VITED_CHECK(B >= 0 && (B == 0 || (images && out_tokens)), "vited_encode: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
@@ -682,13 +725,12 @@ static int decode_impl(vited_engine* e, const float* ctx_tokens, const float* im
     TRY(e->xsrc.ensure((size_t)n * e->Nd * e->D * 4));
     VITED_CUDA_OK(cudaMemcpyAsync(e->xsrc.p, e->x.p, (size_t)n * e->Nd * e->D * 4, cudaMemcpyDeviceToDevice, s));
     TRY(build_kv(e, ctx_tokens + (size_t)i0 * e->Ne * e->D, n, s));
-    std::vector<int> idx(n);
-    for (int i = 0; i < n; ++i) idx[i] = i;
-    TRY(upload_ints(e->ci, idx, s));
+    size_t total = 0;
+    TRY(build_pair_list(e, 2, 0, n, n, &total, s));   // pair p: context p, decoder state p
     HeadArgs head = {};
     head.out = out_logits + (size_t)i0 * e->C;
     head.ci = nullptr; head.xj = nullptr; head.row_begin = 0; head.n_items = 0;
-    TRY(decode_chunk(e, n, e->ci.as<int>(), e->ci.as<int>(), e->xsrc.as<float>(), n, n, head, s));
+    TRY(decode_chunk(e, n, e->ci.as<int>(), e->xj.as<int>(), e->xsrc.as<float>(), n, 0, n, head, s));
   }
   return 0;
 }
@@ -696,6 +738,7 @@ static int decode_impl(vited_engine* e, const float* ctx_tokens, const float* im
 int vited_decode(vited_engine* e, const float* ctx_tokens, const float* images, int B, float* out_logits,
                  void* stream) {
   TRY(check_ready(e));
+  DeviceScope scope(e->device);
   VITED_CHECK(B >= 0 && (B == 0 || (ctx_tokens && images && out_logits)), "vited_decode: bad arguments");
   const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
   return decode_impl(e, ctx_tokens, images, img, B, out_logits, (cudaStream_t)stream);
@@ -703,6 +746,7 @@ int vited_decode(vited_engine* e, const float* ctx_tokens, const float* images, 
 
 int vited_forward_pairs(vited_engine* e, const float* pairs, int B, float* out_logits, void* stream) {
   TRY(check_ready(e));
+  DeviceScope scope(e->device);
   VITED_CHECK(B >= 0 && (B == 0 || (pairs && out_logits)), "vited_forward_pairs: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
@@ -721,6 +765,7 @@ int vited_forward_pairs(vited_engine* e, const float* pairs, int B, float* out_l
 int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int row_begin, int row_end, float* out,
                      void* stream) {
   TRY(check_ready(e));
+  DeviceScope scope(e->device);
   VITED_CHECK(mode == VITED_GRID_ORDERED_OFFDIAG || mode == VITED_GRID_UPPER_TRI_DIAG, "unknown grid mode %d", mode);
   VITED_CHECK(N >= 0 && row_begin >= 0 && row_begin <= row_end && row_end <= N, "bad row range [%d, %d) for N=%d",
               row_begin, row_end, N);
@@ -731,13 +776,17 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
   const size_t D = e->D, Ne = e->Ne, Nd = e->Nd;
   const int step = items_per_batch(e);
 
-  // 1) decoder input state of every item (columns of the grid): computed once per item, reused by every pair
-  TRY(e->xsrc.ensure((size_t)N * Nd * D * 4));
-  for (int i0 = 0; i0 < N; i0 += step) {
-    const int n = (N - i0 < step) ? (N - i0) : step;
-    TRY(patch_tokens(e, images + (size_t)i0 * img, img, n, s));
+  // 1) decoder input state of every item that appears as a COLUMN of this row shard: computed once per item, reused
+  //    by every pair. The upper-triangular grid (hisfrag.py:166-167) never pairs a row with a column j < row_begin,
+  //    so a row shard builds (and holds) only the states of items [row_begin, N).
+  const int c0 = (mode == VITED_GRID_UPPER_TRI_DIAG) ? row_begin : 0;
+  const int n_cols = N - c0;
+  TRY(e->xsrc.ensure((size_t)n_cols * Nd * D * 4));
+  for (int i0 = 0; i0 < n_cols; i0 += step) {
+    const int n = (n_cols - i0 < step) ? (n_cols - i0) : step;
+    TRY(patch_tokens(e, images + (size_t)(c0 + i0) * img, img, n, s));
     TRY(decoder_item_state(e, n, s));
-    TRY(scatter_split(e, e->xsrc.as<float>(), N, i0, n, s));
+    TRY(scatter_split(e, e->xsrc.as<float>(), n_cols, i0, n, s));
   }
 
   // 2) context rows in blocks whose K/V cache stays within the budget (default 8 GB)
@@ -757,21 +806,9 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
     }
     TRY(build_kv(e, e->enc_tok.as<float>(), nr, s));
     // pair list of the block, i-major (data/datasets/pieces_dataset.py:27-32 / hisfrag.py:166-167)
-    std::vector<int> ci, xj;
-    if (mode == VITED_GRID_ORDERED_OFFDIAG) {
-      ci.reserve((size_t)nr * (N - 1));
-      xj.reserve((size_t)nr * (N - 1));
-      for (int i = r0; i < r1; ++i)
-        for (int j = 0; j < N; ++j)
-          if (j != i) { ci.push_back(i - r0); xj.push_back(j); }
-    } else {
-      for (int i = r0; i < r1; ++i)
-        for (int j = i; j < N; ++j) { ci.push_back(i - r0); xj.push_back(j); }
-    }
-    if (ci.empty()) continue;
-    TRY(upload_ints(e->ci, ci, s));
-    TRY(upload_ints(e->xj, xj, s));
-    const size_t total = ci.size();
+    size_t total = 0;
+    TRY(build_pair_list(e, mode == VITED_GRID_ORDERED_OFFDIAG ? 0 : 1, r0, r1, N, &total, s));
+    if (total == 0) continue;
     // equal chunks: a short last chunk would run every kernel of the stack at a fraction of a wave
     const size_t n_chunks = (total + pairs_per_chunk - 1) / pairs_per_chunk;
     const size_t chunk = (total + n_chunks - 1) / n_chunks;
@@ -783,7 +820,7 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
       head.xj = e->xj.as<int>() + p0;
       head.row_begin = 0;  // ci is already relative to r0
       head.n_items = N;
-      TRY(decode_chunk(e, P, e->ci.as<int>() + p0, e->xj.as<int>() + p0, e->xsrc.as<float>(), N, nr, head, s));
+      TRY(decode_chunk(e, P, e->ci.as<int>() + p0, e->xj.as<int>() + p0, e->xsrc.as<float>(), n_cols, c0, nr, head, s));
     }
   }
   return 0;
@@ -791,7 +828,7 @@ int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int 
 
 const char* vited_profile_json(vited_engine* e, void* stream) {
   if (!e) return "{}";
-  cudaSetDevice(e->device);
+  DeviceScope scope(e->device);
   cudaStream_t s = (cudaStream_t)stream;
   struct Acc { double ms = 0, flops = 0, bytes = 0; long n = 0; };
   std::vector<Acc> acc(e->cls_names.size());
@@ -840,6 +877,13 @@ int vited_op_gemm_resid_ln(const void* A, const void* W, const float* bias, floa
   return gemm_resid_ln((const act_t*)A, (const act_t*)W, bias, x, ln_w, ln_b, (act_t*)h, M, N, K, eps, (cudaStream_t)stream);
 }
 
+int vited_op_mlp_resid_ln(const void* h_in, const void* W1, const float* b1, const void* W2, const float* b2, float* x,
+                          const float* ln_w, const float* ln_b, void* h_out, int M, int D, int hidden, float eps,
+                          void* stream) {
+  return mlp_resid_ln((const act_t*)h_in, (const act_t*)W1, b1, (const act_t*)W2, b2, x, ln_w, ln_b, (act_t*)h_out, M, D,
+                      hidden, eps, (cudaStream_t)stream);
+}
+
 int vited_op_resid_ln(float* x, const void* delta, const float* ln_w, const float* ln_b, void* h, int n_seq,
                       int n_patch, int has_cls, int D, float eps, void* stream) {
   ResidLnArgs a;
@@ -878,10 +922,10 @@ int vited_retrieval_rows(const float* sim, const int32_t* labels, int N, int32_t
   return retrieval_rows(sim, labels, N, n_relevant, ap_sum, top1, hits10, hits100, (cudaStream_t)stream);
 }
 
-int vited_puzzle_tables(const float* scores, int scores_are_logits, const int32_t* order, int N, uint32_t* asym_dist,
+int vited_puzzle_tables(const float* scores, int flags, const int32_t* order, int N, uint32_t* asym_dist,
                         int64_t* min_dist, int64_t* second_dist, int32_t* n_candidates, int32_t* candidate,
                         float* asym_compat, float* mutual_compat, int32_t* best_buddy, void* stream) {
-  return puzzle_tables(scores, scores_are_logits, order, N, asym_dist, reinterpret_cast<long long*>(min_dist),
+  return puzzle_tables(scores, flags, order, N, asym_dist, reinterpret_cast<long long*>(min_dist),
                        reinterpret_cast<long long*>(second_dist), n_candidates, candidate, asym_compat, mutual_compat,
                        best_buddy, (cudaStream_t)stream);
 }

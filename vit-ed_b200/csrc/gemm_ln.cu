@@ -315,12 +315,10 @@ int gemm_resid_ln(const act_t* A, const act_t* W, const float* bias, float* x, c
                 reinterpret_cast<uintptr_t>(h)) & 15) == 0, "gemm_resid_ln: operands must be 16-byte aligned");
   const int sms = gemm_num_sms();
   VITED_CHECK(sms >= 2, "gemm_resid_ln: no device");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first())
     VITED_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)LnCfg::SMEM_BYTES));
-    attr_set = true;
-  }
   CUtensorMap tA, tB, tX, tH;
   if (make_tmap_act_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, BM, 128)) return 1;
   if (make_tmap_act_2d(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, 64, NH / 2, 128)) return 1;

@@ -17,9 +17,18 @@
 namespace vited {
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-static int g_num_sms = 0;
 static std::once_flag g_once;
 static int g_init_status = 0;
+
+int device_sm_count() {
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = sms[dev & 63];
+  if (n == 0) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+#define g_num_sms device_sm_count()
 
 static void init_driver_once() {
   void* fn = nullptr;
@@ -31,14 +40,11 @@ static void init_driver_once() {
     return;
   }
   g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
 }
 
 int gemm_num_sms() {
   std::call_once(g_once, init_driver_once);
-  return g_num_sms;
+  return device_sm_count();
 }
 
 // 2-D fp16 tensor map: inner dim = cols (contiguous), outer dim = rows, 128B swizzle, box = 64 cols x box_rows.
@@ -128,21 +134,6 @@ struct GemmCfg {
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 up to 256");
   static_assert(kStages >= 3, "not enough shared memory for the pipeline");
 };
-
-// exact-erf GELU with ONE MUFU op: gelu(v) = max(v, 0) - 0.5*|v|*erfc(|v|/sqrt(2)), and erfc(a/sqrt(2)) = 2^(-Q(a)) with a
-// cubic Q (all coefficients positive, so 2^(-Q) decays monotonically for any |v|) fitted minimax on the GELU value:
-// |error| < 9e-5 everywhere, 1/50 of the fp16 rounding step of an O(1) activation (the result is stored as fp16).
-// 6 FP32 ops + ex2.approx. The fc1 epilogue is instruction-issue bound (16 epilogue warps x 64 columns per tile), so
-// every op counts: the degree-5 fit (6e-7) cost two more FMAs per element. (fit: tools/fit_gelu.py)
-__device__ __forceinline__ float gelu_fast(float v) {
-  const float a = fabsf(v);
-  float q = fmaf(a, -0.0275597216f, -0.488495773f);
-  q = fmaf(a, q, -1.140745f);
-  q *= a;                                   // -Q(|v|)
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
-  return fmaf(-0.5f * a, e, fmaxf(v, 0.0f));
-}
 
 // bias (+ GELU) on one thread's 64 accumulator columns, packed to fp16 and written into the warp's 32x128-byte staging
 // box in the 128B-swizzle pattern the TMA store expects (16-byte chunk c of row r lives at chunk c ^ (r & 7)).
@@ -702,8 +693,12 @@ template <int BN, int ACT>
 static int launch_quad(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                        int N, int K, cudaStream_t stream) {
   using Cfg = PairCfg<BN>;
-  static int max_clusters = -1;
-  if (max_clusters < 0) {
+  static PerDeviceOnce once;
+  static int max_clusters_dev[64];
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  int& max_clusters = max_clusters_dev[dev_id & 63];
+  if (once.first()) {
     VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_quad_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
     // how many 4-CTA clusters the device can hold at once (GPC sizes that are not multiples of 4 strand a few SMs)
@@ -734,12 +729,10 @@ template <int BN, int ACT>
 static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                        int N, int K, cudaStream_t stream) {
   using Cfg = PairCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first())
     VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_pair_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   int pairs = g_num_sms / 2;
   if (pairs > tiles) pairs = tiles;
@@ -754,12 +747,10 @@ template <int BN, int ACT, int KB_RES>
 static int launch_tc(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                      int N, int K, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, KB_RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first())
     VITED_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, ACT, KB_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   const int m_blks = (M + BM - 1) / BM, n_blks = (N + BN - 1) / BN;
   int grid, order = 0;
   if (KB_RES > 0) {

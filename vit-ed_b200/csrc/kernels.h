@@ -29,6 +29,15 @@ bool gemm_resid_ln_supported(int M, int N, int K);
 int gemm_resid_ln(const act_t* A, const act_t* W, const float* bias, float* x, const float* ln_w, const float* ln_b,
                   act_t* h, int M, int N, int K, float eps, cudaStream_t stream);
 
+// ---- fused MLP sub-block + residual + LayerNorm (mlp_ln.cu) ----
+//   x[M,384] (f32, in place) += GELU(h_in[M,384] W1[hidden,384]^T + b1) W2[384,hidden]^T + b2;  h_out = LayerNorm(x) * ln_w + ln_b
+// i.e. `x = x + mlp(norm2(x))` followed by the next layer's `norm1(x)` (vision_transformer.py:126-127, :272) in ONE kernel:
+// the [M, hidden] activations never leave the SM. h_out may alias h_in. Only embed_dim 384, hidden a multiple of 64.
+bool mlp_resid_ln_supported(int M, int D, int hidden);
+int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_t* W2, const float* b2, float* x,
+                 const float* ln_w, const float* ln_b, act_t* h_out, int M, int D, int hidden, float eps,
+                 cudaStream_t stream);
+
 // ---- row-wise kernels (rowops.cu) ----
 // x[r,:] = (gather ? src[map(r),:] : x[r,:]) + delta[r,:]; optionally h[r,:] = LayerNorm(x[r,:]) * w + b (fp16).
 // Row space is the "split" layout: n_seq*n_patch patch rows followed by n_cls cls rows (n_cls = n_seq or 0).
@@ -36,7 +45,8 @@ struct ResidLnArgs {
   float* x;              // [R, D] residual stream (fp32), updated in place when write_x
   const act_t* delta;     // [R, D] or null
   const float* gather_src;   // split-layout source [n_src_seq*n_patch (+ n_src_seq cls rows), D] or null
-  const int* gather_idx;     // [n_seq] source sequence of every destination sequence
+  const int* gather_idx;     // [n_seq] source item of every destination sequence; source sequence = item - gather_off
+  int gather_off;            // first item held in gather_src (vited_score_grid keeps only the columns a row shard needs)
   int n_src_seq;
   const float* ln_w;     // null -> no LayerNorm output
   const float* ln_b;
@@ -71,6 +81,14 @@ struct HeadArgs {
 };
 int head_logits(const HeadArgs& a, cudaStream_t stream);
 
+// pair list of grid rows [r0, r1) on the device, i-major: ci[p] = i - r0 (context row inside the block), xj[p] = j.
+//   mode 0: ordered off-diagonal pairs, j in [0, N) \ {i}  (data/datasets/pieces_dataset.py:27-32)
+//   mode 1: upper triangle incl. diagonal, j in [i, N)       (hisfrag.py:166-167)
+//   mode 2: identity, ci[p] = xj[p] = p for p in [0, r1 - r0)  (two-phase / one-shot decode of B pairs)
+// pair_list_count returns the number of pairs (the caller sizes ci / xj with it).
+size_t pair_list_count(int mode, int r0, int r1, int N);
+int pair_list(int mode, int r0, int r1, int N, int* ci, int* xj, cudaStream_t stream);
+
 // plain copy/convert helpers
 int f32_to_act(const float* in, act_t* out, size_t n, cudaStream_t stream);
 int add_delta_out(const float* x, const act_t* delta, float* out, size_t rows, int D, cudaStream_t stream);
@@ -86,7 +104,7 @@ int retrieval_rows(const float* sim, const int* labels, int N, int* n_rel, doubl
                    int* hits100, cudaStream_t stream);
 
 // ---- solver distance tables (solver_tables.cu): see include/vited_b200.h vited_puzzle_tables ----
-int puzzle_tables(const float* scores, int scores_are_logits, const int* order, int N, uint32_t* asym, long long* min_d,
+int puzzle_tables(const float* scores, int flags, const int* order, int N, uint32_t* asym, long long* min_d,
                   long long* second_d, int* n_cand, int* cand, float* compat, float* mutual, int* best_buddy,
                   cudaStream_t stream);
 

@@ -1,0 +1,459 @@
+// Fused MLP sub-block of the ViT-ED blocks in ONE kernel (embed_dim 384):
+//     x += fc2(GELU(fc1(h) + b1)) + b2      (timm Mlp inside Block / CrossBlock: vision_transformer.py:126, :272)
+//     h  = LayerNorm(x) * g + b              (the NEXT layer's norm1; eps 1e-6)
+// The unfused sequence writes the [rows, 1536] hidden activations to HBM (fc1 + GELU epilogue) and reads them back
+// (fc2): 6 KB of the 10.7 KB per row those two launches move. Here the hidden activations never leave the SM.
+//
+// A CTA pair owns complete 256 x 384 output rows (cta_group::2, 128 rows per CTA). Per tile:
+//   * the h tile (A operand of fc1, 128 x 384 fp16 per CTA = 96 KB) is loaded ONCE and stays in shared memory;
+//   * the hidden dimension is walked in chunks of 64: S_c = h W1_c^T (M 256, N 64, K 384) into one of two 64-column
+//     TMEM buffers; the eight GELU warps turn S_c + b1 into fp16 probabilities-style operands P_c written back over S_c
+//     (tcgen05.st, packed pairs) and the second MMA takes P_c as its A operand straight from TMEM:
+//     O += P_c W2_c^T (M 256, N 2 x 192, K 64) into the 384-column output accumulator;
+//   * issue order G1(0) G1(1) | G2(c) G1(c+2) ...: the tensor pipe runs fc1 of chunk c+1 while the GELU warps work on
+//     chunk c; the weight chunks (W1_c: 64 x 384, W2_c: 384 x 64) stream from L2 through a ring of 12-KB slots;
+//   * the full-row epilogue of gemm_ln.cu (residual tile through TMA boxes, updated row parked in TMEM, shifted one-pass
+//     statistics, Chan combination of the two column halves, normalise, TMA stores) runs on the same eight warps. Its
+//     residual boxes live in the h-tile region, which is dead once fc1 of the last chunk has completed.
+// TMEM: O = columns [0, 384), S buffers [384, 448) and [448, 512). Shared memory: 96 KB h tile / residual boxes,
+// 72 KB weight ring, 32 KB output staging, biases / LayerNorm parameters.
+#include "kernels.h"
+
+namespace vited {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int LN_N = 384;
+constexpr int NH = 192;          // columns per fc2 MMA / per epilogue half
+constexpr int CHUNKS = NH / 32;  // 32-column epilogue chunks per half row
+constexpr int HC = 64;           // hidden units per chunk
+constexpr int KB1 = LN_N / BK;   // k-blocks of fc1 (K = 384)
+
+struct MlpCfg {
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr uint32_t A_KB_BYTES = BM * BK * 2;                 // one k-block of the h tile: 128 rows x 128 B
+  static constexpr uint32_t A_BYTES = KB1 * A_KB_BYTES;               // 96 KB
+  static constexpr uint32_t SLOT_BYTES = 12288;                       // 3 k-blocks of W1 (32 rows each) or 96 rows of W2
+  static constexpr int kSlots = 6;
+  static constexpr uint32_t W1_KB_BYTES = (HC / 2) * BK * 2;          // this CTA's 32 rows of one k-block: 4 KB
+  static constexpr uint32_t XBOX = 32 * 32 * 4;                       // 32 rows x 32 fp32, 128B-swizzled
+  static constexpr uint32_t OUT_BYTES = kEpiWarps * 4096;             // pass-2 staging: 32 rows x 64 fp16 per warp
+  static constexpr uint32_t PART_BYTES = 2 * BM * 16;
+  static constexpr uint32_t BAR_BYTES = 512;
+  static_assert(kEpiWarps * 3 * XBOX == A_BYTES, "the residual boxes (2 in + 1 out per warp) reuse the h-tile region");
+  static uint32_t smem_bytes(int hidden) {
+    return 1024 + A_BYTES + kSlots * SLOT_BYTES + OUT_BYTES + (uint32_t)hidden * 4 + 3 * LN_N * 4 + PART_BYTES + BAR_BYTES;
+  }
+};
+
+constexpr uint32_t kColS = LN_N;   // first TMEM column of the two hidden-chunk buffers
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MlpCfg::kThreads, 1)
+mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
+                   const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
+                   const __grid_constant__ CUtensorMap tmH, const float* __restrict__ b1, const float* __restrict__ b2,
+                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, int M, int hidden, float eps) {
+  using Cfg = MlpCfg;
+  constexpr int kSlots = Cfg::kSlots;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                  // h tile; residual boxes during the epilogue
+  uint8_t* sW = sA + Cfg::A_BYTES;                     // weight ring
+  uint8_t* sOut = sW + kSlots * Cfg::SLOT_BYTES;       // pass-2 staging
+  float* sB1 = reinterpret_cast<float*>(sOut + Cfg::OUT_BYTES);
+  float* sBias = sB1 + hidden;
+  float* sG = sBias + LN_N;
+  float* sBt = sG + LN_N;
+  float4* sPart = reinterpret_cast<float4*>(sBt + LN_N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPart) + Cfg::PART_BYTES);
+  uint64_t* w_full = bars;                    // [kSlots] leader CTA: both CTAs' TMA bytes land here
+  uint64_t* w_empty = w_full + kSlots;        // [kSlots] per CTA, released by the leader's multicast commit
+  uint64_t* a_full = w_empty + kSlots;        // leader CTA: h tile of both CTAs landed
+  uint64_t* a_free = a_full + 1;              // per CTA: the 8 local epilogue warps are done with the residual boxes
+  uint64_t* s_full = a_free + 1;              // [2] per CTA (multicast commit): S_c complete
+  uint64_t* p_full = s_full + 2;              // [2] leader CTA: the GELU warps of BOTH CTAs have written P_c
+  uint64_t* g1_done = p_full + 2;             // per CTA (multicast commit): fc1 of the tile's last chunk has read the h tile
+  uint64_t* tfull = g1_done + 1;              // per CTA (multicast commit): O complete
+  uint64_t* tempty = tfull + 1;               // leader CTA: epilogue warps of BOTH CTAs have drained O
+  uint64_t* xfull = tempty + 1;               // [8 warps][2 boxes]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfull + 2 * Cfg::kEpiWarps);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1);
+  const int num_pairs = (int)(gridDim.x >> 1);
+  const int num_tiles = (M + 2 * BM - 1) / (2 * BM);
+  const int n_chunks = hidden / HC;
+  const int my_tiles = pair < num_tiles ? (num_tiles - pair + num_pairs - 1) / num_pairs : 0;
+
+  for (int i = threadIdx.x; i < hidden; i += Cfg::kThreads) sB1[i] = b1[i];
+  for (int i = threadIdx.x; i < LN_N; i += Cfg::kThreads) {
+    sBias[i] = b2[i];
+    sG[i] = ln_w[i];
+    sBt[i] = ln_b[i];
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmH);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&w_full[s], 1);
+      mbar_init(&w_empty[s], 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_free, Cfg::kEpiWarps);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 2 * Cfg::kEpiWarps);
+    }
+    mbar_init(g1_done, 1);
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 2 * Cfg::kEpiWarps);
+    for (int i = 0; i < 2 * Cfg::kEpiWarps; ++i) mbar_init(&xfull[i], 1);
+    fence_mbar_init();
+  } else if (warp == 2) {
+    tmem_alloc_2cta(tmem_holder, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_launch_dependents();
+  pdl_wait();           // the prologue above overlapped the previous kernel's tail; global memory only from here on
+
+  if (warp == 0) {
+    // ===================== weight producer (both CTAs): slots in the order the issuer consumes them ================
+    // step sequence of a tile: G1(0) G1(1) | G2(0) G1(2) | G2(1) G1(3) | ... | G2(n-3) G1(n-1) | G2(n-2) G2(n-1);
+    // every step takes two slots (fc1: k-blocks 0-2 / 3-5 of this CTA's 32 rows; fc2: this CTA's 96 rows of each N half)
+    if (lane == 0) {
+      uint32_t slot = 0, phase = 0;
+      auto load_w1 = [&](int c) {
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&w_empty[slot], phase ^ 1, 10);
+          uint8_t* dst = sW + slot * Cfg::SLOT_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&w_full[slot], 2 * Cfg::SLOT_BYTES);
+          for (int j = 0; j < 3; ++j)
+            tma_load_2d_2cta(&tmW1, &w_full[slot], dst + j * Cfg::W1_KB_BYTES, (hf * 3 + j) * BK, c * HC + (int)rank * (HC / 2));
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+      };
+      auto load_w2 = [&](int c) {
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&w_empty[slot], phase ^ 1, 11);
+          uint8_t* dst = sW + slot * Cfg::SLOT_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&w_full[slot], 2 * Cfg::SLOT_BYTES);
+          tma_load_2d_2cta(&tmW2, &w_full[slot], dst, c * HC, hf * NH + (int)rank * (NH / 2));
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+      };
+      for (int t = 0; t < my_tiles; ++t) {
+        load_w1(0);
+        if (n_chunks > 1) load_w1(1);
+        for (int c = 0; c < n_chunks; ++c) {
+          load_w2(c);
+          if (c + 2 < n_chunks) load_w1(c + 2);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== h-tile producer (both CTAs): own 128 rows, all six k-blocks =====================
+    if (lane == 0) {
+      for (int t = 0; t < my_tiles; ++t) {
+        const int tile = pair + t * num_pairs;
+        mbar_wait(a_free, (uint32_t)(t & 1) ^ 1u, 12);     // the previous tile's residual boxes are done with the region
+        if (rank == 0) mbar_arrive_expect_tx(a_full, 2 * Cfg::A_BYTES);
+        for (int kb = 0; kb < KB1; ++kb)
+          tma_load_2d_2cta(&tmA, a_full, sA + kb * Cfg::A_KB_BYTES, kb * BK, tile * 2 * BM + (int)rank * BM);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only; warp-uniform, tcgen05 on one elected lane) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_f16(2 * BM, HC);
+      constexpr uint32_t idesc2 = umma_idesc_f16(2 * BM, NH);
+      const uint32_t lo_a0 = umma_desc_sw128_lo(smem_u32(sA));
+      const uint32_t lo_w0 = umma_desc_sw128_lo(smem_u32(sW));
+      uint32_t slot = 0, phase = 0;
+      uint32_t pfull_ph = 0;                               // bit b: parity of the next p_full[b] phase
+      auto g1 = [&](int c, bool last) {                    // S[c & 1] = h W1_c^T
+        const uint32_t d_tmem = tmem_base + kColS + (uint32_t)(c & 1) * HC;
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&w_full[slot], phase, 21);
+          tc_fence_after();
+          const uint32_t lo_w = lo_w0 + slot * (Cfg::SLOT_BYTES >> 4);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              const uint32_t lo_a = lo_a0 + (uint32_t)(hf * 3 + j) * (Cfg::A_KB_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_f16_2cta(d_tmem, umma_desc_pack(lo_a + 2 * k, kUmmaDescSw128Hi),
+                               umma_desc_pack(lo_w + j * (Cfg::W1_KB_BYTES >> 4) + 2 * k, kUmmaDescSw128Hi), idesc1,
+                               (hf | j | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta(&w_empty[slot]);
+          }
+          __syncwarp();
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+        if (elect_one_sync()) {
+          umma_commit_2cta(&s_full[c & 1]);
+          if (last) umma_commit_2cta(g1_done);
+        }
+        __syncwarp();
+      };
+      auto g2 = [&](int c, bool last) {                    // O += P_c W2_c^T, P_c from TMEM
+        const int b = c & 1;
+        mbar_wait(&p_full[b], (pfull_ph >> b) & 1u, 22);
+        pfull_ph ^= 1u << b;
+        tc_fence_after();
+        // P_c: logical packed columns 0..15 at S + 0 (GELU warps of column half 0), 16..31 at S + 32 (half 1)
+        const uint32_t a_tmem = tmem_base + kColS + (uint32_t)b * HC;
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&w_full[slot], phase, 23);
+          tc_fence_after();
+          const uint32_t lo_w = lo_w0 + slot * (Cfg::SLOT_BYTES >> 4);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < HC / 16; ++k)
+              umma_f16_ts_2cta(tmem_base + hf * NH, a_tmem + (k < 2 ? 8 * k : 16 + 8 * k),
+                                umma_desc_pack(lo_w + 2 * k, kUmmaDescSw128Hi), idesc2, (c | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&w_empty[slot]);
+          }
+          __syncwarp();
+          if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        }
+        if (last) {
+          if (elect_one_sync()) umma_commit_2cta(tfull);
+          __syncwarp();
+        }
+      };
+      for (int t = 0; t < my_tiles; ++t) {
+        mbar_wait(a_full, (uint32_t)(t & 1), 20);
+        tc_fence_after();
+        g1(0, n_chunks == 1);
+        if (n_chunks > 1) g1(1, n_chunks == 2);
+        for (int c = 0; c < n_chunks; ++c) {
+          if (c == 0) {                                    // the previous tile's epilogue has drained O
+            mbar_wait(tempty, (uint32_t)(t & 1) ^ 1u, 24);
+            tc_fence_after();
+          }
+          g2(c, c == n_chunks - 1);
+          if (c + 2 < n_chunks) g1(c + 2, c + 3 == n_chunks);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== GELU of the hidden chunks, then the full-row epilogue (both CTAs, own 128 rows) ==========
+    const int ew = warp - 4;
+    const int q = warp & 3;       // TMEM lane quarter: rows q*32 .. q*32+31 of this CTA's 128
+    const int c = ew >> 2;        // column half (of a hidden chunk: 32 of 64; of the output row: 192 of 384)
+    uint8_t* xbox = sA + ew * 3 * Cfg::XBOX;             // two in-boxes, then the out-box
+    uint8_t* obox = xbox + 2 * Cfg::XBOX;
+    uint8_t* hbox = sOut + ew * 4096;
+    uint64_t* my_xfull = xfull + ew * 2;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t tlane = tmem_base + lane_off + c * NH;
+    const uint32_t tS = tmem_base + lane_off + kColS + c * 32;
+    const int sw = lane & 7;
+    uint32_t sfull_ph = 0;        // bit b: parity of the next s_full[b] phase
+    int g = 0;                    // residual boxes issued / consumed so far (2-deep per warp)
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = pair + t * num_pairs;
+      const int row0 = tile * 2 * BM + (int)rank * BM + q * 32;
+      // ---- GELU: P_c = gelu(S_c + b1) as packed fp16 pairs over the first half of this warp's 32 S columns ----
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        const int b = ch & 1;
+        mbar_wait(&s_full[b], (sfull_ph >> b) & 1u, 32);
+        sfull_ph ^= 1u << b;
+        tc_fence_after();
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tS + b * HC, acc);
+        tmem_ld_wait();
+        const float* bp = sB1 + ch * HC + c * 32;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * i);
+          const float v0 = gelu_fast(__uint_as_float(acc[4 * i + 0]) + b4.x);
+          const float v1 = gelu_fast(__uint_as_float(acc[4 * i + 1]) + b4.y);
+          const float v2 = gelu_fast(__uint_as_float(acc[4 * i + 2]) + b4.z);
+          const float v3 = gelu_fast(__uint_as_float(acc[4 * i + 3]) + b4.w);
+          pk[2 * i] = pack_act(v0, v1);
+          pk[2 * i + 1] = pack_act(v2, v3);
+        }
+        tmem_st_32x32b_x16(tS + b * HC, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&p_full[b]);
+      }
+      // ---- the h tile is dead once fc1 of the last chunk has completed: its region now takes the residual boxes ----
+      auto issue_x = [&](int j, int gg) {   // lane 0 only: 32 x 32 fp32 box j of this warp's half row
+        mbar_arrive_expect_tx(&my_xfull[gg & 1], Cfg::XBOX);
+        tma_load_2d(&tmX, &my_xfull[gg & 1], xbox + (gg & 1) * Cfg::XBOX, c * NH + j * 32, row0);
+      };
+      if (lane == 0) {
+        mbar_wait(g1_done, (uint32_t)(t & 1), 33);
+        issue_x(0, g);
+        issue_x(1, g + 1);
+      }
+      mbar_wait(tfull, (uint32_t)(t & 1), 30);
+      tc_fence_after();
+      // ---- pass 1: v = acc + b2 + x; park v in TMEM, write it back to the residual stream, shifted statistics ----
+      float s = 0.f, ss = 0.f, c0 = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < CHUNKS; ++j, ++g) {
+        const int col0 = c * NH + j * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tlane + j * 32, acc);
+        tmem_ld_wait();
+        mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
+        const uint8_t* rowp = xbox + (g & 1) * Cfg::XBOX + lane * 128;
+        if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the out-box
+        __syncwarp();
+        uint8_t* outp = obox + lane * 128;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 xv = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
+          const float4 b4 = *reinterpret_cast<const float4*>(sBias + col0 + 4 * i);
+          float4 v;
+          v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
+          v.y = __uint_as_float(acc[4 * i + 1]) + b4.y + xv.y;
+          v.z = __uint_as_float(acc[4 * i + 2]) + b4.z + xv.z;
+          v.w = __uint_as_float(acc[4 * i + 3]) + b4.w + xv.w;
+          if (j == 0 && i == 0) c0 = v.x;
+          const float d0 = v.x - c0, d1 = v.y - c0, d2 = v.z - c0, d3 = v.w - c0;
+          s += (d0 + d1) + (d2 + d3);
+          ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
+          *reinterpret_cast<float4*>(outp + ((i ^ sw) << 4)) = v;
+          acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
+          acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
+        }
+        tmem_st_32x32b_x32(tlane + j * 32, acc);
+        fence_proxy_async_smem();
+        __syncwarp();                             // every lane has read the in-box and written the out-box
+        if (lane == 0) {
+          if (j + 2 < CHUNKS) issue_x(j + 2, g + 2);   // refill the in-box right away (boxes never cross a tile here)
+          tma_store_2d(&tmX, obox, col0, row0);
+          tma_store_commit();
+        }
+      }
+      tmem_st_wait();
+      // the residual boxes are done: once the last out-box store has been read, the h-tile producer may refill the region
+      if (lane == 0) {
+        tma_store_wait_read();
+        fence_proxy_async_smem();
+        mbar_arrive(a_free);
+      }
+      // ---- combine the two column halves of every row (Chan): n = 192 each ----
+      sPart[c * BM + q * 32 + lane] = make_float4(s, ss, c0, 0.f);
+      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+      const float4 o4 = sPart[(c ^ 1) * BM + q * 32 + lane];
+      const float inv_n = 1.f / NH;
+      const float mean_a = c0 + s * inv_n, m2_a = ss - s * s * inv_n;
+      const float mean_b = o4.z + o4.x * inv_n, m2_b = o4.y - o4.x * o4.x * inv_n;
+      const float dm = mean_b - mean_a;
+      const float mean = 0.5f * (mean_a + mean_b);
+      const float var = (m2_a + m2_b + dm * dm * (0.5f * NH)) * (1.f / LN_N);
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+      // ---- pass 2: normalise out of TMEM, fp16, 64-column slabs through the warp's staging box ----
+#pragma unroll 1
+      for (int jj = 0; jj < CHUNKS / 2; ++jj) {
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int j = jj * 2 + hh;
+          const int col0 = c * NH + j * 32;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tlane + j * 32, v);
+          tmem_ld_wait();
+          if (j == CHUNKS - 1) {
+            // last read of this tile's accumulator: hand O back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float y[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float ga = sG[col0 + 8 * i + e] * rstd;
+              y[e] = fmaf(__uint_as_float(v[8 * i + e]) - mean, ga, sBt[col0 + 8 * i + e]);
+            }
+            uint4 pk;
+            pk.x = pack_act(y[0], y[1]);
+            pk.y = pack_act(y[2], y[3]);
+            pk.z = pack_act(y[4], y[5]);
+            pk.w = pack_act(y[6], y[7]);
+            *reinterpret_cast<uint4*>(hbox + lane * 128 + (((hh * 4 + i) ^ sw) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmH, hbox, c * NH + jj * 64, row0);
+          tma_store_commit();
+        }
+      }
+      // the sPart exchange of the next tile must not overtake a slow partner still reading this tile's entry
+      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool mlp_resid_ln_supported(int M, int D, int hidden) {
+  return D == LN_N && hidden >= HC && hidden % HC == 0 && hidden <= 8192 && M >= 1;
+}
+
+int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_t* W2, const float* b2, float* x,
+                 const float* ln_w, const float* ln_b, act_t* h_out, int M, int D, int hidden, float eps,
+                 cudaStream_t stream) {
+  VITED_CHECK(mlp_resid_ln_supported(M, D, hidden), "mlp_resid_ln: unsupported shape M=%d D=%d hidden=%d", M, D, hidden);
+  VITED_CHECK(((reinterpret_cast<uintptr_t>(h_in) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
+                reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0,
+              "mlp_resid_ln: operands must be 16-byte aligned");
+  const int sms = gemm_num_sms();
+  VITED_CHECK(sms >= 2, "mlp_resid_ln: no device");
+  const uint32_t smem = MlpCfg::smem_bytes(hidden);
+  VITED_CHECK(smem <= 232448, "mlp_resid_ln: hidden=%d needs %u bytes of shared memory", hidden, smem);
+  static PerDeviceOnce once;
+  if (once.first())
+    VITED_CUDA_OK(cudaFuncSetAttribute(mlp_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  CUtensorMap tA, tW1, tW2, tX, tH;
+  if (make_tmap_act_2d(&tA, h_in, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, BM, 128)) return 1;
+  if (make_tmap_act_2d(&tW1, W1, (uint64_t)D, (uint64_t)hidden, (uint64_t)D * 2, 64, HC / 2, 128)) return 1;
+  if (make_tmap_act_2d(&tW2, W2, (uint64_t)hidden, (uint64_t)D, (uint64_t)hidden * 2, 64, NH / 2, 128)) return 1;
+  if (make_tmap_f32_2d(&tX, x, (uint64_t)D, (uint64_t)M, (uint64_t)D * 4, 32, 32, 128)) return 1;
+  if (make_tmap_act_2d(&tH, h_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, 32, 128)) return 1;
+  const int tiles = (M + 2 * BM - 1) / (2 * BM);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  VITED_CUDA_OK(launch_pdl(mlp_ln_pair_kernel, dim3(2 * pairs), dim3(MlpCfg::kThreads), smem, stream, tA, tW1, tW2, tX, tH,
+                           b1, b2, ln_w, ln_b, M, hidden, eps));
+  return 0;
+}
+
+}  // namespace vited

@@ -115,17 +115,23 @@ int retrieval_rows(const float* sim, const int* labels, int N, int* n_rel, doubl
                    int* hits100, cudaStream_t stream) {
   VITED_CHECK(sim && labels && n_rel && ap_sum && top1 && hits10 && hits100, "retrieval_rows: null pointer");
   VITED_CHECK(N >= 2 && N <= 49152, "retrieval_rows: N=%d out of range (2..49152: one row of keys lives in shared memory)", N);
+  const size_t smem = (size_t)N * sizeof(uint32_t);
+  static PerDeviceOnce once;   // the opt-in is raised once per device to the largest row the kernel accepts
+  if (once.first())
+    VITED_CUDA_OK(cudaFuncSetAttribute(retrieval_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 49152 * 4));
   int* d_overflow = nullptr;
   VITED_CUDA_OK(cudaMallocAsync(&d_overflow, sizeof(int), stream));
-  VITED_CUDA_OK(cudaMemsetAsync(d_overflow, 0, sizeof(int), stream));
-  const size_t smem = (size_t)N * sizeof(uint32_t);
-  VITED_CUDA_OK(cudaFuncSetAttribute(retrieval_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  retrieval_rows_kernel<<<N, kThreads, smem, stream>>>(sim, labels, N, n_rel, ap_sum, top1, hits10, hits100, d_overflow);
-  VITED_CUDA_OK(cudaGetLastError());
   int overflow = 0;
-  VITED_CUDA_OK(cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  VITED_CUDA_OK(cudaStreamSynchronize(stream));
-  VITED_CUDA_OK(cudaFreeAsync(d_overflow, stream));
+  // every path below frees d_overflow (stream ordered) before it returns
+  cudaError_t ce = cudaMemsetAsync(d_overflow, 0, sizeof(int), stream);
+  if (ce == cudaSuccess) {
+    retrieval_rows_kernel<<<N, kThreads, smem, stream>>>(sim, labels, N, n_rel, ap_sum, top1, hits10, hits100, d_overflow);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&overflow, d_overflow, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
+  cudaFreeAsync(d_overflow, stream);
+  VITED_CHECK(ce == cudaSuccess, "retrieval_rows: %s", cudaGetErrorString(ce));
   VITED_CHECK(overflow == 0, "retrieval_rows: a query has more than %d same-label items", kMaxRelevant);
   return 0;
 }

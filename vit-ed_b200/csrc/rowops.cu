@@ -104,9 +104,9 @@ __global__ void __launch_bounds__(256) resid_ln_kernel(ResidLnArgs a) {
       if (row < n_patch_rows) {
         const int s = (int)(row / a.n_patch);
         const int t = (int)(row % a.n_patch);
-        srow = (size_t)a.gather_idx[s] * a.n_patch + t;
+        srow = (size_t)(a.gather_idx[s] - a.gather_off) * a.n_patch + t;
       } else {
-        srow = (size_t)a.n_src_seq * a.n_patch + a.gather_idx[row - n_patch_rows];
+        srow = (size_t)a.n_src_seq * a.n_patch + (a.gather_idx[row - n_patch_rows] - a.gather_off);
       }
       src = a.gather_src + srow * D;
     }
@@ -163,9 +163,9 @@ __global__ void __launch_bounds__(256) resid_ln_generic_kernel(ResidLnArgs a) {
     if (a.gather_src != nullptr) {
       size_t srow;
       if (row < n_patch_rows) {
-        srow = (size_t)a.gather_idx[row / a.n_patch] * a.n_patch + (row % a.n_patch);
+        srow = (size_t)(a.gather_idx[row / a.n_patch] - a.gather_off) * a.n_patch + (row % a.n_patch);
       } else {
-        srow = (size_t)a.n_src_seq * a.n_patch + a.gather_idx[row - n_patch_rows];
+        srow = (size_t)a.n_src_seq * a.n_patch + (a.gather_idx[row - n_patch_rows] - a.gather_off);
       }
       src = a.gather_src + srow * D;
     }
@@ -273,6 +273,48 @@ int head_logits(const HeadArgs& a, cudaStream_t stream) {
   size_t blocks = ((size_t)a.P + 7) / 8;
   if (blocks > 148 * 32) blocks = 148 * 32;
   head_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  VITED_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pair lists of a block of grid rows, generated where they are consumed (no host vectors, no upload, no sync)
+// ------------------------------------------------------------------------------------------------------------
+size_t pair_list_count(int mode, int r0, int r1, int N) {
+  const size_t nr = (size_t)(r1 - r0);
+  if (mode == 0) return nr * (size_t)(N - 1);
+  if (mode == 1) return nr * (size_t)N - ((size_t)r1 * (r1 - 1) - (size_t)r0 * (r0 - 1)) / 2;
+  return nr;
+}
+
+__global__ void __launch_bounds__(256) pair_list_kernel(int mode, int r0, int r1, int N, int* __restrict__ ci,
+                                                        int* __restrict__ xj) {
+  for (int i = r0 + (int)blockIdx.x; i < r1; i += (int)gridDim.x) {
+    if (mode == 2) {
+      if (threadIdx.x == 0) { ci[i - r0] = i - r0; xj[i - r0] = i - r0; }
+      continue;
+    }
+    size_t off;
+    int j0, len;
+    if (mode == 0) {
+      off = (size_t)(i - r0) * (N - 1); j0 = 0; len = N - 1;
+    } else {
+      off = (size_t)(i - r0) * N - ((size_t)i * (i - 1) - (size_t)r0 * (r0 - 1)) / 2; j0 = i; len = N - i;
+    }
+    for (int t = threadIdx.x; t < len; t += blockDim.x) {
+      const int j = (mode == 0) ? t + (t >= i ? 1 : 0) : j0 + t;
+      ci[off + t] = i - r0;
+      xj[off + t] = j;
+    }
+  }
+}
+
+int pair_list(int mode, int r0, int r1, int N, int* ci, int* xj, cudaStream_t stream) {
+  VITED_CHECK(mode >= 0 && mode <= 2 && r0 >= 0 && r0 <= r1, "pair_list: bad arguments");
+  if (r1 == r0) return 0;
+  int blocks = r1 - r0;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pair_list_kernel<<<blocks, 256, 0, stream>>>(mode, r0, r1, N, ci, xj);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }

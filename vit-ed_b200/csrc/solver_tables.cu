@@ -35,12 +35,13 @@ __device__ __forceinline__ Two two_push(Two x, unsigned long long v) {
 // with IEEE division, then the fp32 subtraction. (No fast-math flags in this build.)
 __device__ __forceinline__ float one_minus_sigmoid(float x) { return 1.0f - 1.0f / (1.0f + expf(-x)); }
 
-// One CTA per row (i, s). Pass 1: distances (uint32 truncation of fp32 dist * 1000, :229) + the two smallest; pass 2:
+// One CTA per row (i, s). Pass 1: distances (uint32 truncation of dist * 1000, :229) + the two smallest; pass 2:
 // asymmetric compatibility in fp64 rounded to fp32 (:354-360), the number of pieces at the minimum and the lowest such j.
 __global__ void __launch_bounds__(kRowThreads) tables_rows_kernel(
-    const float* __restrict__ scores, int scores_are_logits, const int* __restrict__ order, int N,
+    const float* __restrict__ scores, int flags, const int* __restrict__ order, int N,
     uint32_t* __restrict__ asym, long long* __restrict__ min_d, long long* __restrict__ second_d,
     int* __restrict__ n_cand, int* __restrict__ cand, float* __restrict__ compat) {
+  const bool scores_are_logits = (flags & 1) != 0, f32_product = (flags & 2) != 0;
   const int row = blockIdx.x, i = row >> 2, s = row & 3, bin = (s + 3) & 3;
   const int oi = order != nullptr ? order[i] : i;
   const size_t base = (size_t)row * N;
@@ -57,7 +58,11 @@ __global__ void __launch_bounds__(kRowThreads) tables_rows_kernel(
       const int oj = order != nullptr ? order[j] : j;
       float v = scores[((size_t)oi * N + oj) * 4 + bin];
       if (scores_are_logits) v = one_minus_sigmoid(v);
-      dist = (uint32_t)__fmul_rn(v, 1000.0f);                      // fp32 product, truncating store
+      // evaluation.py:118-129 `pred[k] * 1000.`: np.float32 scalar times a Python float. Under the NumPy 1.x the
+      // reference's pinned stack runs on (torch~=2.1, scipy~=1.9.1) that promotes to float64; NumPy >= 2 (NEP 50)
+      // keeps float32. The products differ in the last place and the truncating uint32 store (:229) then differs by
+      // one whenever the fp32 rounding crosses an integer (~1e-5 of the entries). Default: the float64 product.
+      dist = f32_product ? (uint32_t)__fmul_rn(v, 1000.0f) : (uint32_t)__dmul_rn((double)v, 1000.0);
       t = two_push(t, dist);
     }
     asym[base + j] = dist;
@@ -133,13 +138,14 @@ __global__ void __launch_bounds__(kRowThreads) tables_mutual_kernel(
 
 }  // namespace
 
-int puzzle_tables(const float* scores, int scores_are_logits, const int* order, int N, uint32_t* asym, long long* min_d,
+int puzzle_tables(const float* scores, int flags, const int* order, int N, uint32_t* asym, long long* min_d,
                   long long* second_d, int* n_cand, int* cand, float* compat, float* mutual, int* best_buddy,
                   cudaStream_t stream) {
   VITED_CHECK(N >= 1 && N <= (1 << 20), "puzzle_tables: N=%d out of range", N);
   VITED_CHECK(scores && asym && min_d && second_d && n_cand && cand && compat && mutual && best_buddy,
               "puzzle_tables: null pointer");
-  tables_rows_kernel<<<4 * N, kRowThreads, 0, stream>>>(scores, scores_are_logits, order, N, asym, min_d, second_d,
+  VITED_CHECK((flags & ~3) == 0, "puzzle_tables: unknown flag bits 0x%x", flags);
+  tables_rows_kernel<<<4 * N, kRowThreads, 0, stream>>>(scores, flags, order, N, asym, min_d, second_d,
                                                         n_cand, cand, compat);
   VITED_CUDA_OK(cudaGetLastError());
   tables_mutual_kernel<<<4 * N, kRowThreads, 0, stream>>>(compat, n_cand, cand, N, mutual, best_buddy);

@@ -66,6 +66,20 @@ def equal_row_range(n_rows, world, rank):
     return lo, min(lo + per, n_rows)
 
 
+def puzzle_unit_ranges(n_pieces, world, rank):
+    """BASELINE configs[2] sharding: the (puzzle, row) units of a batch of puzzles -- every unit is one grid
+    row of N_p - 1 pairs -- are numbered puzzle-major and split into ``world`` contiguous equal shares. Returns rank's
+    share as [(puzzle, row_lo, row_hi), ...] (at most one segment per puzzle, puzzle ascending)."""
+    starts = np.concatenate([[0], np.cumsum(np.asarray(n_pieces, dtype=np.int64))])
+    lo, hi = equal_row_range(int(starts[-1]), world, rank)
+    out = []
+    for p in range(len(n_pieces)):
+        a, b = max(lo, int(starts[p])), min(hi, int(starts[p + 1]))
+        if a < b:
+            out.append((p, a - int(starts[p]), b - int(starts[p])))
+    return out
+
+
 # --------------------------------------------------------------------------------------------- collectives
 def _all_gather_rows(block, ranges, n_rows):
     """all-gather variable-height row blocks -> [n_rows, ...] on every rank (pads to the tallest block)."""
@@ -102,6 +116,62 @@ def score_puzzle(model, images, gather=True):
     if world == 1 or not gather:
         return block
     return _all_gather_rows(block, ranges, n)
+
+
+@torch.no_grad()
+def score_puzzles(model, puzzles, n_pieces=None, gather=True, blocks_out=None):
+    """A batch of puzzles, each scored all-pairs, the (puzzle, row) units sharded over the ranks (``puzzle_unit_ranges``)
+    with no data-path collective and ONE all-gather of the score blocks at the end. Replaces the per-puzzle loop of
+    evaluation.py:82-114 for a whole evaluation set.
+
+    puzzles[p]: CUDA tensor [N_p, 3, S, S] of puzzle p's pieces, or a zero-argument callable returning it (called only
+    on the ranks that own rows of puzzle p; ``n_pieces`` must then list every N_p). Returns a list with one
+    [N_p, N_p, C] fp32 logits tensor per puzzle (diagonals zero); with ``gather=False`` (or a single rank's share)
+    entries of puzzles this rank owns no rows of are None and partially owned puzzles hold the owned rows only,
+    as ``(row_lo, row_hi, block)``."""
+    rank, world = _dist_info()
+    if n_pieces is None:
+        n_pieces = [int(p.shape[0]) for p in puzzles]
+    mine = puzzle_unit_ranges(n_pieces, world, rank)
+    n_classes = model.num_classes
+    owned = {p: (puzzles[p]() if callable(puzzles[p]) else puzzles[p]) for p, _, _ in mine}
+    dev = next(iter(owned.values())).device if owned else next(model.parameters()).device
+    # this rank's blocks, back to back in one flat buffer (what the all-gather moves)
+    sizes = [(hi - lo) * n_pieces[p] * n_classes for p, lo, hi in mine]
+    flat_len = [sum((hi - lo) * n_pieces[p] * n_classes for p, lo, hi in puzzle_unit_ranges(n_pieces, world, r))
+                for r in range(world)]
+    longest = max(flat_len) if flat_len else 0
+    flat = blocks_out if blocks_out is not None else torch.zeros(longest, dtype=torch.float32, device=dev)
+    if flat.numel() < longest or flat.dtype != torch.float32 or flat.device != dev:
+        raise _lib.VitedError(f'score_puzzles: blocks_out must be a fp32 buffer of at least {longest} elements on {dev}')
+    off = 0
+    for (p, lo, hi), size in zip(mine, sizes):
+        images = owned[p]
+        if images.shape[0] != n_pieces[p]:
+            raise _lib.VitedError(f'score_puzzles: puzzle {p} has {images.shape[0]} pieces, n_pieces says {n_pieces[p]}')
+        block = flat[off:off + size].view(hi - lo, n_pieces[p], n_classes)
+        block.zero_()                      # the diagonal is never written
+        model.score_grid(images, _lib.GRID_ORDERED_OFFDIAG, lo, hi, out=block)
+        off += size
+    if world == 1 or not gather:
+        out, off = [None] * len(n_pieces), 0
+        for (p, lo, hi), size in zip(mine, sizes):
+            block = flat[off:off + size].view(hi - lo, n_pieces[p], n_classes)
+            out[p] = block if (lo, hi) == (0, n_pieces[p]) else (lo, hi, block)
+            off += size
+        return out
+    import torch.distributed as dist
+    gathered = torch.empty(world * longest, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, flat[:longest])     # NCCL: one ncclAllGather over NVLink
+    gathered = gathered.view(world, longest)
+    out = [torch.zeros((n, n, n_classes), dtype=torch.float32, device=dev) for n in n_pieces]
+    for r in range(world):
+        off = 0
+        for p, lo, hi in puzzle_unit_ranges(n_pieces, world, r):
+            size = (hi - lo) * n_pieces[p] * n_classes
+            out[p][lo:hi] = gathered[r, off:off + size].view(hi - lo, n_pieces[p], n_classes)
+            off += size
+    return out
 
 
 @torch.no_grad()

@@ -227,7 +227,7 @@ class VisionTransformerCustom(nn.Module):
         return self._engine
 
     def _upload_weights(self):
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        stream = self._stream(torch.device('cuda', self._engine_device))
         sd = self.state_dict()
         n_expected = _lib.lib.vited_num_weights_expected(self._engine)
         expected = [_lib.lib.vited_weight_name(self._engine, i).decode() for i in range(n_expected)]
@@ -264,14 +264,17 @@ class VisionTransformerCustom(nn.Module):
         import json
         if self._engine is None:
             return {}
-        return json.loads(_lib.lib.vited_profile_json(self._engine, self._stream()).decode())
+        return json.loads(_lib.lib.vited_profile_json(
+            self._engine, self._stream(torch.device('cuda', self._engine_device))).decode())
 
     def launch_count(self):
         return int(_lib.lib.vited_launch_count(self._engine)) if self._engine is not None else 0
 
     @staticmethod
-    def _stream():
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    def _stream(device):
+        """The caller's current stream ON THE TENSORS' DEVICE (not on torch's current device, which may be another
+        GPU); the C entry points make that device current for their own duration and restore the caller's."""
+        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
     @staticmethod
     def _prep(t):
@@ -289,7 +292,7 @@ class VisionTransformerCustom(nn.Module):
         eng = self._ensure_engine(x1.device)
         out = torch.empty((x1.shape[0], self.patch_embed.num_patches, self.embed_dim), dtype=torch.float32,
                           device=x1.device)
-        _lib.check(_lib.lib.vited_encode(eng, x1.data_ptr(), x1.shape[0], out.data_ptr(), self._stream()),
+        _lib.check(_lib.lib.vited_encode(eng, x1.data_ptr(), x1.shape[0], out.data_ptr(), self._stream(x1.device)),
                    'vited_encode')
         return out
 
@@ -307,8 +310,10 @@ class VisionTransformerCustom(nn.Module):
                 raise ValueError(f'expected context tokens [{x2.shape[0]}, {n_e}, {self.embed_dim}], got {tuple(x.shape)}')
             eng = self._ensure_engine(x2.device)
             out = torch.empty((x2.shape[0], self.num_classes), dtype=torch.float32, device=x2.device)
+            if x.device != x2.device:
+                raise _lib.VitedError(f'context tokens are on {x.device}, images on {x2.device}')
             _lib.check(_lib.lib.vited_decode(eng, x.data_ptr(), x2.data_ptr(), x2.shape[0], out.data_ptr(),
-                                             self._stream()), 'vited_decode')
+                                             self._stream(x2.device)), 'vited_decode')
             return out
         x = self._prep(x)
         if x.dim() != 5 or x.shape[1] != 2:
@@ -316,7 +321,7 @@ class VisionTransformerCustom(nn.Module):
         self._check_images(x[:, 0])
         eng = self._ensure_engine(x.device)
         out = torch.empty((x.shape[0], self.num_classes), dtype=torch.float32, device=x.device)
-        _lib.check(_lib.lib.vited_forward_pairs(eng, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream()),
+        _lib.check(_lib.lib.vited_forward_pairs(eng, x.data_ptr(), x.shape[0], out.data_ptr(), self._stream(x.device)),
                    'vited_forward_pairs')
         return out
 
@@ -340,7 +345,7 @@ class VisionTransformerCustom(nn.Module):
         if out is None:
             out = torch.zeros((row_end - row_begin, n, self.num_classes), dtype=torch.float32, device=images.device)
         _lib.check(_lib.lib.vited_score_grid(eng, images.data_ptr(), n, int(mode), int(row_begin), int(row_end),
-                                             out.data_ptr(), self._stream()), 'vited_score_grid')
+                                             out.data_ptr(), self._stream(images.device)), 'vited_score_grid')
         return out
 
 

@@ -33,10 +33,17 @@ class PuzzleTables:
     start_piece_ordering: list = field(default_factory=list)   # [(piece, numb_bb_neighbors, total_compatibility)]
 
 
-def build_tables(scores, order=None, scores_are_logits=True):
+def build_tables(scores, order=None, scores_are_logits=True, scalar_rules='numpy1'):
     """scores: CUDA fp32 tensor [N, N, 4] indexed by origin piece id -- the logits of ``grid.score_puzzle``
     (``scores_are_logits=True``: 1 - sigmoid is applied on the device, evaluation.py:109-114) or distances.
-    order[k]: origin id of the piece at list position k (evaluation.py:87 shuffles), None = identity."""
+    order[k]: origin id of the piece at list position k (evaluation.py:87 shuffles), None = identity.
+    scalar_rules: how the closure's ``pred[k] * 1000.`` (np.float32 scalar x Python float) is evaluated --
+    'numpy1' (default): float64, as under the NumPy 1.x the reference's pinned requirements run on; 'numpy2': float32
+    (NEP 50), what the same reference code computes when run under NumPy >= 2. The truncated uint32 distances differ
+    by one on ~1e-5 of the entries."""
+    if scalar_rules not in ('numpy1', 'numpy2'):
+        raise _lib.VitedError(f"build_tables: scalar_rules must be 'numpy1' or 'numpy2', got {scalar_rules!r}")
+    flags = (1 if scores_are_logits else 0) | (2 if scalar_rules == 'numpy2' else 0)
     if not (isinstance(scores, torch.Tensor) and scores.is_cuda):
         raise _lib.VitedError('build_tables: scores must be a CUDA tensor (there is no CPU path)')
     if scores.dtype != torch.float32 or scores.dim() != 3 or scores.shape[0] != scores.shape[1] or scores.shape[2] != 4:
@@ -61,7 +68,7 @@ def build_tables(scores, order=None, scores_are_logits=True):
         bb = torch.empty((n, 4), dtype=torch.int32, device=dev)
         p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _lib.check(_lib.lib.vited_puzzle_tables(p(scores), 1 if scores_are_logits else 0, p(order_t), n, p(asym), p(min_d),
+        _lib.check(_lib.lib.vited_puzzle_tables(p(scores), flags, p(order_t), n, p(asym), p(min_d),
                                                 p(second_d), p(n_cand), p(cand), p(compat), p(mutual), p(bb), stream),
                    'vited_puzzle_tables')
         tables = PuzzleTables(
