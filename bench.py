@@ -372,9 +372,12 @@ def run_ours(args):
     # is filled from the committed ncu --set full capture of the SAME kernels at the SAME per-launch shape
     # (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the raw page) when this run's algorithmic bytes
     # per launch match the capture's to 2 %, and is null otherwise.
+    #   mlp_ln  : mlp_ln_pair_kernel (fc1 + GELU + fc2 + residual + LayerNorm, hidden activations in TMEM): tensor bound
     fams = {
-        'gemm_ln': dict(match=lambda k: k.startswith('gemm_ln_') or k.startswith('mlp_ln'), bound='hbm',
-                        kernel='gemm_ln_pair_kernel / mlp_ln_pair_kernel (tcgen05 Linear [+ GELU + Linear] + residual + LayerNorm, full-row epilogue out of TMEM)'),
+        'mlp_ln': dict(match=lambda k: k.startswith('mlp_ln'), bound='tensor',
+                       kernel='mlp_ln_pair_kernel (tcgen05 fc1 -> GELU -> fc2 with the hidden chunk handed over in TMEM, + residual + LayerNorm full-row epilogue)'),
+        'gemm_ln': dict(match=lambda k: k.startswith('gemm_ln_'), bound='hbm',
+                        kernel='gemm_ln_pair_kernel (tcgen05 Linear + residual + LayerNorm, full-row epilogue out of TMEM)'),
         'gemm': dict(match=lambda k: k.startswith('gemm_n'), bound='tensor',
                      kernel='gemm_tc_pair_kernel (tcgen05/TMEM/TMA cta_group::2 GEMM, bias / GELU epilogue)'),
         'attn': dict(match=lambda k: k in ('attn_self', 'attn_cross'), bound='hbm',

@@ -8,4 +8,4 @@ set -euo pipefail
 cd "$(dirname "$0")/.."
 VITED_OUT_DIR=$PWD/tools/bin/bf16 VITED_EXTRA_FLAGS="-DVITED_ACT_BF16=1" bash vit-ed_b200/csrc/build.sh
 VITED_OUT_DIR=$PWD/tools/bin/jitter VITED_EXTRA_FLAGS="-DVITED_JITTER" bash vit-ed_b200/csrc/build.sh
-VITED_OUT_DIR=$PWD/tools/bin/trace VITED_EXTRA_FLAGS="-DVITED_LN_TRACE -DVITED_ATTN_TRACE" bash vit-ed_b200/csrc/build.sh
+VITED_OUT_DIR=$PWD/tools/bin/trace VITED_EXTRA_FLAGS="-DVITED_LN_TRACE -DVITED_ATTN_TRACE -DVITED_MLP_TRACE" bash vit-ed_b200/csrc/build.sh

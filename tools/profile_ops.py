@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from vited_b200 import _lib as L  # noqa: E402
 
-M = 4032 * 65
+M = int(os.environ.get('ROWS', 4032 * 65))
 D = 384
 torch.manual_seed(0)
 reps = int(os.environ.get('REPS', '2'))
@@ -47,6 +47,22 @@ def gemm_ln(K):
 
 gemm_ln(384)
 gemm_ln(1536)
+
+
+def mlp_ln():
+    hin = torch.randn(M, 384, device='cuda').to(L.act_dtype())
+    W1 = (torch.randn(1536, 384, device='cuda') / math.sqrt(384)).to(L.act_dtype())
+    W2 = (torch.randn(384, 1536, device='cuda') / math.sqrt(1536)).to(L.act_dtype())
+    b1 = torch.randn(1536, device='cuda'); b2 = torch.randn(384, device='cuda')
+    xx = torch.randn(M, 384, device='cuda')
+    lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
+    for _ in range(reps):
+        L.check(L.lib.vited_op_mlp_resid_ln(hin.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(), xx.data_ptr(),
+                                            lw.data_ptr(), lb.data_ptr(), hin.data_ptr(), M, 384, 1536, 1e-6, None), 'mlp_ln')
+    torch.cuda.synchronize()
+
+
+mlp_ln()
 P, H, hd, Np = 4032, 12, 32, 64
 qkv = torch.randn(M, 3 * D, device='cuda').to(L.act_dtype())
 o = torch.empty(M, D, dtype=L.act_dtype(), device='cuda')

@@ -52,8 +52,13 @@ struct P64Maps {
 };
 
 __global__ void __launch_bounds__(P64::THREADS, 1)
-attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, int cls_only) {
+attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, int mode) {
   using C = P64;
+  const int cls_only = mode & 1;
+  // mode bit 1 -- MEASUREMENT ONLY (VITED_P64_KV_ONCE=1, results are wrong): K/V tiles are fetched only the first time
+  // a ring slot is used, every later unit reuses whatever the slot holds. The launch then moves Q and O only: the
+  // upper bound of what a design that keeps a context piece's K/V resident in shared memory could gain.
+  const bool kv_once = (mode & 2) != 0;
   extern __shared__ uint8_t attn_tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NS * C::STAGE);
@@ -114,13 +119,17 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
         mbar_wait(&empty[s], ph ^ 1, 50);
         uint8_t* st = smem + s * C::STAGE;
         // cls_only (last decoder layer, only the class-token row reaches the head): the 64 patch queries are not loaded
-        const uint32_t bytes = (cls_only ? 2 : 3) * 64 * C::RB + (a.q_has_cls ? C::RB : 0) + (a.k_has_cls ? 2 * C::RB : 0);
+        const bool load_kv = !kv_once || i < C::NS;
+        const uint32_t bytes = ((cls_only ? 0 : 1) + (load_kv ? 2 : 0)) * 64 * C::RB + (a.q_has_cls ? C::RB : 0) +
+                               (a.k_has_cls && load_kv ? 2 * C::RB : 0);
         mbar_arrive_expect_tx(&full[s], bytes);
         if (!cls_only) tma_load_2d(&maps.q_tile, &full[s], st, col, b * 64);
         if (a.q_has_cls) tma_load_2d(&maps.q_row, &full[s], st + 64 * C::RB, col, a.n_seq * 64 + b);
-        tma_load_2d(&maps.k_tile, &full[s], st + C::TB, col, kvb * 64);
-        tma_load_2d(&maps.v_tile, &full[s], st + 2 * C::TB, col, kvb * 64);
-        if (a.k_has_cls) {
+        if (load_kv) {
+          tma_load_2d(&maps.k_tile, &full[s], st + C::TB, col, kvb * 64);
+          tma_load_2d(&maps.v_tile, &full[s], st + 2 * C::TB, col, kvb * 64);
+        }
+        if (a.k_has_cls && load_kv) {
           tma_load_2d(&maps.k_row, &full[s], st + C::TB + 64 * C::RB, col, a.n_kv_seq * 64 + kvb);
           tma_load_2d(&maps.v_row, &full[s], st + 2 * C::TB + 64 * C::RB, col, a.n_kv_seq * 64 + kvb);
         }
@@ -712,7 +721,9 @@ static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream
   if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 64, 64)) return 1;
   if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 32, 1, 64)) return 1;
   const unsigned grid = (unsigned)(units < (size_t)sms ? units : (size_t)sms);
-  VITED_CUDA_OK(launch_pdl(attn_p64_kernel, dim3(grid), dim3(P64::THREADS), P64::BYTES, stream, a, maps, (int)units, cls_only));
+  static const int kv_once = [] { const char* v = getenv("VITED_P64_KV_ONCE"); return v ? atoi(v) : 0; }();
+  VITED_CUDA_OK(launch_pdl(attn_p64_kernel, dim3(grid), dim3(P64::THREADS), P64::BYTES, stream, a, maps, (int)units,
+                           cls_only | (kv_once ? 2 : 0)));
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }

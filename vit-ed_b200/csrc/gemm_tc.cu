@@ -47,68 +47,72 @@ int gemm_num_sms() {
   return device_sm_count();
 }
 
-// 2-D fp16 tensor map: inner dim = cols (contiguous), outer dim = rows, 128B swizzle, box = 64 cols x box_rows.
-static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
-                     uint32_t box_rows) {
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {64, box_rows};
+// Every launch needs 3-6 tensor maps and a step makes ~7,500 launches over a handful of buffers and shapes that repeat
+// chunk after chunk: encoded maps are kept in a small direct-mapped cache keyed by everything that goes into the
+// encoding (a CUtensorMap is a pure function of these values, so a hit is always valid, also after the buffer was
+// freed and another one allocated at the same address).
+struct TmapKey {
+  const void* ptr; uint64_t cols, rows, stride; uint32_t box_cols, box_rows; int32_t swizzle, dtype, promo;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && cols == o.cols && rows == o.rows && stride == o.stride && box_cols == o.box_cols &&
+           box_rows == o.box_rows && swizzle == o.swizzle && dtype == o.dtype && promo == o.promo;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+constexpr int kTmapCacheSize = 1024;
+static TmapSlot g_tmap_cache[kTmapCacheSize];
+static std::mutex g_tmap_mutex;
+
+static int encode_cached(CUtensorMap* tm, const TmapKey& k) {
+  uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= (k.cols * 0x100000001B3ull) ^ (k.rows * 0xC2B2AE3D27D4EB4Full) ^ (k.stride << 7) ^ ((uint64_t)k.box_cols << 40) ^
+       ((uint64_t)k.box_rows << 48) ^ ((uint64_t)(k.swizzle * 4 + k.dtype * 2 + k.promo) << 56);
+  h ^= h >> 29;
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  TmapSlot& sl = g_tmap_cache[h % kTmapCacheSize];
+  if (sl.valid && sl.key == k) { *tm = sl.map; return 0; }
+  cuuint64_t gdim[2] = {k.cols, k.rows};
+  cuuint64_t gstride[1] = {k.stride};
+  cuuint32_t box[2] = {k.box_cols, k.box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, VITED_ACT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  const CUtensorMapSwizzle sw = k.swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : k.swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUtensorMapDataType dt = k.dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : k.dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = g_encode(tm, dt, 2, const_cast<void*>(k.ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        k.promo ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p cols=%llu rows=%llu stride=%llu box_rows=%u", (int)r, ptr,
-              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_rows);
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p cols=%llu rows=%llu stride=%llu box=%ux%u swizzle=%d dtype=%d",
+              (int)r, k.ptr, (unsigned long long)k.cols, (unsigned long long)k.rows, (unsigned long long)k.stride,
+              k.box_cols, k.box_rows, k.swizzle, k.dtype);
     return 1;
   }
+  sl.key = k;
+  sl.map = *tm;
+  sl.valid = true;
   return 0;
 }
 
+// 2-D fp16 tensor map: inner dim = cols (contiguous), outer dim = rows, 128B swizzle, box = 64 cols x box_rows.
+static int make_tmap(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                     uint32_t box_rows) {
+  return encode_cached(tm, TmapKey{ptr, cols, rows, row_stride_bytes, 64, box_rows, 128, VITED_ACT_BF16, 1});
+}
 // generic 2-D fp16 tensor map for other kernels (attention): box = box_cols x box_rows, swizzle_bytes in {0, 64, 128}
 int make_tmap_act_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   std::call_once(g_once, init_driver_once);
   if (g_init_status) return 1;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = g_encode(tm, VITED_ACT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p cols=%llu rows=%llu stride=%llu box=%ux%u swizzle=%d", (int)r,
-              ptr, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_cols,
-              box_rows, swizzle_bytes);
-    return 1;
-  }
-  return 0;
+  return encode_cached(tm, TmapKey{ptr, cols, rows, row_stride_bytes, box_cols, box_rows, swizzle_bytes, VITED_ACT_BF16, 0});
 }
 
-// 2-D fp32 tensor map (residual stream tiles of the fused GEMM + residual + LayerNorm kernel, gemm_ln.cu)
+// 2-D fp32 tensor map (residual stream tiles of the fused GEMM + residual + LayerNorm kernels, gemm_ln.cu / mlp_ln.cu)
 int make_tmap_f32_2d(CUtensorMap* tm, const void* ptr, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   std::call_once(g_once, init_driver_once);
   if (g_init_status) return 1;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {row_stride_bytes};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(f32) failed (%d): ptr=%p cols=%llu rows=%llu stride=%llu box=%ux%u swizzle=%d", (int)r,
-              ptr, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)row_stride_bytes, box_cols,
-              box_rows, swizzle_bytes);
-    return 1;
-  }
-  return 0;
+  return encode_cached(tm, TmapKey{ptr, cols, rows, row_stride_bytes, box_cols, box_rows, swizzle_bytes, 2, 0});
 }
 
 constexpr int BM = 128;

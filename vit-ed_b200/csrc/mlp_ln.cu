@@ -16,7 +16,7 @@
 //     statistics, Chan combination of the two column halves, normalise, TMA stores) runs on the same eight warps. Its
 //     residual boxes live in the h-tile region, which is dead once fc1 of the last chunk has completed.
 // TMEM: O = columns [0, 384), S buffers [384, 448) and [448, 512). Shared memory: 96 KB h tile / residual boxes,
-// 72 KB weight ring, 32 KB output staging, biases / LayerNorm parameters.
+// 96 KB weight ring, 16 KB output staging, biases / LayerNorm parameters.
 #include "kernels.h"
 
 namespace vited {
@@ -37,10 +37,10 @@ struct MlpCfg {
   static constexpr uint32_t A_KB_BYTES = BM * BK * 2;                 // one k-block of the h tile: 128 rows x 128 B
   static constexpr uint32_t A_BYTES = KB1 * A_KB_BYTES;               // 96 KB
   static constexpr uint32_t SLOT_BYTES = 12288;                       // 3 k-blocks of W1 (32 rows each) or 96 rows of W2
-  static constexpr int kSlots = 6;
+  static constexpr int kSlots = 8;   // 6 slots left the issuer waiting for weights 11.6 k of 63 k cycles per tile (trace)
   static constexpr uint32_t W1_KB_BYTES = (HC / 2) * BK * 2;          // this CTA's 32 rows of one k-block: 4 KB
   static constexpr uint32_t XBOX = 32 * 32 * 4;                       // 32 rows x 32 fp32, 128B-swizzled
-  static constexpr uint32_t OUT_BYTES = kEpiWarps * 4096;             // pass-2 staging: 32 rows x 64 fp16 per warp
+  static constexpr uint32_t OUT_BYTES = kEpiWarps * 2048;             // pass-2 staging: 32 rows x 32 fp16 per warp (64B swizzle)
   static constexpr uint32_t PART_BYTES = 2 * BM * 16;
   static constexpr uint32_t BAR_BYTES = 512;
   static_assert(kEpiWarps * 3 * XBOX == A_BYTES, "the residual boxes (2 in + 1 out per warp) reuse the h-tile region");
@@ -50,6 +50,15 @@ struct MlpCfg {
 };
 
 constexpr uint32_t kColS = LN_N;   // first TMEM column of the two hidden-chunk buffers
+
+#ifdef VITED_MLP_TRACE   // clock64 trace of CTA 0 (tools/trace_mlp_ln.py); compiled out of the product library
+__device__ long long g_mlp_trace[2 * 32 * 8];   // [0 = GELU/epilogue warp (q0,c0), 1 = MMA warp][tile][event]
+#define TRM(who, t, ev, val) do { if (blockIdx.x == 0 && lane == 0 && (t) < 32) g_mlp_trace[((who) * 32 + (t)) * 8 + (ev)] = (val); } while (0)
+#define TRM_CLK() clock64()
+#else
+#define TRM(who, t, ev, val) do { } while (0)
+#define TRM_CLK() 0ll
+#endif
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MlpCfg::kThreads, 1)
 mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
@@ -184,10 +193,16 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint32_t lo_w0 = umma_desc_sw128_lo(smem_u32(sW));
       uint32_t slot = 0, phase = 0;
       uint32_t pfull_ph = 0;                               // bit b: parity of the next p_full[b] phase
+#ifdef VITED_MLP_TRACE
+      long long acc_wait_p = 0, acc_wait_w = 0;
+#define TRM_WAIT(accu, stmt) do { const long long _c0 = clock64(); stmt; accu += clock64() - _c0; } while (0)
+#else
+#define TRM_WAIT(accu, stmt) do { stmt; } while (0)
+#endif
       auto g1 = [&](int c, bool last) {                    // S[c & 1] = h W1_c^T
         const uint32_t d_tmem = tmem_base + kColS + (uint32_t)(c & 1) * HC;
         for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&w_full[slot], phase, 21);
+          TRM_WAIT(acc_wait_w, mbar_wait(&w_full[slot], phase, 21));
           tc_fence_after();
           const uint32_t lo_w = lo_w0 + slot * (Cfg::SLOT_BYTES >> 4);
           if (elect_one_sync()) {
@@ -213,13 +228,13 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       };
       auto g2 = [&](int c, bool last) {                    // O += P_c W2_c^T, P_c from TMEM
         const int b = c & 1;
-        mbar_wait(&p_full[b], (pfull_ph >> b) & 1u, 22);
+        TRM_WAIT(acc_wait_p, mbar_wait(&p_full[b], (pfull_ph >> b) & 1u, 22));
         pfull_ph ^= 1u << b;
         tc_fence_after();
         // P_c: logical packed columns 0..15 at S + 0 (GELU warps of column half 0), 16..31 at S + 32 (half 1)
         const uint32_t a_tmem = tmem_base + kColS + (uint32_t)b * HC;
         for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(&w_full[slot], phase, 23);
+          TRM_WAIT(acc_wait_w, mbar_wait(&w_full[slot], phase, 23));
           tc_fence_after();
           const uint32_t lo_w = lo_w0 + slot * (Cfg::SLOT_BYTES >> 4);
           if (elect_one_sync()) {
@@ -238,18 +253,27 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       };
       for (int t = 0; t < my_tiles; ++t) {
+        TRM(1, t, 0, TRM_CLK());
         mbar_wait(a_full, (uint32_t)(t & 1), 20);
+        TRM(1, t, 1, TRM_CLK());
         tc_fence_after();
         g1(0, n_chunks == 1);
         if (n_chunks > 1) g1(1, n_chunks == 2);
         for (int c = 0; c < n_chunks; ++c) {
           if (c == 0) {                                    // the previous tile's epilogue has drained O
+            TRM(1, t, 2, TRM_CLK());
             mbar_wait(tempty, (uint32_t)(t & 1) ^ 1u, 24);
+            TRM(1, t, 3, TRM_CLK());
             tc_fence_after();
           }
           g2(c, c == n_chunks - 1);
           if (c + 2 < n_chunks) g1(c + 2, c + 3 == n_chunks);
         }
+        TRM(1, t, 4, TRM_CLK());
+#ifdef VITED_MLP_TRACE
+        TRM(1, t, 5, acc_wait_p);
+        TRM(1, t, 6, acc_wait_w);
+#endif
       }
     }
   } else if (warp >= 4) {
@@ -259,7 +283,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int c = ew >> 2;        // column half (of a hidden chunk: 32 of 64; of the output row: 192 of 384)
     uint8_t* xbox = sA + ew * 3 * Cfg::XBOX;             // two in-boxes, then the out-box
     uint8_t* obox = xbox + 2 * Cfg::XBOX;
-    uint8_t* hbox = sOut + ew * 4096;
+    uint8_t* hbox = sOut + ew * 2048;
     uint64_t* my_xfull = xfull + ew * 2;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t tlane = tmem_base + lane_off + c * NH;
@@ -271,9 +295,13 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int tile = pair + t * num_pairs;
       const int row0 = tile * 2 * BM + (int)rank * BM + q * 32;
       // ---- GELU: P_c = gelu(S_c + b1) as packed fp16 pairs over the first half of this warp's 32 S columns ----
+#ifdef VITED_MLP_TRACE
+      long long acc_wait_s = 0;
+      if (ew == 0) TRM(0, t, 0, TRM_CLK());
+#endif
       for (int ch = 0; ch < n_chunks; ++ch) {
         const int b = ch & 1;
-        mbar_wait(&s_full[b], (sfull_ph >> b) & 1u, 32);
+        TRM_WAIT(acc_wait_s, mbar_wait(&s_full[b], (sfull_ph >> b) & 1u, 32));
         sfull_ph ^= 1u << b;
         tc_fence_after();
         uint32_t acc[32];
@@ -302,12 +330,16 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_arrive_expect_tx(&my_xfull[gg & 1], Cfg::XBOX);
         tma_load_2d(&tmX, &my_xfull[gg & 1], xbox + (gg & 1) * Cfg::XBOX, c * NH + j * 32, row0);
       };
+#ifdef VITED_MLP_TRACE
+      if (ew == 0) { TRM(0, t, 1, TRM_CLK()); TRM(0, t, 6, acc_wait_s); }
+#endif
       if (lane == 0) {
         mbar_wait(g1_done, (uint32_t)(t & 1), 33);
         issue_x(0, g);
         issue_x(1, g + 1);
       }
       mbar_wait(tfull, (uint32_t)(t & 1), 30);
+      if (ew == 0) TRM(0, t, 2, TRM_CLK());
       tc_fence_after();
       // ---- pass 1: v = acc + b2 + x; park v in TMEM, write it back to the residual stream, shifted statistics ----
       float s = 0.f, ss = 0.f, c0 = 0.f;
@@ -349,6 +381,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       }
       tmem_st_wait();
+      if (ew == 0) TRM(0, t, 3, TRM_CLK());
       // the residual boxes are done: once the last out-box store has been read, the h-tile producer may refill the region
       if (lane == 0) {
         tma_store_wait_read();
@@ -366,47 +399,52 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const float mean = 0.5f * (mean_a + mean_b);
       const float var = (m2_a + m2_b + dm * dm * (0.5f * NH)) * (1.f / LN_N);
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
-      // ---- pass 2: normalise out of TMEM, fp16, 64-column slabs through the warp's staging box ----
+      // ---- pass 2: normalise out of TMEM, fp16, 32-column chunks through the warp's staging box (64B-swizzled rows) ----
+      const int sw2 = (lane >> 1) & 3;
 #pragma unroll 1
-      for (int jj = 0; jj < CHUNKS / 2; ++jj) {
-        if (lane == 0) tma_store_wait_read();
+      for (int j = 0; j < CHUNKS; ++j) {
+        const int col0 = c * NH + j * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tlane + j * 32, v);
+        tmem_ld_wait();
+        if (j == CHUNKS - 1) {
+          // last read of this tile's accumulator: hand O back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty);
+        }
+        if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the staging box
         __syncwarp();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int j = jj * 2 + hh;
-          const int col0 = c * NH + j * 32;
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tlane + j * 32, v);
-          tmem_ld_wait();
-          if (j == CHUNKS - 1) {
-            // last read of this tile's accumulator: hand O back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(tempty);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float y[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float ga = sG[col0 + 8 * i + e] * rstd;
-              y[e] = fmaf(__uint_as_float(v[8 * i + e]) - mean, ga, sBt[col0 + 8 * i + e]);
-            }
-            uint4 pk;
-            pk.x = pack_act(y[0], y[1]);
-            pk.y = pack_act(y[2], y[3]);
-            pk.z = pack_act(y[4], y[5]);
-            pk.w = pack_act(y[6], y[7]);
-            *reinterpret_cast<uint4*>(hbox + lane * 128 + (((hh * 4 + i) ^ sw) << 4)) = pk;
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float4 g0 = *reinterpret_cast<const float4*>(sG + col0 + 8 * i);
+          const float4 g1v = *reinterpret_cast<const float4*>(sG + col0 + 8 * i + 4);
+          const float4 t0 = *reinterpret_cast<const float4*>(sBt + col0 + 8 * i);
+          const float4 t1 = *reinterpret_cast<const float4*>(sBt + col0 + 8 * i + 4);
+          float y[8];
+          y[0] = fmaf((__uint_as_float(v[8 * i + 0]) - mean) * rstd, g0.x, t0.x);
+          y[1] = fmaf((__uint_as_float(v[8 * i + 1]) - mean) * rstd, g0.y, t0.y);
+          y[2] = fmaf((__uint_as_float(v[8 * i + 2]) - mean) * rstd, g0.z, t0.z);
+          y[3] = fmaf((__uint_as_float(v[8 * i + 3]) - mean) * rstd, g0.w, t0.w);
+          y[4] = fmaf((__uint_as_float(v[8 * i + 4]) - mean) * rstd, g1v.x, t1.x);
+          y[5] = fmaf((__uint_as_float(v[8 * i + 5]) - mean) * rstd, g1v.y, t1.y);
+          y[6] = fmaf((__uint_as_float(v[8 * i + 6]) - mean) * rstd, g1v.z, t1.z);
+          y[7] = fmaf((__uint_as_float(v[8 * i + 7]) - mean) * rstd, g1v.w, t1.w);
+          uint4 pk;
+          pk.x = pack_act(y[0], y[1]);
+          pk.y = pack_act(y[2], y[3]);
+          pk.z = pack_act(y[4], y[5]);
+          pk.w = pack_act(y[6], y[7]);
+          *reinterpret_cast<uint4*>(hbox + lane * 64 + ((i ^ sw2) << 4)) = pk;
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmH, hbox, c * NH + jj * 64, row0);
+          tma_store_2d(&tmH, hbox, col0, row0);
           tma_store_commit();
         }
       }
+      if (ew == 0) TRM(0, t, 4, TRM_CLK());
       // the sPart exchange of the next tile must not overtake a slow partner still reading this tile's entry
       asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
     }
@@ -447,7 +485,7 @@ int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_
   if (make_tmap_act_2d(&tW1, W1, (uint64_t)D, (uint64_t)hidden, (uint64_t)D * 2, 64, HC / 2, 128)) return 1;
   if (make_tmap_act_2d(&tW2, W2, (uint64_t)hidden, (uint64_t)D, (uint64_t)hidden * 2, 64, NH / 2, 128)) return 1;
   if (make_tmap_f32_2d(&tX, x, (uint64_t)D, (uint64_t)M, (uint64_t)D * 4, 32, 32, 128)) return 1;
-  if (make_tmap_act_2d(&tH, h_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, 32, 128)) return 1;
+  if (make_tmap_act_2d(&tH, h_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 32, 32, 64)) return 1;
   const int tiles = (M + 2 * BM - 1) / (2 * BM);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
@@ -457,3 +495,9 @@ int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_
 }
 
 }  // namespace vited
+
+#ifdef VITED_MLP_TRACE
+extern "C" __attribute__((visibility("default"))) int vited_debug_mlp_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, vited::g_mlp_trace, sizeof(long long) * 2 * 32 * 8);
+}
+#endif
