@@ -4,7 +4,7 @@ import ctypes, math, os, sys
 import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = ctypes.CDLL(os.path.join(ROOT, 'tools', 'bin', 'trace', 'libvited_b200.so'))
+lib = ctypes.CDLL(os.environ.get('TRACE_LIB') or os.path.join(ROOT, 'tools', 'bin', 'trace', 'libvited_b200.so'))
 vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 lib.vited_op_mlp_resid_ln.argtypes = [vp] * 9 + [ci, ci, ci, cf, vp]
 lib.vited_op_mlp_resid_ln.restype = ci

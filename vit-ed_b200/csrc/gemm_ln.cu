@@ -200,30 +200,43 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int col0 = c * NH + j * 32;
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tlane + j * 32, acc);
-        tmem_ld_wait();
         mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
-        const uint8_t* rowp = xbox + (g & 1) * Cfg::XBOX + lane * 128;
+        tmem_ld_wait();
+        // shared-window addresses of this lane's 128-byte row in the in-box / out-box (16-byte chunk i lives at i ^ sw)
+        const uint32_t in_row = smem_u32(xbox) + (uint32_t)(g & 1) * Cfg::XBOX + lane * 128;
+        const uint32_t out_row = smem_u32(hbox) + lane * 128;
+        const uint32_t bias_a = smem_u32(sBias) + col0 * 4;
         // the updated row leaves through the warp's second staging box (idle during this pass), NOT through the box it
         // came in: the in-box can then be refilled as soon as the warp has read it, without waiting for a store
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the out-box
         __syncwarp();
-        uint8_t* outp = hbox + lane * 128;
+        // first the updated row: it goes to the out-box at once, so that the stores have drained by the time the proxy
+        // fence in front of the TMA store is reached (MEMBAR.ALL.CTA waits for every store in flight: ~300 cycles when it
+        // came right behind the last store); the statistics are computed while they drain
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 xv = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
-          const float4 b4 = *reinterpret_cast<const float4*>(sBias + col0 + 4 * i);
+          const float4 xv = lds_f4(in_row + ((i ^ sw) << 4));
+          const float4 b4 = lds_f4(bias_a + 16 * i);
           float4 v;
           v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
           v.y = __uint_as_float(acc[4 * i + 1]) + b4.y + xv.y;
           v.z = __uint_as_float(acc[4 * i + 2]) + b4.z + xv.z;
           v.w = __uint_as_float(acc[4 * i + 3]) + b4.w + xv.w;
-          if (j == 0 && i == 0) c0 = v.x;
-          const float d0 = v.x - c0, d1 = v.y - c0, d2 = v.z - c0, d3 = v.w - c0;
-          s += (d0 + d1) + (d2 + d3);
-          ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
-          *reinterpret_cast<float4*>(outp + ((i ^ sw) << 4)) = v;
+          sts_f4(out_row + ((i ^ sw) << 4), v);
           acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
           acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
+        }
+        if (j == 0) c0 = __uint_as_float(acc[0]);
+        {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains each
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = __uint_as_float(acc[i]) - c0;
+            s4[i & 3] += d;
+            q4[i & 3] = fmaf(d, d, q4[i & 3]);
+          }
+          s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          ss += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
         tmem_st_32x32b_x32(tlane + j * 32, acc);
         fence_proxy_async_smem();
@@ -249,6 +262,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
       if (who >= 0) TRL(who, t, 3);
       // ---- pass 2: normalise out of TMEM, fp16, 64-column slabs through the warp's staging box ----
+      const uint32_t hbox_a = smem_u32(hbox) + lane * 128, g_a = smem_u32(sG), bt_a = smem_u32(sBt);
 #pragma unroll 1
       for (int jj = 0; jj < CHUNKS / 2; ++jj) {
         if (lane == 0) tma_store_wait_read();
@@ -268,18 +282,25 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
+            const float4 g0 = lds_f4(g_a + col0 * 4 + 32 * i);
+            const float4 g1v = lds_f4(g_a + col0 * 4 + 32 * i + 16);
+            const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
+            const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
             float y[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float ga = sG[col0 + 8 * i + e] * rstd;
-              y[e] = fmaf(__uint_as_float(v[8 * i + e]) - mean, ga, sBt[col0 + 8 * i + e]);
-            }
+            y[0] = fmaf((__uint_as_float(v[8 * i + 0]) - mean) * rstd, g0.x, t0.x);
+            y[1] = fmaf((__uint_as_float(v[8 * i + 1]) - mean) * rstd, g0.y, t0.y);
+            y[2] = fmaf((__uint_as_float(v[8 * i + 2]) - mean) * rstd, g0.z, t0.z);
+            y[3] = fmaf((__uint_as_float(v[8 * i + 3]) - mean) * rstd, g0.w, t0.w);
+            y[4] = fmaf((__uint_as_float(v[8 * i + 4]) - mean) * rstd, g1v.x, t1.x);
+            y[5] = fmaf((__uint_as_float(v[8 * i + 5]) - mean) * rstd, g1v.y, t1.y);
+            y[6] = fmaf((__uint_as_float(v[8 * i + 6]) - mean) * rstd, g1v.z, t1.z);
+            y[7] = fmaf((__uint_as_float(v[8 * i + 7]) - mean) * rstd, g1v.w, t1.w);
             uint4 pk;
             pk.x = pack_act(y[0], y[1]);
             pk.y = pack_act(y[2], y[3]);
             pk.z = pack_act(y[4], y[5]);
             pk.w = pack_act(y[6], y[7]);
-            *reinterpret_cast<uint4*>(hbox + lane * 128 + (((hh * 4 + i) ^ sw) << 4)) = pk;
+            sts_u4(hbox_a + (((hh * 4 + i) ^ sw) << 4), pk);
           }
         }
         fence_proxy_async_smem();

@@ -307,11 +307,11 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tS + b * HC, acc);
         tmem_ld_wait();
-        const float* bp = sB1 + ch * HC + c * 32;
+        const uint32_t bp = smem_u32(sB1) + (uint32_t)(ch * HC + c * 32) * 4;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bp + 4 * i);
+          const float4 b4 = lds_f4(bp + 16 * i);
           const float v0 = gelu_fast(__uint_as_float(acc[4 * i + 0]) + b4.x);
           const float v1 = gelu_fast(__uint_as_float(acc[4 * i + 1]) + b4.y);
           const float v2 = gelu_fast(__uint_as_float(acc[4 * i + 2]) + b4.z);
@@ -348,28 +348,41 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int col0 = c * NH + j * 32;
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tlane + j * 32, acc);
-        tmem_ld_wait();
         mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
-        const uint8_t* rowp = xbox + (g & 1) * Cfg::XBOX + lane * 128;
+        tmem_ld_wait();
+        // shared-window addresses of this lane's 128-byte row in the in-box / out-box (16-byte chunk i lives at i ^ sw)
+        const uint32_t in_row = smem_u32(xbox) + (uint32_t)(g & 1) * Cfg::XBOX + lane * 128;
+        const uint32_t out_row = smem_u32(obox) + lane * 128;
+        const uint32_t bias_a = smem_u32(sBias) + col0 * 4;
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the out-box
         __syncwarp();
-        uint8_t* outp = obox + lane * 128;
+        // first the updated row: it goes to the out-box at once, so that the stores have drained by the time the proxy
+        // fence in front of the TMA store is reached (MEMBAR.ALL.CTA waits for every store in flight: ~300 cycles when it
+        // came right behind the last store); the statistics are computed while they drain
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 xv = *reinterpret_cast<const float4*>(rowp + ((i ^ sw) << 4));
-          const float4 b4 = *reinterpret_cast<const float4*>(sBias + col0 + 4 * i);
+          const float4 xv = lds_f4(in_row + ((i ^ sw) << 4));
+          const float4 b4 = lds_f4(bias_a + 16 * i);
           float4 v;
           v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
           v.y = __uint_as_float(acc[4 * i + 1]) + b4.y + xv.y;
           v.z = __uint_as_float(acc[4 * i + 2]) + b4.z + xv.z;
           v.w = __uint_as_float(acc[4 * i + 3]) + b4.w + xv.w;
-          if (j == 0 && i == 0) c0 = v.x;
-          const float d0 = v.x - c0, d1 = v.y - c0, d2 = v.z - c0, d3 = v.w - c0;
-          s += (d0 + d1) + (d2 + d3);
-          ss = fmaf(d0, d0, ss); ss = fmaf(d1, d1, ss); ss = fmaf(d2, d2, ss); ss = fmaf(d3, d3, ss);
-          *reinterpret_cast<float4*>(outp + ((i ^ sw) << 4)) = v;
+          sts_f4(out_row + ((i ^ sw) << 4), v);
           acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
           acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
+        }
+        if (j == 0) c0 = __uint_as_float(acc[0]);
+        {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains each
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = __uint_as_float(acc[i]) - c0;
+            s4[i & 3] += d;
+            q4[i & 3] = fmaf(d, d, q4[i & 3]);
+          }
+          s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          ss += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
         tmem_st_32x32b_x32(tlane + j * 32, acc);
         fence_proxy_async_smem();
@@ -401,26 +414,17 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
       // ---- pass 2: normalise out of TMEM, fp16, 32-column chunks through the warp's staging box (64B-swizzled rows) ----
       const int sw2 = (lane >> 1) & 3;
-#pragma unroll 1
-      for (int j = 0; j < CHUNKS; ++j) {
+      const uint32_t hbox_a = smem_u32(hbox) + lane * 64, g_a = smem_u32(sG), bt_a = smem_u32(sBt);
+      auto normalise_chunk = [&](const uint32_t (&v)[32], int j) {
         const int col0 = c * NH + j * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tlane + j * 32, v);
-        tmem_ld_wait();
-        if (j == CHUNKS - 1) {
-          // last read of this tile's accumulator: hand O back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_leader(tempty);
-        }
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the staging box
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 g0 = *reinterpret_cast<const float4*>(sG + col0 + 8 * i);
-          const float4 g1v = *reinterpret_cast<const float4*>(sG + col0 + 8 * i + 4);
-          const float4 t0 = *reinterpret_cast<const float4*>(sBt + col0 + 8 * i);
-          const float4 t1 = *reinterpret_cast<const float4*>(sBt + col0 + 8 * i + 4);
+          const float4 g0 = lds_f4(g_a + col0 * 4 + 32 * i);
+          const float4 g1v = lds_f4(g_a + col0 * 4 + 32 * i + 16);
+          const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
+          const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
           float y[8];
           y[0] = fmaf((__uint_as_float(v[8 * i + 0]) - mean) * rstd, g0.x, t0.x);
           y[1] = fmaf((__uint_as_float(v[8 * i + 1]) - mean) * rstd, g0.y, t0.y);
@@ -435,7 +439,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           pk.y = pack_act(y[2], y[3]);
           pk.z = pack_act(y[4], y[5]);
           pk.w = pack_act(y[6], y[7]);
-          *reinterpret_cast<uint4*>(hbox + lane * 64 + ((i ^ sw2) << 4)) = pk;
+          sts_u4(hbox_a + ((i ^ sw2) << 4), pk);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -443,6 +447,21 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tma_store_2d(&tmH, hbox, col0, row0);
           tma_store_commit();
         }
+      };
+      // (a two-register-buffer version with the TMEM read of chunk j + 1 in flight measured slower: 8.0 k vs 6.0 k
+      //  cycles per tile -- both epilogue passes are instruction-issue bound, not latency bound; profiles/README.md)
+#pragma unroll 1
+      for (int j = 0; j < CHUNKS; ++j) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tlane + j * 32, v);
+        tmem_ld_wait();
+        if (j == CHUNKS - 1) {
+          // last read of this tile's accumulator: hand O back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty);
+        }
+        normalise_chunk(v, j);
       }
       if (ew == 0) TRM(0, t, 4, TRM_CLK());
       // the sPart exchange of the next tile must not overtake a slow partner still reading this tile's entry
