@@ -143,6 +143,51 @@ VITED_API int vited_prepare_pieces(const uint8_t* lab_image, int H, int W, int p
  * images [N, S, S, 3] u8 (device) -> out [N, 3, S, S] f32 = (v / 255 - 0.5) / 0.5, bit-identical to torch's fp32 ops. */
 VITED_API int vited_normalize_u8(const uint8_t* images, int N, int S, float* out, void* stream);
 
+/* ---- Hisfrag training step ----
+ * replaces: the compute of HisfragTrainer.train_step (hisfrag.py:149-159: encode the batch, decode the pairs
+ * model(tokens[groups[:, 1]], samples[groups[:, 0]]), nn.BCEWithLogitsLoss :60-61) and of the backward pass that
+ * misc/engine.py:189-257 runs through autograd. The host side (vit-ed_b200/train.py) walks the layers and calls these
+ * single-kernel entry points; every Linear (forward, dgrad dX = dY W, wgrad dW = dY^T X) is vited_op_gemm on the tcgen05
+ * kernel with 16-bit operands (h16), fed by the transposes below; everything elementwise is fp32. Plain row-major
+ * [rows, cols] buffers, sequences as consecutive token rows with the class token first. All pointers are device
+ * pointers; `alpha` arguments fold the loss-scale removal into the accumulation of parameter gradients.
+ *   cast:        out h16 = in f32 * scale                      axpby16: y f32 = alpha * x h16 + beta * y
+ *   axpy32:      y += alpha * x (f32)                          transpose: out h16 [C, ld_out] = scale * in[R, C]^T (f32 or
+ *                                                              h16 input), rows R..ld_out-1 of the K dimension zero filled
+ *   ln_forward:  h h16 = LayerNorm(x f32) * w + b, stats[r] = (mean, rstd)
+ *   ln_backward: dx += d LN / dx (dh f32); dw += alpha * sum dh * xhat; db += alpha * sum dh
+ *   gelu_forward / gelu_backward: exact-erf GELU on h16 z; dz f32 = da f32 * gelu'(z)
+ *   colsum:      db[c] += alpha * sum_r dy[r, c]
+ *   gather_rows / scatter_add_rows: blocks of rows_per consecutive rows moved between [block idx[b]] of one buffer and
+ *                block b of the other (pairs <-> items; position / class-token broadcast and its gradient)
+ *   attention:   softmax(q k^T * scale) v per (sequence, head), fp32 math on h16 q / k / v; backward = 1 recomputes the
+ *                probabilities and accumulates dq (+=), dk, dv (atomic +=) in f32 from d_o f32
+ *   bce_logits:  loss = mean BCE-with-logits; dlogits = (sigmoid(logit) - label) * grad_scale / n */
+VITED_API int vited_train_cast(const float* in, void* out, int64_t n, float scale, void* stream);
+VITED_API int vited_train_axpby16(const void* x, float* y, int64_t n, float alpha, float beta, void* stream);
+VITED_API int vited_train_axpy32(const float* x, float* y, int64_t n, float alpha, void* stream);
+VITED_API int vited_train_transpose(const void* in, int in_is_f32, int ld_in, void* out, int ld_out, int R, int C,
+                                    float scale, void* stream);
+VITED_API int vited_train_ln_forward(const float* x, const float* w, const float* b, void* h, float* stats, int R, int D,
+                                     float eps, void* stream);
+VITED_API int vited_train_ln_backward(const float* dh, const float* x, const float* stats, const float* w, float* dx,
+                                      float* dw, float* db, int R, int D, float alpha, void* stream);
+VITED_API int vited_train_gelu_forward(const void* z, void* a, int64_t n, void* stream);
+VITED_API int vited_train_gelu_backward(const float* da, const void* z, float* dz, int64_t n, void* stream);
+VITED_API int vited_train_colsum(const float* dy, float* db, int R, int N, float alpha, void* stream);
+VITED_API int vited_train_gather_rows(const float* in, const int32_t* idx, float* out, int n_blocks, int rows_per,
+                                      int in_block_stride, int in_row_off, int out_block_stride, int out_row_off, int D,
+                                      int accumulate, void* stream);
+VITED_API int vited_train_scatter_add_rows(const float* src, const int32_t* idx, float* dst, int n_blocks, int rows_per,
+                                           int src_block_stride, int src_row_off, int dst_block_stride, int dst_row_off,
+                                           int D, float alpha, void* stream);
+VITED_API int vited_train_attention(int backward, const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld,
+                                    void* o, int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk,
+                                    int dk_ld, float* dv, int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale,
+                                    void* stream);
+VITED_API int vited_train_bce_logits(const float* logits, const float* labels, int n, float* loss, float* dlogits,
+                                     float grad_scale, void* stream);
+
 /* ---- consumer side of the puzzle grid ----
  * replaces: the tables InterPieceDistance.__init__ fills through 4*N*(N-1) callbacks into evaluation.py:116-131's
  * distance_function -- PieceDistanceInformation.calculate_inter_piece_distances (paikin_tal_solver/

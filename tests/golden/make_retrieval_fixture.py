@@ -36,6 +36,35 @@ def trainable(key, t):
     return t.dim() == 1 or key in ('cls_token', 'head.weight')
 
 
+MIXED = dict(n_writers=12, per_writer=4, seed=6)   # 8 writers seen in training + 4 unseen ones: metrics below 1
+
+
+def mixed_set():
+    from vited_b200 import synthetic
+    return synthetic.synthetic_fragments(MIXED['n_writers'], MIXED['per_writer'], KW['img_size'], seed=MIXED['seed'],
+                                         writer_seed=WRITER_SEED)
+
+
+def add_mixed_only():
+    """Re-evaluates the stored vectors on the mixed set without retraining (python make_retrieval_fixture.py mixed)."""
+    from oracle import vited_oracle as orc
+    path = os.path.join(HERE, 'retrieval_weights.npz')
+    z = dict(np.load(path))
+    sd = base_state_dict()
+    for k, v in z.items():
+        if not k.startswith('__'):
+            sd[k] = torch.from_numpy(v)
+    imgs, labels = mixed_set()
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        sim = orc.score_fragment_grid(sd, KW['num_heads'], imgs)
+    m = orc.wi19_metrics(orc.sim_to_distance(sim), labels.numpy(), kind='stable')
+    print('mixed set (8 seen + 4 unseen writers x 4): mAP %.4f top-1 %.4f Pr@10 %.4f Pr@100 %.4f' % m)
+    z['__mixed_sim__'] = sim.numpy()
+    z['__mixed_metrics__'] = np.array(m, dtype=np.float64)
+    np.savez_compressed(path, **z)
+
+
 def main():
     from oracle import vited_oracle as orc
     from vited_b200 import synthetic
@@ -82,4 +111,8 @@ def main():
 
 
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'mixed':
+        add_mixed_only()
+    else:
+        main()
+        add_mixed_only()

@@ -236,8 +236,8 @@ def test_training_pair_construction_matches_reference(name):
     from oracle import vited_oracle as orc
     og, ol = orc.train_pairs(z[f'{name}_targets'], int(z[f'{name}_perm_seed']))
     assert torch.equal(groups, og) and torch.equal(labels, ol)
-    with pytest.raises(vited_b200.VitedError):
-        train.train_step()
+    with pytest.raises(vited_b200.VitedError):                       # no CPU path: CUDA tensors only
+        train.train_step(None, torch.zeros(2, 3, 64, 64), [0, 0])
 
 
 def test_row_split_and_crop_geometry_properties():

@@ -71,6 +71,20 @@ SIGNATURES = {
     "vited_retrieval_rows": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vited_puzzle_tables": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vited_workspace_bytes": (_i64, [_vp]),
+    "vited_train_cast": (_i, [_vp, _vp, _i64, _f, _vp]),
+    "vited_train_axpby16": (_i, [_vp, _vp, _i64, _f, _f, _vp]),
+    "vited_train_axpy32": (_i, [_vp, _vp, _i64, _f, _vp]),
+    "vited_train_transpose": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _f, _vp]),
+    "vited_train_ln_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "vited_train_ln_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "vited_train_gelu_forward": (_i, [_vp, _vp, _i64, _vp]),
+    "vited_train_gelu_backward": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "vited_train_colsum": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "vited_train_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "vited_train_scatter_add_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "vited_train_attention": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i,
+                                   _i, _f, _vp]),
+    "vited_train_bce_logits": (_i, [_vp, _vp, _i, _vp, _vp, _f, _vp]),
     "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vited_op_gemm_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "vited_op_mlp_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

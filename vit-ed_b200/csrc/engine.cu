@@ -908,6 +908,59 @@ int vited_op_im2col(const float* images, void* out, int B, int C, int S, int p, 
   return im2col_patches(images, (act_t*)out, B, C, S, p, (cudaStream_t)stream);
 }
 
+// ---- training-step kernels (train_ops.cu) ----
+int vited_train_cast(const float* in, void* out, int64_t n, float scale, void* stream) {
+  return train_cast_scale(in, (act_t*)out, (size_t)n, scale, (cudaStream_t)stream);
+}
+int vited_train_axpby16(const void* x, float* y, int64_t n, float alpha, float beta, void* stream) {
+  return train_act_axpby((const act_t*)x, y, (size_t)n, alpha, beta, (cudaStream_t)stream);
+}
+int vited_train_axpy32(const float* x, float* y, int64_t n, float alpha, void* stream) {
+  return train_f32_axpy(x, y, (size_t)n, alpha, (cudaStream_t)stream);
+}
+int vited_train_transpose(const void* in, int in_is_f32, int ld_in, void* out, int ld_out, int R, int C, float scale,
+                          void* stream) {
+  return train_transpose(in, in_is_f32, ld_in, (act_t*)out, ld_out, R, C, scale, (cudaStream_t)stream);
+}
+int vited_train_ln_forward(const float* x, const float* w, const float* b, void* h, float* stats, int R, int D, float eps,
+                           void* stream) {
+  return train_ln_forward(x, w, b, (act_t*)h, stats, R, D, eps, (cudaStream_t)stream);
+}
+int vited_train_ln_backward(const float* dh, const float* x, const float* stats, const float* w, float* dx, float* dw,
+                            float* db, int R, int D, float alpha, void* stream) {
+  return train_ln_backward(dh, x, stats, w, dx, dw, db, R, D, alpha, (cudaStream_t)stream);
+}
+int vited_train_gelu_forward(const void* z, void* a, int64_t n, void* stream) {
+  return train_gelu_forward((const act_t*)z, (act_t*)a, (size_t)n, (cudaStream_t)stream);
+}
+int vited_train_gelu_backward(const float* da, const void* z, float* dz, int64_t n, void* stream) {
+  return train_gelu_backward(da, (const act_t*)z, dz, (size_t)n, (cudaStream_t)stream);
+}
+int vited_train_colsum(const float* dy, float* db, int R, int N, float alpha, void* stream) {
+  return train_colsum(dy, db, R, N, alpha, (cudaStream_t)stream);
+}
+int vited_train_gather_rows(const float* in, const int32_t* idx, float* out, int n_blocks, int rows_per, int in_block_stride,
+                            int in_row_off, int out_block_stride, int out_row_off, int D, int accumulate, void* stream) {
+  return train_gather_rows(in, idx, out, n_blocks, rows_per, in_block_stride, in_row_off, out_block_stride, out_row_off, D,
+                           accumulate, (cudaStream_t)stream);
+}
+int vited_train_scatter_add_rows(const float* src, const int32_t* idx, float* dst, int n_blocks, int rows_per,
+                                 int src_block_stride, int src_row_off, int dst_block_stride, int dst_row_off, int D,
+                                 float alpha, void* stream) {
+  return train_scatter_add_rows(src, idx, dst, n_blocks, rows_per, src_block_stride, src_row_off, dst_block_stride,
+                                dst_row_off, D, alpha, (cudaStream_t)stream);
+}
+int vited_train_attention(int backward, const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o,
+                          int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk, int dk_ld, float* dv,
+                          int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale, void* stream) {
+  return train_attention(backward, (const act_t*)q, q_ld, (const act_t*)k, k_ld, (const act_t*)v, v_ld, (act_t*)o, o_ld, d_o,
+                         do_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld, n_seq, H, hd, Tq, Tk, scale, (cudaStream_t)stream);
+}
+int vited_train_bce_logits(const float* logits, const float* labels, int n, float* loss, float* dlogits, float grad_scale,
+                           void* stream) {
+  return train_bce_logits(logits, labels, n, loss, dlogits, grad_scale, (cudaStream_t)stream);
+}
+
 int vited_prepare_pieces(const uint8_t* lab_image, int H, int W, int piece_width, int side, int off, int out_size,
                          float* out, int* n_pieces, void* stream) {
   return prepare_pieces(lab_image, H, W, piece_width, side, off, out_size, out, n_pieces, (cudaStream_t)stream);

@@ -108,6 +108,27 @@ int puzzle_tables(const float* scores, int flags, const int* order, int N, uint3
                   long long* second_d, int* n_cand, int* cand, float* compat, float* mutual, int* best_buddy,
                   cudaStream_t stream);
 
+// ---- training-step kernels (train_ops.cu): see include/vited_b200.h vited_train_* ----
+int train_cast_scale(const float* in, act_t* out, size_t n, float scale, cudaStream_t s);
+int train_act_axpby(const act_t* x, float* y, size_t n, float alpha, float beta, cudaStream_t s);
+int train_f32_axpy(const float* x, float* y, size_t n, float alpha, cudaStream_t s);
+int train_transpose(const void* in, int in_is_f32, int ld_in, act_t* out, int ld_out, int R, int C, float scale, cudaStream_t s);
+int train_ln_forward(const float* x, const float* w, const float* b, act_t* h, float* stats, int R, int D, float eps, cudaStream_t s);
+int train_ln_backward(const float* dh, const float* x, const float* stats, const float* w, float* dx, float* dw, float* db,
+                      int R, int D, float alpha, cudaStream_t s);
+int train_gelu_forward(const act_t* z, act_t* a, size_t n, cudaStream_t s);
+int train_gelu_backward(const float* da, const act_t* z, float* dz, size_t n, cudaStream_t s);
+int train_colsum(const float* dy, float* db, int R, int N, float alpha, cudaStream_t s);
+int train_gather_rows(const float* in, const int* idx, float* out, int n_blocks, int rows_per, int in_block_stride,
+                      int in_row_off, int out_block_stride, int out_row_off, int D, int accumulate, cudaStream_t s);
+int train_scatter_add_rows(const float* src, const int* idx, float* dst, int n_blocks, int rows_per, int src_block_stride,
+                           int src_row_off, int dst_block_stride, int dst_row_off, int D, float alpha, cudaStream_t s);
+int train_attention(int backward, const act_t* q, int q_ld, const act_t* k, int k_ld, const act_t* v, int v_ld, act_t* o,
+                    int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk, int dk_ld, float* dv, int dv_ld,
+                    int n_seq, int H, int hd, int Tq, int Tk, float scale, cudaStream_t s);
+int train_bce_logits(const float* logits, const float* labels, int n, float* loss, float* dlogits, float grad_scale,
+                     cudaStream_t s);
+
 // ---- attention (attention.cu) ----
 // Sequences live in the split layout. Logical token s of sequence b: s==0 && has_cls ? cls row : patch row.
 struct AttnArgs {
