@@ -593,6 +593,57 @@ def run_hisfrag(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Side measurement of BASELINE.json configs[4]: one Hisfrag20 training step (forward with saved activations,
+    BCE-with-logits, backward to every parameter, gradient all-reduce) per rank on 24 synthetic 512 px images of 8
+    writers (3 per writer as MPerClassSampler(m=3), hisfrag.py:107 -> 24 positive + 48 negative pairs), through
+    vited_b200.train.train_step. Reports steps/s and pairs/s over all ranks. The attention forward / backward of this
+    path are plain fp32 kernels so far, so this is a functional number, not a tuned one."""
+    import vited_b200
+    from vited_b200 import synthetic, train
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device('cuda', local if world > 1 else 0)
+    model = vited_b200.build_model(vited_b200.get_config('hisfrag'))
+    model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0), strict=True)
+    model = model.to(dev)
+    n_img = args.items if args.items != 512 else 24
+    samples, labels = synthetic.synthetic_fragments(n_img // 3, 3, 512, seed=100 + rank)
+    samples = samples.to(dev)
+    gen = torch.Generator().manual_seed(rank)
+    for _ in range(max(args.warmup, 1)):
+        loss, logits, groups, _ = train.train_step(model, samples, labels, generator=gen)
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, logits, groups, _ = train.train_step(model, samples, labels, generator=gen)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps, world)
+    gnorm = float(torch.sqrt(sum(p.grad.double().pow(2).sum() for p in model.parameters())))
+    train.train_step(model, samples, labels, generator=gen, profile=True)
+    prof = model.train_profile
+    if rank == 0:
+        line = {'metric': 'training steps/sec (Hisfrag20 ViT-ED, fwd + bwd + gradient all-reduce)', 'value': 1e3 / ms,
+                'unit': 'steps/s', 'pairs_per_s': world * groups.shape[0] * 1e3 / ms, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': vited_b200.ACT_NAME, 'data': 'synthetic',
+                'config': {'workload': f'configs[4]: Hisfrag20 patch16 512px training step, {n_img} images / GPU -> '
+                                       f'{groups.shape[0]} pairs / GPU, DDP-style gradient averaging over {world} GPU(s)'},
+                'loss': float(loss), 'grad_norm': gnorm, 'gpu_launches': int(model.train_launches) * args.steps,
+                'classes_rank0': prof}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -602,8 +653,9 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-extras', action='store_true',
                     help='skip the same-workload N=1 rate and the torch GPU baseline (profiling runs)')
-    ap.add_argument('--workload', default='puzzle', choices=['puzzle', 'hisfrag'],
-                    help="'hisfrag' = the Hisfrag20 model (configs[3]) on an all-pairs grid of --items fragments")
+    ap.add_argument('--workload', default='puzzle', choices=['puzzle', 'hisfrag', 'train'],
+                    help="'hisfrag' = the Hisfrag20 model (configs[3]) on an all-pairs grid of --items fragments; "
+                         "'train' = one Hisfrag20 training step per rank (configs[4])")
     ap.add_argument('--items', type=int, default=512, help='fragments for --workload hisfrag')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
@@ -615,6 +667,8 @@ def main():
             raise SystemExit('bench.py: no CUDA device; the scoring path has no CPU fallback (use --impl reference)')
         if args.workload == 'hisfrag':
             run_hisfrag(args)
+        elif args.workload == 'train':
+            run_train(args)
         else:
             run_ours(args)
 

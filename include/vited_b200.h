@@ -160,8 +160,10 @@ VITED_API int vited_normalize_u8(const uint8_t* images, int N, int S, float* out
  *   colsum:      db[c] += alpha * sum_r dy[r, c]
  *   gather_rows / scatter_add_rows: blocks of rows_per consecutive rows moved between [block idx[b]] of one buffer and
  *                block b of the other (pairs <-> items; position / class-token broadcast and its gradient)
- *   attention:   softmax(q k^T * scale) v per (sequence, head), fp32 math on h16 q / k / v; backward = 1 recomputes the
- *                probabilities and accumulates dq (+=), dk, dv (atomic +=) in f32 from d_o f32
+ *   attention:   softmax(q k^T * scale) v per (sequence, head) on the warp-level tensor cores (wmma, fp32 accumulation;
+ *                head_dim 32 / 64), flash style: the forward stores o h16 and lse [n_seq, H, Tq] (log-sum-exp per query
+ *                row); backward = 1 takes o, lse and d_o f32, recomputes the probabilities block by block (nothing
+ *                quadratic is stored, no atomics), writes dsum [n_seq, H, Tq] = do . o and accumulates dq, dk, dv (+=, f32)
  *   bce_logits:  loss = mean BCE-with-logits; dlogits = (sigmoid(logit) - label) * grad_scale / n */
 VITED_API int vited_train_cast(const float* in, void* out, int64_t n, float scale, void* stream);
 VITED_API int vited_train_axpby16(const void* x, float* y, int64_t n, float alpha, float beta, void* stream);
@@ -182,9 +184,9 @@ VITED_API int vited_train_scatter_add_rows(const float* src, const int32_t* idx,
                                            int src_block_stride, int src_row_off, int dst_block_stride, int dst_row_off,
                                            int D, float alpha, void* stream);
 VITED_API int vited_train_attention(int backward, const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld,
-                                    void* o, int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk,
-                                    int dk_ld, float* dv, int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale,
-                                    void* stream);
+                                    void* o, int o_ld, float* lse, const float* d_o, int do_ld, float* dsum, float* dq,
+                                    int dq_ld, float* dk, int dk_ld, float* dv, int dv_ld, int n_seq, int H, int hd, int Tq,
+                                    int Tk, float scale, void* stream);
 VITED_API int vited_train_bce_logits(const float* logits, const float* labels, int n, float* loss, float* dlogits,
                                      float grad_scale, void* stream);
 

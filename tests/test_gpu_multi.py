@@ -42,6 +42,22 @@ def _worker(rank, world, port, q):
         upper = fmodel.score_grid(frags, vited_b200.GRID_UPPER_TRI_DIAG, 0, 23)[..., 0]
         out['fragments'] = (sim - grid.mirror_upper(upper)).abs().max().item()
         out['symmetric'] = bool(torch.equal(sim, sim.t()))
+        # training step: every rank its own batch, gradients averaged over the ranks (what DDP does)
+        from vited_b200 import train
+        z, kw = helpers.load_model_case('small_hd64')
+        tmodel, _ = helpers.make_gpu_model(kw, 2)
+        samples = synthetic.synthetic_images(6, kw['img_size'], seed=70 + rank).cuda()
+        gen = torch.Generator().manual_seed(5)
+        train.train_step(tmodel, samples, [0, 0, 0, 1, 1, 1], generator=gen, all_reduce=False)
+        local = torch.cat([p.grad.reshape(-1) for p in tmodel.parameters()]).clone()
+        gen = torch.Generator().manual_seed(5)
+        train.train_step(tmodel, samples, [0, 0, 0, 1, 1, 1], generator=gen, all_reduce=True)
+        averaged = torch.cat([p.grad.reshape(-1) for p in tmodel.parameters()])
+        both = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(both, local)
+        want = sum(both) / world
+        out['ddp'] = ((averaged - want).abs().max() / want.abs().max()).item()
+        out['ddp_differs_from_local'] = bool((averaged - local).abs().max() > 0)
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -66,3 +82,4 @@ def test_sharded_grids_under_nccl_equal_single_gpu_grids():
         # rounding noise of the unfused / fused sub-block boundary (see test_grid_properties_puzzle_model)
         assert out['puzzles'] < 1e-2 and out['puzzle'] < 1e-2 and out['fragments'] < 1e-2, (rank, out)
         assert out['symmetric'], rank
+        assert out['ddp'] < 1e-6 and out['ddp_differs_from_local'], (rank, out)

@@ -82,8 +82,8 @@ SIGNATURES = {
     "vited_train_colsum": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "vited_train_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vited_train_scatter_add_rows": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
-    "vited_train_attention": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i,
-                                   _i, _f, _vp]),
+    "vited_train_attention": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i,
+                                   _i, _i, _i, _f, _vp]),
     "vited_train_bce_logits": (_i, [_vp, _vp, _i, _vp, _vp, _f, _vp]),
     "vited_op_gemm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vited_op_gemm_resid_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

@@ -951,10 +951,11 @@ int vited_train_scatter_add_rows(const float* src, const int32_t* idx, float* ds
                                 dst_row_off, D, alpha, (cudaStream_t)stream);
 }
 int vited_train_attention(int backward, const void* q, int q_ld, const void* k, int k_ld, const void* v, int v_ld, void* o,
-                          int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk, int dk_ld, float* dv,
-                          int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale, void* stream) {
-  return train_attention(backward, (const act_t*)q, q_ld, (const act_t*)k, k_ld, (const act_t*)v, v_ld, (act_t*)o, o_ld, d_o,
-                         do_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld, n_seq, H, hd, Tq, Tk, scale, (cudaStream_t)stream);
+                          int o_ld, float* lse, const float* d_o, int do_ld, float* dsum, float* dq, int dq_ld, float* dk,
+                          int dk_ld, float* dv, int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale,
+                          void* stream) {
+  return train_attention(backward, (const act_t*)q, q_ld, (const act_t*)k, k_ld, (const act_t*)v, v_ld, (act_t*)o, o_ld, lse,
+                         d_o, do_ld, dsum, dq, dq_ld, dk, dk_ld, dv, dv_ld, n_seq, H, hd, Tq, Tk, scale, (cudaStream_t)stream);
 }
 int vited_train_bce_logits(const float* logits, const float* labels, int n, float* loss, float* dlogits, float grad_scale,
                            void* stream) {

@@ -124,8 +124,14 @@ int train_gather_rows(const float* in, const int* idx, float* out, int n_blocks,
 int train_scatter_add_rows(const float* src, const int* idx, float* dst, int n_blocks, int rows_per, int src_block_stride,
                            int src_row_off, int dst_block_stride, int dst_row_off, int D, float alpha, cudaStream_t s);
 int train_attention(int backward, const act_t* q, int q_ld, const act_t* k, int k_ld, const act_t* v, int v_ld, act_t* o,
-                    int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk, int dk_ld, float* dv, int dv_ld,
-                    int n_seq, int H, int hd, int Tq, int Tk, float scale, cudaStream_t s);
+                    int o_ld, float* lse, const float* d_o, int do_ld, float* dsum, float* dq, int dq_ld, float* dk, int dk_ld,
+                    float* dv, int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale, cudaStream_t s);
+// tensor-core (wmma) version of train_attention for head_dim 32 / 64 (train_attn.cu); the backward pass also reads the
+// forward output o (D_i = do_i . o_i)
+bool train_attention_wmma_supported(int hd);
+int train_attention_wmma(int backward, const act_t* q, int q_ld, const act_t* k, int k_ld, const act_t* v, int v_ld, act_t* o,
+                         int o_ld, float* lse, const float* d_o, int do_ld, float* dsum, float* dq, int dq_ld, float* dk,
+                         int dk_ld, float* dv, int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale, cudaStream_t s);
 int train_bce_logits(const float* logits, const float* labels, int n, float* loss, float* dlogits, float grad_scale,
                      cudaStream_t s);
 

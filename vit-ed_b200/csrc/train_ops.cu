@@ -10,6 +10,7 @@
 // Plain row-major layouts here ([rows, cols], sequences as consecutive token rows, class token first): the split token
 // layout of the scoring path is an inference-side optimisation.
 #include "kernels.h"
+#include <cstdlib>
 
 namespace vited {
 
@@ -135,12 +136,41 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ da, const act_t* __res
 // ---------------------------------------------------------------------------------------------------------------
 // bias gradient: db[c] += alpha * sum_r dy[r, c]
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, int R, int N, float alpha) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  float s = 0.f;
-  for (int r = blockIdx.y; r < R; r += gridDim.y) s += dy[(size_t)r * N + c];
-  atomicAdd(&db[c], alpha * s);
+// block (32, 8): thread (tx, ty) sums 4 adjacent columns over rows ty, ty + 8 * gridDim.y, ... (float4 loads, four
+// rows in flight), the 8 partial sums of a column group are combined in shared memory, one atomicAdd per column
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, float* __restrict__ db, int R, int N,
+                                                     float alpha) {
+  __shared__ float4 part[8][32];
+  const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < N) {
+    const int step = 8 * gridDim.y;
+    int r = blockIdx.y * 8 + threadIdx.y;
+    for (; r + 3 * step < R; r += 4 * step) {
+      const float4 a = *reinterpret_cast<const float4*>(dy + (size_t)r * N + c4);
+      const float4 b = *reinterpret_cast<const float4*>(dy + (size_t)(r + step) * N + c4);
+      const float4 c = *reinterpret_cast<const float4*>(dy + (size_t)(r + 2 * step) * N + c4);
+      const float4 d = *reinterpret_cast<const float4*>(dy + (size_t)(r + 3 * step) * N + c4);
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < R; r += step) {
+      const float4 a = *reinterpret_cast<const float4*>(dy + (size_t)r * N + c4);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c4 < N) {
+    for (int t = 1; t < 8; ++t) {
+      const float4 p = part[t][threadIdx.x];
+      acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+    }
+    atomicAdd(&db[c4 + 0], alpha * acc.x);
+    atomicAdd(&db[c4 + 1], alpha * acc.y);
+    atomicAdd(&db[c4 + 2], alpha * acc.z);
+    atomicAdd(&db[c4 + 3], alpha * acc.w);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -173,71 +203,146 @@ __global__ void scatter_add_rows_kernel(const float* __restrict__ src, const int
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// softmax attention, plain layout, one CTA per (sequence, head), one warp per query row at a time.
-//   q row (s, i): q[(s * Tq + i) * q_ld + h * hd ...]; k / v row (s, j) likewise with Tk, k_ld / v_ld.
+// softmax attention, plain layout: q row (s, i) at q[(s * Tq + i) * q_ld + h * hd ...], k / v row (s, j) likewise.
+// Three kernels, one warp per row, no atomics and nothing quadratic stored:
+//   forward      (per query row i): p = softmax(q_i K^T * scale), o_i = p V, lse_i = log sum exp
+//   backward dQ  (per query row i): p recomputed from lse, dP_j = do_i . v_j, D_i = sum_j p_j dP_j (stored),
+//                                   dS_j = p_j (dP_j - D_i) * scale, dq_i += dS K
+//   backward dKV (per key row j):   the same p_ij / dS_ij for all i, dk_j += dS^T Q, dv_j += P^T dO
+// A CTA handles kRowsPerCta consecutive rows of one (sequence, head), its four warps taking rows in turn.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kAttnWarps = 4;
+constexpr int kRowsPerCta = 16;
 
-template <bool BWD>
+__device__ __forceinline__ float dot_row16(const act_t* __restrict__ a, const act_t* __restrict__ b, int hd) {
+  float acc = 0.f;
+  for (int d = 0; d < hd; d += 8) {
+    const uint4 ua = *reinterpret_cast<const uint4*>(a + d), ub = *reinterpret_cast<const uint4*>(b + d);
+    const float2 a0 = unpack_act(ua.x), a1 = unpack_act(ua.y), a2 = unpack_act(ua.z), a3 = unpack_act(ua.w);
+    const float2 b0 = unpack_act(ub.x), b1 = unpack_act(ub.y), b2 = unpack_act(ub.z), b3 = unpack_act(ub.w);
+    acc += a0.x * b0.x + a0.y * b0.y + a1.x * b1.x + a1.y * b1.y + a2.x * b2.x + a2.y * b2.y + a3.x * b3.x + a3.y * b3.y;
+  }
+  return acc;
+}
+__device__ __forceinline__ float dot_row_f32_16(const float* __restrict__ a, const act_t* __restrict__ b, int hd) {
+  float acc = 0.f;
+  for (int d = 0; d < hd; d += 8) {
+    const float4 x0 = *reinterpret_cast<const float4*>(a + d), x1 = *reinterpret_cast<const float4*>(a + d + 4);
+    const uint4 ub = *reinterpret_cast<const uint4*>(b + d);
+    const float2 b0 = unpack_act(ub.x), b1 = unpack_act(ub.y), b2 = unpack_act(ub.z), b3 = unpack_act(ub.w);
+    acc += x0.x * b0.x + x0.y * b0.y + x0.z * b1.x + x0.w * b1.y + x1.x * b2.x + x1.y * b2.y + x1.z * b3.x + x1.w * b3.y;
+  }
+  return acc;
+}
+
 __global__ void __launch_bounds__(32 * kAttnWarps)
-attn_train_kernel(const act_t* __restrict__ q, int q_ld, const act_t* __restrict__ k, int k_ld, const act_t* __restrict__ v,
-                  int v_ld, act_t* __restrict__ o, int o_ld, const float* __restrict__ d_o, int do_ld,
-                  float* __restrict__ dq, int dq_ld, float* __restrict__ dk, int dk_ld, float* __restrict__ dv, int dv_ld,
-                  int H, int hd, int Tq, int Tk, float scale) {
-  extern __shared__ float smem_p[];            // [kAttnWarps][Tk] probabilities (+ [kAttnWarps][Tk] dS in the backward pass)
-  const int s = blockIdx.x / H, h = blockIdx.x % H;
+attn_fwd_kernel(const act_t* __restrict__ q, int q_ld, const act_t* __restrict__ k, int k_ld, const act_t* __restrict__ v,
+                int v_ld, act_t* __restrict__ o, int o_ld, float* __restrict__ lse, int H, int hd, int Tq, int Tk,
+                float scale) {
+  extern __shared__ float smem_p[];            // [kAttnWarps][Tk]
+  const int blocks_per = (Tq + kRowsPerCta - 1) / kRowsPerCta;
+  const int sh = blockIdx.x / blocks_per, rb = blockIdx.x % blocks_per;
+  const int s = sh / H, h = sh % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* p = smem_p + (size_t)warp * Tk * (BWD ? 2 : 1);
-  float* ds = p + Tk;
-  for (int i = warp; i < Tq; i += kAttnWarps) {
+  float* p = smem_p + (size_t)warp * Tk;
+  const act_t* kb = k + (size_t)s * Tk * k_ld + h * hd;
+  const act_t* vb = v + (size_t)s * Tk * v_ld + h * hd;
+  for (int i = rb * kRowsPerCta + warp; i < Tq && i < (rb + 1) * kRowsPerCta; i += kAttnWarps) {
     const act_t* qi = q + ((size_t)s * Tq + i) * q_ld + h * hd;
-    // scores and softmax
     float mx = -INFINITY;
     for (int j = lane; j < Tk; j += 32) {
-      const act_t* kj = k + ((size_t)s * Tk + j) * k_ld + h * hd;
-      float acc = 0.f;
-      for (int d = 0; d < hd; ++d) acc += act2f(qi[d]) * act2f(kj[d]);
-      acc *= scale;
-      p[j] = acc;
-      mx = fmaxf(mx, acc);
+      const float sc = dot_row16(qi, kb + (size_t)j * k_ld, hd) * scale;
+      p[j] = sc;
+      mx = fmaxf(mx, sc);
     }
     mx = warp_max(mx);
     float sum = 0.f;
     for (int j = lane; j < Tk; j += 32) { const float e = expf(p[j] - mx); p[j] = e; sum += e; }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int j = lane; j < Tk; j += 32) p[j] *= inv;
     __syncwarp();
-    if (!BWD) {
-      for (int d = lane; d < hd; d += 32) {
-        float acc = 0.f;
-        for (int j = 0; j < Tk; ++j) acc += p[j] * act2f(v[((size_t)s * Tk + j) * v_ld + h * hd + d]);
-        o[((size_t)s * Tq + i) * o_ld + h * hd + d] = f2act(acc);
+    for (int d = lane; d < hd; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < Tk; ++j) acc += p[j] * act2f(vb[(size_t)j * v_ld + d]);
+      o[((size_t)s * Tq + i) * o_ld + h * hd + d] = f2act(acc * inv);
+    }
+    if (lane == 0) lse[((size_t)s * H + h) * Tq + i] = mx + logf(sum);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32 * kAttnWarps)
+attn_bwd_dq_kernel(const act_t* __restrict__ q, int q_ld, const act_t* __restrict__ k, int k_ld, const act_t* __restrict__ v,
+                   int v_ld, const float* __restrict__ d_o, int do_ld, const float* __restrict__ lse,
+                   float* __restrict__ dsum, float* __restrict__ dq, int dq_ld, int H, int hd, int Tq, int Tk, float scale) {
+  extern __shared__ float smem_p[];            // [kAttnWarps][2][Tk]: p_j, then p_j dP_j -> dS_j
+  const int blocks_per = (Tq + kRowsPerCta - 1) / kRowsPerCta;
+  const int sh = blockIdx.x / blocks_per, rb = blockIdx.x % blocks_per;
+  const int s = sh / H, h = sh % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pp = smem_p + (size_t)warp * 2 * Tk;
+  float* ds = pp + Tk;
+  const act_t* kb = k + (size_t)s * Tk * k_ld + h * hd;
+  const act_t* vb = v + (size_t)s * Tk * v_ld + h * hd;
+  for (int i = rb * kRowsPerCta + warp; i < Tq && i < (rb + 1) * kRowsPerCta; i += kAttnWarps) {
+    const act_t* qi = q + ((size_t)s * Tq + i) * q_ld + h * hd;
+    const float* doi = d_o + ((size_t)s * Tq + i) * do_ld + h * hd;
+    const float l = lse[((size_t)s * H + h) * Tq + i];
+    float dacc = 0.f;
+    for (int j = lane; j < Tk; j += 32) {
+      const float pj = expf(dot_row16(qi, kb + (size_t)j * k_ld, hd) * scale - l);
+      const float dp = dot_row_f32_16(doi, vb + (size_t)j * v_ld, hd);
+      pp[j] = pj;
+      ds[j] = pj * dp;
+      dacc += pj * dp;
+    }
+    const float D = warp_sum(dacc);
+    if (lane == 0) dsum[((size_t)s * H + h) * Tq + i] = D;
+    for (int j = lane; j < Tk; j += 32) ds[j] = (ds[j] - pp[j] * D) * scale;     // dS_j = p_j (dP_j - D_i) * scale
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float acc = 0.f;
+      for (int j = 0; j < Tk; ++j) acc += ds[j] * act2f(kb[(size_t)j * k_ld + d]);
+      dq[((size_t)s * Tq + i) * dq_ld + h * hd + d] += acc;
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32 * kAttnWarps)
+attn_bwd_dkv_kernel(const act_t* __restrict__ q, int q_ld, const act_t* __restrict__ k, int k_ld, const act_t* __restrict__ v,
+                    int v_ld, const float* __restrict__ d_o, int do_ld, const float* __restrict__ lse,
+                    const float* __restrict__ dsum, float* __restrict__ dk, int dk_ld, float* __restrict__ dv, int dv_ld,
+                    int H, int hd, int Tq, int Tk, float scale) {
+  extern __shared__ float smem_p[];            // [kAttnWarps][2][Tq]: p_ij and dS_ij of the warp's key row
+  const int blocks_per = (Tk + kRowsPerCta - 1) / kRowsPerCta;
+  const int sh = blockIdx.x / blocks_per, rb = blockIdx.x % blocks_per;
+  const int s = sh / H, h = sh % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pp = smem_p + (size_t)warp * 2 * Tq;
+  float* ds = pp + Tq;
+  const act_t* qb = q + (size_t)s * Tq * q_ld + h * hd;
+  const float* dob = d_o + (size_t)s * Tq * do_ld + h * hd;
+  const float* lb = lse + ((size_t)s * H + h) * Tq;
+  const float* Db = dsum + ((size_t)s * H + h) * Tq;
+  for (int j = rb * kRowsPerCta + warp; j < Tk && j < (rb + 1) * kRowsPerCta; j += kAttnWarps) {
+    const act_t* kj = k + ((size_t)s * Tk + j) * k_ld + h * hd;
+    const act_t* vj = v + ((size_t)s * Tk + j) * v_ld + h * hd;
+    for (int i = lane; i < Tq; i += 32) {
+      const float pij = expf(dot_row16(qb + (size_t)i * q_ld, kj, hd) * scale - lb[i]);
+      const float dp = dot_row_f32_16(dob + (size_t)i * do_ld, vj, hd);
+      pp[i] = pij;
+      ds[i] = pij * (dp - Db[i]) * scale;
+    }
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float ak = 0.f, av = 0.f;
+      for (int i = 0; i < Tq; ++i) {
+        ak += ds[i] * act2f(qb[(size_t)i * q_ld + d]);
+        av += pp[i] * dob[(size_t)i * do_ld + d];
       }
-    } else {
-      const float* doi = d_o + ((size_t)s * Tq + i) * do_ld + h * hd;
-      // dP_j = do_i . v_j ; D = sum_j p_j dP_j ; dS_j = p_j (dP_j - D)
-      float dsum = 0.f;
-      for (int j = lane; j < Tk; j += 32) {
-        const act_t* vj = v + ((size_t)s * Tk + j) * v_ld + h * hd;
-        float acc = 0.f;
-        for (int d = 0; d < hd; ++d) acc += doi[d] * act2f(vj[d]);
-        ds[j] = acc;
-        dsum += p[j] * acc;
-      }
-      dsum = warp_sum(dsum);
-      for (int j = lane; j < Tk; j += 32) ds[j] = p[j] * (ds[j] - dsum) * scale;
-      __syncwarp();
-      for (int d = lane; d < hd; d += 32) {
-        float acc = 0.f;
-        const float qd = act2f(qi[d]), dod = doi[d];
-        for (int j = 0; j < Tk; ++j) {
-          acc += ds[j] * act2f(k[((size_t)s * Tk + j) * k_ld + h * hd + d]);
-          atomicAdd(&dk[((size_t)s * Tk + j) * dk_ld + h * hd + d], ds[j] * qd);
-          atomicAdd(&dv[((size_t)s * Tk + j) * dv_ld + h * hd + d], p[j] * dod);
-        }
-        dq[((size_t)s * Tq + i) * dq_ld + h * hd + d] += acc;
-      }
+      dk[((size_t)s * Tk + j) * dk_ld + h * hd + d] += ak;
+      dv[((size_t)s * Tk + j) * dv_ld + h * hd + d] += av;
     }
     __syncwarp();
   }
@@ -328,10 +433,11 @@ int train_gelu_backward(const float* da, const act_t* z, float* dz, size_t n, cu
 }
 int train_colsum(const float* dy, float* db, int R, int N, float alpha, cudaStream_t s) {
   if (R == 0 || N == 0) return 0;
-  int gy = (R + 63) / 64;
-  if (gy > 64) gy = 64;
-  dim3 grid((N + 127) / 128, gy);
-  colsum_kernel<<<grid, 128, 0, s>>>(dy, db, R, N, alpha);
+  VITED_CHECK(N % 4 == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0, "colsum: N=%d must be a multiple of 4, dy 16-byte aligned", N);
+  int gy = (R + 127) / 128;                    // ~16 rows per thread
+  if (gy > 148 * 4) gy = 148 * 4;
+  dim3 grid((N + 127) / 128, gy), block(32, 8);
+  colsum_kernel<<<grid, block, 0, s>>>(dy, db, R, N, alpha);
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -354,22 +460,45 @@ int train_scatter_add_rows(const float* src, const int* idx, float* dst, int n_b
   return 0;
 }
 int train_attention(int backward, const act_t* q, int q_ld, const act_t* k, int k_ld, const act_t* v, int v_ld, act_t* o,
-                    int o_ld, const float* d_o, int do_ld, float* dq, int dq_ld, float* dk, int dk_ld, float* dv, int dv_ld,
-                    int n_seq, int H, int hd, int Tq, int Tk, float scale, cudaStream_t s) {
+                    int o_ld, float* lse, const float* d_o, int do_ld, float* dsum, float* dq, int dq_ld, float* dk, int dk_ld,
+                    float* dv, int dv_ld, int n_seq, int H, int hd, int Tq, int Tk, float scale, cudaStream_t s) {
   if (n_seq == 0) return 0;
-  const size_t smem = (size_t)kAttnWarps * Tk * sizeof(float) * (backward ? 2 : 1);
-  VITED_CHECK(smem <= 200 * 1024, "train attention: %d keys need %zu bytes of shared memory", Tk, smem);
+  static const int simt = [] { const char* e = getenv("VITED_TRAIN_ATTN_SIMT"); return e ? atoi(e) : 0; }();
+  VITED_CHECK(hd % 8 == 0 && q_ld % 8 == 0 && k_ld % 8 == 0 && v_ld % 8 == 0, "train attention: head_dim / strides must be multiples of 8");
+  VITED_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
+              "train attention: q / k / v must be 16-byte aligned");
+  if (!simt && train_attention_wmma_supported(hd)) {
+    VITED_CHECK(o && lse && o_ld % 8 == 0, "train attention: the tensor-core path needs o (also in the backward pass) and lse");
+    if (backward)
+      VITED_CHECK(d_o && dsum && dq && dk && dv && do_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d_o) & 15) == 0,
+                  "train attention backward: bad arguments");
+    return train_attention_wmma(backward, q, q_ld, k, k_ld, v, v_ld, o, o_ld, lse, d_o, do_ld, dsum, dq, dq_ld, dk, dk_ld, dv,
+                                dv_ld, n_seq, H, hd, Tq, Tk, scale, s);
+  }
+  const int tmax = Tq > Tk ? Tq : Tk;
+  const size_t smem = (size_t)kAttnWarps * 2 * tmax * sizeof(float);
+  VITED_CHECK(smem <= 200 * 1024, "train attention: %d tokens need %zu bytes of shared memory", tmax, smem);
   static PerDeviceOnce once;
   if (once.first()) {
-    VITED_CUDA_OK(cudaFuncSetAttribute(attn_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VITED_CUDA_OK(cudaFuncSetAttribute(attn_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
-  if (backward)
-    attn_train_kernel<true><<<n_seq * H, 32 * kAttnWarps, smem, s>>>(q, q_ld, k, k_ld, v, v_ld, o, o_ld, d_o, do_ld, dq, dq_ld,
-                                                                    dk, dk_ld, dv, dv_ld, H, hd, Tq, Tk, scale);
-  else
-    attn_train_kernel<false><<<n_seq * H, 32 * kAttnWarps, smem, s>>>(q, q_ld, k, k_ld, v, v_ld, o, o_ld, d_o, do_ld, dq, dq_ld,
-                                                                     dk, dk_ld, dv, dv_ld, H, hd, Tq, Tk, scale);
+  const int qblocks = n_seq * H * ((Tq + kRowsPerCta - 1) / kRowsPerCta);
+  const int kblocks = n_seq * H * ((Tk + kRowsPerCta - 1) / kRowsPerCta);
+  if (!backward) {
+    VITED_CHECK(o && lse, "train attention forward: null output");
+    attn_fwd_kernel<<<qblocks, 32 * kAttnWarps, (size_t)kAttnWarps * Tk * sizeof(float), s>>>(q, q_ld, k, k_ld, v, v_ld, o, o_ld,
+                                                                                              lse, H, hd, Tq, Tk, scale);
+  } else {
+    VITED_CHECK(d_o && lse && dsum && dq && dk && dv && do_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d_o) & 15) == 0,
+                "train attention backward: bad arguments");
+    attn_bwd_dq_kernel<<<qblocks, 32 * kAttnWarps, (size_t)kAttnWarps * 2 * Tk * sizeof(float), s>>>(
+        q, q_ld, k, k_ld, v, v_ld, d_o, do_ld, lse, dsum, dq, dq_ld, H, hd, Tq, Tk, scale);
+    VITED_CUDA_OK(cudaGetLastError());
+    attn_bwd_dkv_kernel<<<kblocks, 32 * kAttnWarps, (size_t)kAttnWarps * 2 * Tq * sizeof(float), s>>>(
+        q, q_ld, k, k_ld, v, v_ld, d_o, do_ld, lse, dsum, dk, dk_ld, dv, dv_ld, H, hd, Tq, Tk, scale);
+  }
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -57,10 +57,30 @@ class _Ops:
         self.grads = {}
         self.w16, self.w16t = {}, {}
         self.launches = 0
+        self.profile = None          # {op name: [events]} when train_step(profile=True): per-kernel-class device time
+        self._last = None
 
     def _chk(self, status, what):
         self.launches += 1
         _lib.check(status, what)
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(torch.cuda.current_stream(self.dev))
+            self.profile.append((what, self._last, ev))
+            self._last = ev
+
+    def profile_begin(self):
+        self.profile = []
+        self._last = torch.cuda.Event(enable_timing=True)
+        self._last.record(torch.cuda.current_stream(self.dev))
+
+    def profile_read(self):
+        torch.cuda.synchronize(self.dev)
+        out = {}
+        for what, a, b in self.profile:
+            ms, n = out.get(what, (0.0, 0))
+            out[what] = (ms + a.elapsed_time(b), n + 1)
+        return {k: {'ms': round(v[0], 3), 'launches': v[1]} for k, v in sorted(out.items(), key=lambda kv: -kv[1][0])}
 
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(shape, dtype=dtype, device=self.dev)
@@ -185,15 +205,21 @@ class _LayerNorm:
                                                   d, 1.0 / ops.S, ops.stream), 'train_ln_backward')
 
 
-def _attention(ops, backward, q, k, v, n_seq, heads, hd, tq, tk, d_o=None, dq=None, dk=None, dv=None):
-    """q / k / v: 16-bit 2-D views (row stride = their leading dimension). Forward returns o16 [n_seq * tq, heads * hd]."""
+def _attention(ops, backward, q, k, v, n_seq, heads, hd, tq, tk, o=None, lse=None, d_o=None, dq=None, dk=None, dv=None):
+    """q / k / v: 16-bit 2-D views (row stride = their leading dimension). Forward returns (o16 [n_seq * tq, heads * hd],
+    lse [n_seq, heads, tq]); the backward pass recomputes the probabilities from lse and takes the forward output o
+    (D_i = do_i . o_i)."""
     scale = hd ** -0.5
-    o = None if backward else ops.empty(n_seq * tq, heads * hd, dtype=ops.act)
+    if not backward:
+        o = ops.empty(n_seq * tq, heads * hd, dtype=ops.act)
+    if not backward:
+        lse = ops.empty(n_seq, heads, tq)
+    dsum = ops.empty(n_seq, heads, tq) if backward else None
     ld = lambda t: t.stride(0) if t is not None else 0
     ops._chk(_lib.lib.vited_train_attention(1 if backward else 0, _p(q), ld(q), _p(k), ld(k), _p(v), ld(v), _p(o), ld(o),
-                                            _p(d_o), ld(d_o), _p(dq), ld(dq), _p(dk), ld(dk), _p(dv), ld(dv), n_seq, heads, hd,
-                                            tq, tk, scale, ops.stream), 'train_attention')
-    return o
+                                            _p(lse), _p(d_o), ld(d_o), _p(dsum), _p(dq), ld(dq), _p(dk), ld(dk), _p(dv), ld(dv),
+                                            n_seq, heads, hd, tq, tk, scale, ops.stream), 'train_attention')
+    return o, lse
 
 
 class _SelfAttn:
@@ -212,7 +238,7 @@ class _SelfAttn:
         h16 = self.norm.forward(x32)
         self.qkv16 = self.qkv.forward(h16)                        # [R, 3D]: q | k | v
         q, k, v = self.qkv16[:, :d], self.qkv16[:, d:2 * d], self.qkv16[:, 2 * d:]
-        o16 = _attention(ops, False, q, k, v, self.n_seq, self.heads, self.hd, self.t, self.t)
+        o16, self.lse = _attention(ops, False, q, k, v, self.n_seq, self.heads, self.hd, self.t, self.t)
         y16 = self.proj.forward(o16)
         out = ops.to_f32(y16)
         return ops.add_(out, x32)                                 # residual
@@ -223,8 +249,8 @@ class _SelfAttn:
         do32 = self.proj.backward(dout32)
         dqkv = ops.zeros(dout32.shape[0], 3 * d)
         q, k, v = self.qkv16[:, :d], self.qkv16[:, d:2 * d], self.qkv16[:, 2 * d:]
-        _attention(ops, True, q, k, v, self.n_seq, self.heads, self.hd, self.t, self.t, d_o=do32, dq=dqkv[:, :d],
-                   dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
+        _attention(ops, True, q, k, v, self.n_seq, self.heads, self.hd, self.t, self.t, o=self.proj.x16, lse=self.lse, d_o=do32,
+                   dq=dqkv[:, :d], dk=dqkv[:, d:2 * d], dv=dqkv[:, 2 * d:])
         dh32 = self.qkv.backward(dqkv)
         dx32 = dout32.clone()                                     # residual path (device copy: plumbing)
         self.norm.backward(dh32, dx32)
@@ -248,8 +274,8 @@ class _CrossAttn:
         self.hd = d // self.heads
         self.q16 = self.q.forward(self.norm_x.forward(x32))
         self.kv16 = self.kv.forward(self.norm_c.forward(ctx32))   # [P * Ne, 2D]: k | v
-        o16 = _attention(ops, False, self.q16, self.kv16[:, :d], self.kv16[:, d:], self.n_seq, self.heads, self.hd, self.tq,
-                         self.tk)
+        o16, self.lse = _attention(ops, False, self.q16, self.kv16[:, :d], self.kv16[:, d:], self.n_seq, self.heads, self.hd,
+                                   self.tq, self.tk)
         out = ops.to_f32(self.proj.forward(o16))
         return ops.add_(out, x32)
 
@@ -260,7 +286,7 @@ class _CrossAttn:
         dq = ops.zeros(*self.q16.shape)
         dkv = ops.zeros(*self.kv16.shape)
         _attention(ops, True, self.q16, self.kv16[:, :d], self.kv16[:, d:], self.n_seq, self.heads, self.hd, self.tq, self.tk,
-                   d_o=do32, dq=dq, dk=dkv[:, :d], dv=dkv[:, d:])
+                   o=self.proj.x16, lse=self.lse, d_o=do32, dq=dq, dk=dkv[:, :d], dv=dkv[:, d:])
         dx32 = dout32.clone()
         self.norm_x.backward(self.q.backward(dq), dx32)
         self.norm_c.backward(self.kv.backward(dkv), dctx32)       # accumulates into the context gradient
@@ -307,12 +333,32 @@ def _scatter_add(ops, src32, idx, n_blocks, rows_per, src_stride, src_off, dst, 
                                                    dst_stride, dst_off, d, alpha, ops.stream), 'train_scatter_add_rows')
 
 
+def all_reduce_gradients(model):
+    """DistributedDataParallel's gradient averaging (the reference wraps the model in DDP, misc/engine.py:74-77): one
+    NCCL all-reduce over a single flat fp32 bucket of every parameter gradient, then 1 / world. No-op without an
+    initialised process group. (The overlap of this collective with the backward pass is not built.)"""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    params = [p for p in model.parameters() if p.grad is not None]
+    flat = torch.cat([p.grad.reshape(-1).float() for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+
+
 @torch.no_grad()
-def train_step(model, samples, targets, generator=None, loss_scale=1024.0, groups=None, labels=None):
+def train_step(model, samples, targets, generator=None, loss_scale=1024.0, groups=None, labels=None, all_reduce=True,
+               profile=False):
     """One training step of HisfragTrainer without the optimiser (hisfrag.py:117-159): the pairs of the batch, the
     forward ``model(tokens[groups[:, 1]], samples[groups[:, 0]])`` with the encoder in the graph, ``BCEWithLogitsLoss``,
     and the backward pass to every parameter. Returns (loss, logits [P, C], groups, labels) and leaves the gradients in
-    ``p.grad`` of the model's parameters (fp32), as ``loss.backward()`` would. Dropout / stochastic depth are not
+    ``p.grad`` of the model's parameters (fp32), as ``loss.backward()`` would -- averaged over the ranks of an
+    initialised process group when ``all_reduce`` (what DistributedDataParallel does). Dropout / stochastic depth are not
     modelled (the reference's DROP_PATH_RATE would have to be 0)."""
     if not (isinstance(samples, torch.Tensor) and samples.is_cuda):
         raise _lib.VitedError('train_step runs on CUDA (sm_100a) tensors only; there is no CPU fallback')
@@ -320,12 +366,17 @@ def train_step(model, samples, targets, generator=None, loss_scale=1024.0, group
     if groups is None:
         groups, labels = prepare_pairs(targets, generator)
     with torch.cuda.device(dev):
-        return _train_step(model, samples.float().contiguous(), groups, labels, loss_scale)
+        out = _train_step(model, samples.float().contiguous(), groups, labels, loss_scale, profile)
+        if all_reduce:
+            all_reduce_gradients(model)
+        return out
 
 
-def _train_step(model, samples, groups, labels, loss_scale):
+def _train_step(model, samples, groups, labels, loss_scale, profile=False):
     dev = samples.device
     ops = _Ops(dev, loss_scale)
+    if profile:
+        ops.profile_begin()
     sd = {k: v.detach().float().contiguous() for k, v in model.state_dict().items()}
     if next(iter(sd.values())).device != dev:
         raise _lib.VitedError('model parameters and samples are on different devices; call model.cuda()')
@@ -420,4 +471,5 @@ def _train_step(model, samples, groups, labels, loss_scale):
         g = ops.grads.get(name)
         p.grad = torch.zeros_like(p) if g is None else g.view_as(p).to(p.dtype)
     model.train_launches = ops.launches
+    model.train_profile = ops.profile_read() if profile else None   # time between consecutive calls, by entry point
     return loss[0], logits, groups, labels
