@@ -141,10 +141,14 @@ def test_gemm_cta_pair_variant():
 
 
 def test_gemm_quad_cluster_variant():
-    """The opt-in 4-CTA-cluster kernel (two cta_group::2 pairs sharing TMA-multicast weight tiles) against torch,
-    including an odd number of 256-row blocks (the second pair of the last cluster computes on zero-filled rows)."""
+    """The 4-CTA-cluster kernel (two cta_group::2 pairs sharing TMA-multicast weight tiles; a measured negative result
+    that only exists in -DVITED_EXPERIMENTAL builds, tools/build_variants.sh) against torch, including an odd number of
+    256-row blocks (the second pair of the last cluster computes on zero-filled rows)."""
     import subprocess, sys, os
     from tests.conftest import ROOT
+    lib = os.path.join(ROOT, 'tools', 'bin', 'experimental', 'libvited_b200.so')
+    if not os.path.exists(lib):
+        pytest.skip('no experimental build (tools/build_variants.sh)')
     code = (
         "import torch, math, sys; sys.path.insert(0, %r)\n"
         "from vited_b200 import _lib as L\n"
@@ -162,7 +166,7 @@ def test_gemm_quad_cluster_variant():
         "    assert not bad.any(), (M, N, K, int(bad.sum()), float(err.max()), bad.nonzero()[0].tolist())\n"
         "    print('ok', M, N, K, float(err.max()))\n"
     ) % ROOT
-    env = dict(os.environ, VITED_GEMM_QUAD='1')
+    env = dict(os.environ, VITED_GEMM_QUAD='1', VITED_LIB=lib)
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 

@@ -534,6 +534,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+#ifdef VITED_EXPERIMENTAL   // measured negative results, kept as a record (profiles/README.md): not in the product library
 // =====================================================================================================================
 // Quad variant: a cluster of FOUR CTAs = two cta_group::2 pairs that compute two different 256-row tiles against the
 // SAME weight tile. Every GEMM of the step moves 7.5-9.4 TB/s through L2 (profiles/): the weight tile is re-read from L2
@@ -729,6 +730,8 @@ static int launch_quad(const CUtensorMap& tA, const CUtensorMap& tB, const CUten
   return 0;
 }
 
+#endif  // VITED_EXPERIMENTAL
+
 template <int BN, int ACT>
 static int launch_pair(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const float* bias, int M,
                        int N, int K, cudaStream_t stream) {
@@ -782,9 +785,11 @@ int gemm_simt(const act_t* A, const act_t* W, const float* bias, act_t* C, int M
               cudaStream_t stream);
 
 static int g_block_n = 0;   // 0 = unread; VITED_GEMM_BN=128|192|256 overrides the automatic tile width (tuning knob)
-static int g_quad = -1;     // VITED_GEMM_QUAD=1 enables the 4-CTA-cluster kernel with multicast weight tiles (large M)
 static int g_pair = -1;     // VITED_GEMM_PAIR=0 disables the CTA-pair (cta_group::2) kernel (used for large M by default)
-static int g_resident = -1; // VITED_GEMM_RESIDENT=1 enables the resident-weights variant (measured slower: off by default)
+#ifdef VITED_EXPERIMENTAL
+static int g_quad = -1;     // VITED_GEMM_QUAD=1 enables the 4-CTA-cluster kernel with multicast weight tiles (large M)
+static int g_resident = -1; // VITED_GEMM_RESIDENT=1 enables the resident-weights variant (measured slower)
+#endif
 
 int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M, int N, int K, int act, int impl,
               cudaStream_t stream) {
@@ -800,19 +805,25 @@ int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M,
   if (g_block_n == 0) {
     const char* e = getenv("VITED_GEMM_BN");
     g_block_n = e ? atoi(e) : -1;
+#ifdef VITED_EXPERIMENTAL
     const char* r = getenv("VITED_GEMM_RESIDENT");
     g_resident = r ? atoi(r) : 0;
+    const char* qd = getenv("VITED_GEMM_QUAD");
+    g_quad = qd ? atoi(qd) : 0;
+#endif
     const char* o = getenv("VITED_GEMM_ORDER");
     g_order = o ? atoi(o) : 0;
     const char* pr = getenv("VITED_GEMM_PAIR");
     g_pair = pr ? atoi(pr) : 1;
-    const char* qd = getenv("VITED_GEMM_QUAD");
-    g_quad = qd ? atoi(qd) : 0;
   }
   const int m_blks = (M + BM - 1) / BM;
   // resident weights: K <= 384, 128-wide panels, and enough m-blocks per panel to amortise loading it
+#ifdef VITED_EXPERIMENTAL
   const bool resident = g_resident && g_block_n < 0 && K <= 384 && N % 128 == 0 && N / 128 <= 16 &&
                         m_blks >= 4 * (g_num_sms / (N / 128));
+#else
+  const bool resident = false;   // the resident-weights instantiation (KB_RES = 6) exists in -DVITED_EXPERIMENTAL builds only
+#endif
   int bn = 128;
   if (!resident) {
     if (g_block_n == 128 || g_block_n == 192 || g_block_n == 256) bn = g_block_n;
@@ -823,6 +834,7 @@ int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M,
   if (make_tmap(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, BM)) return 1;
   if (g_pair && g_block_n != 128 && m_blks >= 2 * g_num_sms && (N % 256 == 0 || N % 192 == 0)) {
     const int pbn = (g_block_n == 192 || g_block_n == 256) ? g_block_n : (N % 256 == 0 ? 256 : 192);
+#ifdef VITED_EXPERIMENTAL
     if (g_quad && m_blks >= 4 * g_num_sms) {
       if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)pbn / 4)) return 1;
       if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
@@ -832,6 +844,7 @@ int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M,
       return act == ACT_GELU ? launch_quad<192, ACT_GELU>(tA, tB, tC, bias, M, N, K, stream)
                              : launch_quad<192, ACT_NONE>(tA, tB, tC, bias, M, N, K, stream);
     }
+#endif
     if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)pbn / 2)) return 1;
     if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
     if (pbn == 256)
@@ -842,7 +855,9 @@ int gemm_act(const act_t* A, const act_t* W, const float* bias, act_t* C, int M,
   }
   if (make_tmap(&tB, W, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, (uint32_t)bn)) return 1;
   if (make_tmap(&tC, C, (uint64_t)N, (uint64_t)M, (uint64_t)N * 2, 32)) return 1;
+#ifdef VITED_EXPERIMENTAL
   if (resident) return launch_act<128, 6>(tA, tB, tC, bias, M, N, K, act, stream);
+#endif
   if (bn == 128) return launch_act<128, 0>(tA, tB, tC, bias, M, N, K, act, stream);
   if (bn == 256) return launch_act<256, 0>(tA, tB, tC, bias, M, N, K, act, stream);
   return launch_act<192, 0>(tA, tB, tC, bias, M, N, K, act, stream);
