@@ -305,3 +305,58 @@ def test_context_rows_in_several_kv_blocks(name, mode, n):
     # the blocks really were smaller than the grid: K/V bytes per item x n exceeds the budget
     ne = (kw['img_size'] // kw['patch_size']) ** 2
     assert kw['c_depth'] * ne * 2 * kw['embed_dim'] * 2 * n > 1_000_000
+
+
+def test_full_size_puzzle_grid_properties():
+    """BASELINE configs[1] at full size (540 pieces = 291,060 ordered pairs, 37 chunks of 7,867 pairs through the fused
+    kernels), checked through size-independent properties: every off-diagonal entry written and finite, the diagonal
+    untouched, the grid deterministic bit for bit, a row shard bit-identical to the same rows of the full grid, and
+    sampled entries equal to the pair-wise API (model(pairs)) up to the rounding of the small-batch path."""
+    import vited_b200
+    from vited_b200 import grid, pieces, synthetic
+    model = vited_b200.build_model(vited_b200.get_config('puzzle'))
+    model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0), strict=True)
+    model = model.cuda().eval()
+    img = synthetic.synthetic_puzzle_image(18, 30, piece=64, seed=0)
+    images, (rows, cols) = pieces.prepare_pieces_device(img, 64, 0.07, 64)
+    n = rows * cols
+    assert n == 540
+    full = grid.score_puzzle(model, images)
+    again = grid.score_puzzle(model, images)
+    assert torch.equal(full, again), 'the grid is not deterministic'
+    assert torch.isfinite(full).all()
+    off = ~torch.eye(n, dtype=torch.bool, device='cuda')
+    assert (full[off] != 0).any(dim=-1).all(), 'an off-diagonal pair was left unwritten'
+    assert float(full.diagonal(dim1=0, dim2=1).abs().max()) == 0.0
+    part = model.score_grid(images, vited_b200.GRID_ORDERED_OFFDIAG, 301, 339)
+    # a shard runs other chunk sizes than the full grid (equal chunks of ITS pair count): same kernels, same rows
+    np.testing.assert_allclose(part.cpu().numpy(), full[301:339].cpu().numpy(), rtol=0, atol=2e-3)
+    g = torch.Generator().manual_seed(11)
+    pi = torch.randint(0, n, (256,), generator=g)
+    pj = (pi + 1 + torch.randint(0, n - 1, (256,), generator=g)) % n
+    direct = model(torch.stack([images[pi], images[pj]], dim=1))
+    np.testing.assert_allclose(direct.cpu().numpy(), full[pi, pj].cpu().numpy(), rtol=0, atol=1e-2)
+
+
+def test_fragment_grid_properties_hisfrag_model():
+    """The real Hisfrag20 model on 40 fragments (820 pairs a <= b, two chunks, every fused kernel): the matrix is
+    symmetric, deterministic, a row shard of the upper triangle reproduces the full one, the lower triangle of a shard's
+    block stays untouched, and sampled entries equal the two-phase API (encode, then decode) on the same pairs."""
+    import vited_b200
+    from vited_b200 import grid, synthetic
+    z, kw = helpers.load_model_case('hisfrag20_patch16_512')
+    model, _ = helpers.make_gpu_model(kw, 0)
+    n = 40
+    images = synthetic.synthetic_images(n, kw['img_size'], seed=77).cuda()
+    sim = grid.score_fragments(model, images)
+    assert torch.equal(sim, sim.t()) and torch.isfinite(sim).all()
+    assert torch.equal(sim, grid.score_fragments(model, images)), 'the grid is not deterministic'
+    part = model.score_grid(images, vited_b200.GRID_UPPER_TRI_DIAG, 10, 25)[..., 0]
+    keep = torch.triu(torch.ones(n, n, dtype=torch.bool, device='cuda'))[10:25]
+    assert float(part[~keep].abs().max()) == 0.0
+    np.testing.assert_allclose(part[keep].cpu().numpy(), sim[10:25][keep].cpu().numpy(), rtol=0, atol=2e-3)
+    a = torch.tensor([0, 3, 17, 17, 39, 8])
+    b = torch.tensor([0, 30, 17, 21, 39, 33])
+    tokens = model(images[a], forward_first_part=True)
+    direct = model(tokens, images[b])[:, 0]
+    np.testing.assert_allclose(direct.cpu().numpy(), sim[a, b].cpu().numpy(), rtol=0, atol=1e-2)

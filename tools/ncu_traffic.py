@@ -37,7 +37,8 @@ for l in want:
     wr = to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
     out[l['cls']] = dict(kernel=r[col['Kernel Name']][:80], dram_bytes=rd + wr, dram_read=rd, dram_write=wr,
                          algorithmic_bytes=l['algorithmic_bytes'], ratio=(rd + wr) / l['algorithmic_bytes'],
-                         duration_us=float(r[col['gpu__time_duration.sum']]),
+                         duration_us=float(r[col['gpu__time_duration.sum']]) *
+                         {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(units[col['gpu__time_duration.sum']], 1.0),
                          tensor_pipe_pct=float(r[col['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']]))
 json.dump(dict(source=f'ncu --set full --clock-control none of tools/profile_ops.py at {manifest["rows"]} rows per launch '
                       f'({rep.split("/")[-1]}); dram__bytes_read.sum + dram__bytes_write.sum per launch',
