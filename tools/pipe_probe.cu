@@ -33,6 +33,12 @@ __global__ void probe(float* out, long long* cyc, int iters) {
     } else if (MODE == 2) {
 #pragma unroll
       for (int i = 0; i < 16; i += 2) { uint32_t o; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o) : "f"(x[i]), "f"(x[i + 1])); x[i] = __uint_as_float(o); }
+    } else if (MODE == 6) {   // ex2 on packed fp16 pairs: two exponentials per MUFU instruction?
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { uint32_t u = __float_as_uint(x[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u)); x[i] = __uint_as_float(u); }
+    } else if (MODE == 7) {   // HADD2
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { uint32_t u = __float_as_uint(x[i]); asm volatile("add.rn.f16x2 %0, %0, %0;" : "+r"(u)); x[i] = __uint_as_float(u); }
     } else if (MODE == 3) {
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
@@ -80,6 +86,8 @@ void run(const char* name, int per_iter_ops, int bytes_per_op) {
 }
 int main() {
   run<0>("MUFU.EX2", 16, 0);
+  run<6>("EX2.F16x2", 16, 0);
+  run<7>("HADD2", 16, 0);
   run<1>("FFMA", 16, 0);
   run<2>("F2FP", 8, 0);
   run<3>("LDTM.x32", 1, 4096);
