@@ -2,6 +2,7 @@
 16-bit-rounded operands; fp16 unless the library was built with -DVITED_ACT_BF16=1). Tolerances are stated per test."""
 import ctypes
 import math
+import os
 
 import pytest
 import torch
@@ -193,10 +194,21 @@ def test_resid_ln(D, has_cls):
     assert (h.float() - h_ref).abs().max().item() <= (1e-2 * h_ref.abs().max().item() + 1e-3) * _r16()
 
 
+def _epi_variant(epi_warps, monkeypatch):
+    """The 16-warp (four column groups) form of the two full-row epilogues is a measured-neutral variant that only exists
+    in -DVITED_EXPERIMENTAL builds (tools/build_variants.sh; select with VITED_LIB=tools/bin/experimental/...)."""
+    if epi_warps == '16' and 'experimental' not in os.environ.get('VITED_LIB', ''):
+        pytest.skip('16 epilogue warps: experimental build only (VITED_LIB=tools/bin/experimental/libvited_b200.so)')
+    monkeypatch.setenv('VITED_EPI_WARPS', epi_warps)
+
+
 @pytest.mark.parametrize('shape', [(256, 384), (70000, 384), (33333, 1536), (1, 384), (300, 64), (40000, 192)],
                          ids=lambda s: 'x'.join(map(str, s)))
-def test_gemm_resid_ln_fused(shape):
-    """x += A W^T + b; h = LayerNorm(x): the fused tcgen05 epilogue against fp32 torch on the same 16-bit operands."""
+@pytest.mark.parametrize('epi_warps', ['8', '16'])
+def test_gemm_resid_ln_fused(shape, epi_warps, monkeypatch):
+    """x += A W^T + b; h = LayerNorm(x): the fused tcgen05 epilogue against fp32 torch on the same 16-bit operands,
+    in both epilogue forms (8 warps x 192-column half rows, 16 warps x 96-column quarter rows)."""
+    _epi_variant(epi_warps, monkeypatch)
     L = _lib()
     M, K = shape
     N = 384
@@ -223,10 +235,13 @@ def test_gemm_resid_ln_fused(shape):
 
 @pytest.mark.parametrize('shape', [(256, 1536), (70000, 1536), (33333, 1536), (1, 1536), (300, 64), (40000, 192),
                                    (262144 + 77, 1536)], ids=lambda s: 'x'.join(map(str, s)))
-def test_mlp_resid_ln_fused(shape):
+@pytest.mark.parametrize('epi_warps', ['8', '16'])
+def test_mlp_resid_ln_fused(shape, epi_warps, monkeypatch):
     """x += fc2(GELU(fc1(h))) + b2; h = LayerNorm(x): the fused MLP kernel (hidden activations kept in TMEM, GELU
     output fed to the second MMA as its A operand from TMEM) against fp32 torch on the same 16-bit operands, with the
-    hidden activations rounded to 16 bits where the kernel rounds them. In place: h_out aliases h_in."""
+    hidden activations rounded to 16 bits where the kernel rounds them. In place: h_out aliases h_in. Both epilogue
+    forms (VITED_EPI_WARPS = 8 / 16)."""
+    _epi_variant(epi_warps, monkeypatch)
     L = _lib()
     M, HID = shape
     D = 384
@@ -322,6 +337,18 @@ def test_cross_attention(cfg, impl):
     got = torch.cat([o[P * n_patch:].view(P, 1, D), o[:P * n_patch].view(P, n_patch, D)], dim=1).float()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
+
+
+@pytest.mark.parametrize('cfg', [(40, 6, 64, 1024, 1), (1, 1, 64, 256, 1), (30, 2, 64, 256, 1), (3, 6, 64, 1024, 1)],
+                         ids=lambda c: 'x'.join(map(str, c)))
+def test_long_attention_class_token_as_work_item(cfg, monkeypatch):
+    """The long-sequence tcgen05 kernel computes the class-token query rows on four CUDA-core warps by default (covered by
+    test_self_attention / test_cross_attention); VITED_L64_CLS_WARPS=0 selects the earlier form -- the class-token query
+    as an extra work item of the tile pipeline -- which must give the same rows."""
+    monkeypatch.setenv('VITED_L64_CLS_WARPS', '0')
+    test_self_attention(cfg, 0)
+    n_seq, H, hd, n_patch, _ = cfg
+    test_cross_attention((n_seq, max(1, n_seq // 3), H, hd, n_patch), 0)
 
 
 @pytest.mark.parametrize('cfg', [(3, 3, 64, 8), (2, 3, 512, 16), (5, 3, 64, 32)])

@@ -45,8 +45,10 @@ def main():
     st = None
     M = 4032 * 65
     out = []
-    for name, N, K, act in (('qkv', 1152, 384, 0), ('proj', 384, 384, 0), ('fc1_gelu', 1536, 384, 1),
-                            ('fc2', 384, 1536, 0), ('kv', 768, 384, 0)):
+    only = os.environ.get('OPS', 'all')          # OPS=fused: only the two full-row kernels (both epilogue forms)
+    gemm_shapes = (('qkv', 1152, 384, 0), ('proj', 384, 384, 0), ('fc1_gelu', 1536, 384, 1), ('fc2', 384, 1536, 0),
+                   ('kv', 768, 384, 0))
+    for name, N, K, act in (gemm_shapes if only == 'all' else ()):
         A = torch.randn(M, K, device='cuda').to(L.act_dtype())
         W = (torch.randn(N, K, device='cuda') / math.sqrt(K)).to(L.act_dtype())
         b = torch.randn(N, device='cuda')
@@ -60,8 +62,10 @@ def main():
                             gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm, bn=os.environ.get('VITED_GEMM_BN', 'auto')))
         ms = timeit(lambda: torch.matmul(A, W.t(), out=C), flush=flush)
         out.append(dict(op=f'cublas_{name}', M=M, N=N, K=K, ms=ms, tflops=2.0 * M * N * K / ms / 1e9))
-    # fused GEMM + residual + LayerNorm (N = 384)
-    for name, K in (('proj', 384), ('fc2', 1536)):
+    # fused GEMM + residual + LayerNorm (N = 384), both epilogue forms (VITED_EPI_WARPS is read at every launch)
+    default_epi = os.environ.get('VITED_EPI_WARPS')
+    for epi, name, K in [(e, n, k) for e in ('8', '16') for n, k in (('proj', 384), ('fc2', 1536))]:
+        os.environ['VITED_EPI_WARPS'] = epi
         A = torch.randn(M, K, device='cuda').to(L.act_dtype())
         W = (torch.randn(384, K, device='cuda') / math.sqrt(K)).to(L.act_dtype())
         b = torch.randn(384, device='cuda')
@@ -72,7 +76,7 @@ def main():
                                                                   lb.data_ptr(), hh.data_ptr(), M, 384, K, 1e-6, st), 'gemm_ln'), flush=flush)
         fl = 2.0 * M * 384 * K
         by = M * K * 2 + 384 * K * 2 + M * 384 * (4 + 4 + 2)
-        out.append(dict(op=f'gemm_ln_{name}', M=M, N=384, K=K, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+        out.append(dict(op=f'gemm_ln_{name}_epi{epi}', M=M, N=384, K=K, ms=ms, tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
         del A, W, xx, hh
     # fused MLP sub-block + residual + LayerNorm (fc1 -> GELU -> fc2, hidden activations never written)
     hin = torch.randn(M, 384, device='cuda').to(L.act_dtype())
@@ -82,14 +86,25 @@ def main():
     xx = torch.randn(M, 384, device='cuda')
     lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
     hh = torch.empty(M, 384, dtype=L.act_dtype(), device='cuda')
-    ms = timeit(lambda: L.check(L.lib.vited_op_mlp_resid_ln(hin.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
-                                                             xx.data_ptr(), lw.data_ptr(), lb.data_ptr(), hh.data_ptr(), M, 384, 1536,
-                                                             1e-6, st), 'mlp_ln'), flush=flush)
-    fl = 4.0 * M * 384 * 1536
-    by = M * 384 * (2 + 4 + 4 + 2) + 4 * 384 * 1536
-    out.append(dict(op='mlp_ln', M=M, D=384, hidden=1536, ms=ms, tflops=fl / ms / 1e9, tflops_frac=fl / ms / 1e9 / tf,
-                    gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+    for epi in ('8', '16'):
+        os.environ['VITED_EPI_WARPS'] = epi
+        ms = timeit(lambda: L.check(L.lib.vited_op_mlp_resid_ln(hin.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                                                 xx.data_ptr(), lw.data_ptr(), lb.data_ptr(), hh.data_ptr(), M, 384, 1536,
+                                                                 1e-6, st), 'mlp_ln'), flush=flush)
+        fl = 4.0 * M * 384 * 1536
+        by = M * 384 * (2 + 4 + 4 + 2) + 4 * 384 * 1536
+        out.append(dict(op=f'mlp_ln_epi{epi}', M=M, D=384, hidden=1536, ms=ms, tflops=fl / ms / 1e9, tflops_frac=fl / ms / 1e9 / tf,
+                        gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+    if default_epi is None:
+        os.environ.pop('VITED_EPI_WARPS', None)
+    else:
+        os.environ['VITED_EPI_WARPS'] = default_epi
     del hin, xx, hh
+    if only != 'all':
+        for r in out:
+            r['peaks'] = src
+            print(json.dumps(r))
+        return
     # resid + LN
     D = 384
     x = torch.randn(M, D, device='cuda')

@@ -65,6 +65,10 @@ struct PerDeviceOnce {
   }
 };
 int device_sm_count();   // SM count of the CURRENT device (cached per device); gemm_tc.cu
+// Epilogue warps per CTA of the two full-row kernels (gemm_ln.cu, mlp_ln.cu): 8 (two column groups) or, in
+// -DVITED_EXPERIMENTAL builds, 16 (four; measured neutral). VITED_EPI_WARPS=8|16 is read at every launch so that tests
+// and A/B runs can switch in-process.
+int epilogue_warps();    // gemm_tc.cu
 
 #ifdef __CUDACC__
 // Launch `kernel` so that it may overlap the tail of the previous kernel in `stream` (see pdl_wait below). Only for
@@ -385,6 +389,28 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// width-generic forms for the full-row epilogues, which exist with 32- and 16-column chunks (8 / 16 epilogue warps)
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_32x32b_x32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_32x32b_x16(taddr, r); }
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_32x32b_x32(taddr, r); }
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st_32x32b_x16(taddr, r); }
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[8]) { tmem_st_32x32b_x8(taddr, r); }
+// 16-byte chunk i of this lane's row inside a TMA box whose rows are ROWB bytes = the box's swizzle span
+// (128B swizzle: chunk ^ (row & 7); 64B swizzle: chunk ^ ((row >> 1) & 3)); one lane = one row
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz_chunk(int i, int lane) {
+  static_assert(ROWB == 128 || ROWB == 64, "box rows of 128 or 64 bytes");
+  return ROWB == 128 ? (uint32_t)(i ^ (lane & 7)) : (uint32_t)(i ^ ((lane >> 1) & 3));
+}
 // D[tmem] (+)= A[tmem, packed fp16 pairs] * B[smem desc]
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
                                              uint32_t accumulate) {

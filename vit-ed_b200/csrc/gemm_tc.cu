@@ -11,6 +11,7 @@
 //                                             and the 64-column slab sl, stages its 32x64 fp16 sub-tile in a private
 //                                             4 KB swizzled buffer and TMA-stores it itself (no CTA-wide barrier).
 #include "kernels.h"
+#include <cstdlib>
 #include <cudaTypedefs.h>
 #include <mutex>
 
@@ -45,6 +46,12 @@ static void init_driver_once() {
 int gemm_num_sms() {
   std::call_once(g_once, init_driver_once);
   return device_sm_count();
+}
+
+int epilogue_warps() {
+  const char* v = getenv("VITED_EPI_WARPS");
+  if (v != nullptr && v[0] != 0) return atoi(v) == 16 ? 16 : 8;
+  return 8;
 }
 
 // Every launch needs 3-6 tensor maps and a step makes ~7,500 launches over a handful of buffers and shapes that repeat

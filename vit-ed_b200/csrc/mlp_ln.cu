@@ -17,6 +17,9 @@
 //     residual boxes live in the h-tile region, which is dead once fc1 of the last chunk has completed.
 // TMEM: O = columns [0, 384), S buffers [384, 448) and [448, 512). Shared memory: 96 KB h tile / residual boxes,
 // 96 KB weight ring, 16 KB output staging, biases / LayerNorm parameters.
+// Template parameter CG = column groups of the GELU / epilogue warps: 2 (8 warps: 32 hidden columns of a chunk and a
+// 192-column half row each) or 4 (16 warps: 16 hidden columns and a 96-column quarter row each, residual boxes of half
+// the width, weight ring of 6 slots, 32 KB staging) -- same bytes, twice as many independent chains in flight.
 #include "kernels.h"
 
 namespace vited {
@@ -26,24 +29,33 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int LN_N = 384;
-constexpr int NH = 192;          // columns per fc2 MMA / per epilogue half
-constexpr int CHUNKS = NH / 32;  // 32-column epilogue chunks per half row
+constexpr int NH = 192;          // columns per fc2 MMA
 constexpr int HC = 64;           // hidden units per chunk
 constexpr int KB1 = LN_N / BK;   // k-blocks of fc1 (K = 384)
 
+template <int CG>
 struct MlpCfg {
-  static constexpr int kEpiWarps = 8;
+  static_assert(CG == 2 || CG == 4, "two or four column groups");
+  static constexpr int kEpiWarps = 4 * CG;
   static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  static constexpr int NW = LN_N / CG;                                // output columns per epilogue warp: 192 / 96
+  static constexpr int XW = 64 / CG;                                  // columns per residual box: 32 / 16
+  static constexpr int CHUNKS = NW / XW;                              // residual boxes per warp and tile: 6
+  static constexpr int ROWB = XW * 4;                                 // bytes per residual-box row = swizzle span: 128 / 64
+  static constexpr int GW = HC / CG;                                  // hidden columns of a chunk per GELU warp: 32 / 16
   static constexpr uint32_t A_KB_BYTES = BM * BK * 2;                 // one k-block of the h tile: 128 rows x 128 B
   static constexpr uint32_t A_BYTES = KB1 * A_KB_BYTES;               // 96 KB
   static constexpr uint32_t SLOT_BYTES = 12288;                       // 3 k-blocks of W1 (32 rows each) or 96 rows of W2
-  static constexpr int kSlots = 8;   // 6 slots left the issuer waiting for weights 11.6 k of 63 k cycles per tile (trace)
+  // 6 slots left the issuer waiting for weights 11.6 k of 63 k cycles per tile (trace), 8 changed nothing in the step:
+  // the issuer runs ahead of the tensor pipe by the ring depth. The 16-warp form needs the 24 KB for its staging boxes.
+  static constexpr int kSlots = CG == 2 ? 8 : 6;
   static constexpr uint32_t W1_KB_BYTES = (HC / 2) * BK * 2;          // this CTA's 32 rows of one k-block: 4 KB
-  static constexpr uint32_t XBOX = 32 * 32 * 4;                       // 32 rows x 32 fp32, 128B-swizzled
+  static constexpr uint32_t XBOX = 32 * ROWB;                         // 32 rows x XW fp32, hardware-swizzled: 4 KB / 2 KB
   static constexpr uint32_t OUT_BYTES = kEpiWarps * 2048;             // pass-2 staging: 32 rows x 32 fp16 per warp (64B swizzle)
-  static constexpr uint32_t PART_BYTES = 2 * BM * 16;
+  static constexpr uint32_t PART_BYTES = CG * BM * 8;                 // (mean, M2) of every row part
   static constexpr uint32_t BAR_BYTES = 512;
   static_assert(kEpiWarps * 3 * XBOX == A_BYTES, "the residual boxes (2 in + 1 out per warp) reuse the h-tile region");
+  static_assert((2 * kSlots + 9 + 2 * kEpiWarps) * 8 + 4 <= BAR_BYTES, "barrier block");
   static uint32_t smem_bytes(int hidden) {
     return 1024 + A_BYTES + kSlots * SLOT_BYTES + OUT_BYTES + (uint32_t)hidden * 4 + 3 * LN_N * 4 + PART_BYTES + BAR_BYTES;
   }
@@ -60,13 +72,15 @@ __device__ long long g_mlp_trace[2 * 32 * 8];   // [0 = GELU/epilogue warp (q0,c
 #define TRM_CLK() 0ll
 #endif
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MlpCfg::kThreads, 1)
+template <int CG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MlpCfg<CG>::kThreads, 1)
 mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
                    const __grid_constant__ CUtensorMap tmH, const float* __restrict__ b1, const float* __restrict__ b2,
                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, int M, int hidden, float eps) {
-  using Cfg = MlpCfg;
+  using Cfg = MlpCfg<CG>;
   constexpr int kSlots = Cfg::kSlots;
+  constexpr int NW = Cfg::NW, XW = Cfg::XW, CHUNKS = Cfg::CHUNKS, ROWB = Cfg::ROWB, GW = Cfg::GW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                  // h tile; residual boxes during the epilogue
@@ -76,7 +90,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   float* sBias = sB1 + hidden;
   float* sG = sBias + LN_N;
   float* sBt = sG + LN_N;
-  float4* sPart = reinterpret_cast<float4*>(sBt + LN_N);
+  float2* sPart = reinterpret_cast<float2*>(sBt + LN_N);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPart) + Cfg::PART_BYTES);
   uint64_t* w_full = bars;                    // [kSlots] leader CTA: both CTAs' TMA bytes land here
   uint64_t* w_empty = w_full + kSlots;        // [kSlots] per CTA, released by the leader's multicast commit
@@ -87,7 +101,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* g1_done = p_full + 2;             // per CTA (multicast commit): fc1 of the tile's last chunk has read the h tile
   uint64_t* tfull = g1_done + 1;              // per CTA (multicast commit): O complete
   uint64_t* tempty = tfull + 1;               // leader CTA: epilogue warps of BOTH CTAs have drained O
-  uint64_t* xfull = tempty + 1;               // [8 warps][2 boxes]
+  uint64_t* xfull = tempty + 1;               // [epilogue warps][2 boxes]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(xfull + 2 * Cfg::kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
@@ -231,7 +245,8 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         TRM_WAIT(acc_wait_p, mbar_wait(&p_full[b], (pfull_ph >> b) & 1u, 22));
         pfull_ph ^= 1u << b;
         tc_fence_after();
-        // P_c: logical packed columns 0..15 at S + 0 (GELU warps of column half 0), 16..31 at S + 32 (half 1)
+        // P_c: GELU column group g (GW hidden units) leaves its GW / 2 packed columns at S + g * GW, so the 16 hidden
+        // units of k-step k start at column (16k / GW) * GW + (16k % GW) / 2
         const uint32_t a_tmem = tmem_base + kColS + (uint32_t)b * HC;
         for (int hf = 0; hf < 2; ++hf) {
           TRM_WAIT(acc_wait_w, mbar_wait(&w_full[slot], phase, 23));
@@ -240,7 +255,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (elect_one_sync()) {
 #pragma unroll
             for (int k = 0; k < HC / 16; ++k)
-              umma_f16_ts_2cta(tmem_base + hf * NH, a_tmem + (k < 2 ? 8 * k : 16 + 8 * k),
+              umma_f16_ts_2cta(tmem_base + hf * NH, a_tmem + (uint32_t)((16 * k / GW) * GW + (16 * k % GW) / 2),
                                 umma_desc_pack(lo_w + 2 * k, kUmmaDescSw128Hi), idesc2, (c | k) != 0 ? 1u : 0u);
             umma_commit_2cta(&w_empty[slot]);
           }
@@ -280,21 +295,20 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== GELU of the hidden chunks, then the full-row epilogue (both CTAs, own 128 rows) ==========
     const int ew = warp - 4;
     const int q = warp & 3;       // TMEM lane quarter: rows q*32 .. q*32+31 of this CTA's 128
-    const int c = ew >> 2;        // column half (of a hidden chunk: 32 of 64; of the output row: 192 of 384)
+    const int c = ew >> 2;        // column group (of a hidden chunk: GW of 64; of the output row: NW of 384)
     uint8_t* xbox = sA + ew * 3 * Cfg::XBOX;             // two in-boxes, then the out-box
     uint8_t* obox = xbox + 2 * Cfg::XBOX;
     uint8_t* hbox = sOut + ew * 2048;
     uint64_t* my_xfull = xfull + ew * 2;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t tlane = tmem_base + lane_off + c * NH;
-    const uint32_t tS = tmem_base + lane_off + kColS + c * 32;
-    const int sw = lane & 7;
+    const uint32_t tlane = tmem_base + lane_off + c * NW;
+    const uint32_t tS = tmem_base + lane_off + kColS + c * GW;
     uint32_t sfull_ph = 0;        // bit b: parity of the next s_full[b] phase
     int g = 0;                    // residual boxes issued / consumed so far (2-deep per warp)
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = pair + t * num_pairs;
       const int row0 = tile * 2 * BM + (int)rank * BM + q * 32;
-      // ---- GELU: P_c = gelu(S_c + b1) as packed fp16 pairs over the first half of this warp's 32 S columns ----
+      // ---- GELU: P_c = gelu(S_c + b1) as packed fp16 pairs over the first half of this warp's GW S columns ----
 #ifdef VITED_MLP_TRACE
       long long acc_wait_s = 0;
       if (ew == 0) TRM(0, t, 0, TRM_CLK());
@@ -304,13 +318,13 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         TRM_WAIT(acc_wait_s, mbar_wait(&s_full[b], (sfull_ph >> b) & 1u, 32));
         sfull_ph ^= 1u << b;
         tc_fence_after();
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tS + b * HC, acc);
+        uint32_t acc[GW];
+        tmem_ld_cols(tS + b * HC, acc);
         tmem_ld_wait();
-        const uint32_t bp = smem_u32(sB1) + (uint32_t)(ch * HC + c * 32) * 4;
-        uint32_t pk[16];
+        const uint32_t bp = smem_u32(sB1) + (uint32_t)(ch * HC + c * GW) * 4;
+        uint32_t pk[GW / 2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < GW / 4; ++i) {
           const float4 b4 = lds_f4(bp + 16 * i);
           const float v0 = gelu_fast(__uint_as_float(acc[4 * i + 0]) + b4.x);
           const float v1 = gelu_fast(__uint_as_float(acc[4 * i + 1]) + b4.y);
@@ -319,16 +333,16 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           pk[2 * i] = pack_act(v0, v1);
           pk[2 * i + 1] = pack_act(v2, v3);
         }
-        tmem_st_32x32b_x16(tS + b * HC, pk);
+        tmem_st_cols(tS + b * HC, pk);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&p_full[b]);
       }
       // ---- the h tile is dead once fc1 of the last chunk has completed: its region now takes the residual boxes ----
-      auto issue_x = [&](int j, int gg) {   // lane 0 only: 32 x 32 fp32 box j of this warp's half row
+      auto issue_x = [&](int j, int gg) {   // lane 0 only: 32-row x XW-column fp32 box j of this warp's row part
         mbar_arrive_expect_tx(&my_xfull[gg & 1], Cfg::XBOX);
-        tma_load_2d(&tmX, &my_xfull[gg & 1], xbox + (gg & 1) * Cfg::XBOX, c * NH + j * 32, row0);
+        tma_load_2d(&tmX, &my_xfull[gg & 1], xbox + (gg & 1) * Cfg::XBOX, c * NW + j * XW, row0);
       };
 #ifdef VITED_MLP_TRACE
       if (ew == 0) { TRM(0, t, 1, TRM_CLK()); TRM(0, t, 6, acc_wait_s); }
@@ -345,14 +359,14 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       float s = 0.f, ss = 0.f, c0 = 0.f;
 #pragma unroll 1
       for (int j = 0; j < CHUNKS; ++j, ++g) {
-        const int col0 = c * NH + j * 32;
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tlane + j * 32, acc);
+        const int col0 = c * NW + j * XW;
+        uint32_t acc[XW];
+        tmem_ld_cols(tlane + j * XW, acc);
         mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
         tmem_ld_wait();
-        // shared-window addresses of this lane's 128-byte row in the in-box / out-box (16-byte chunk i lives at i ^ sw)
-        const uint32_t in_row = smem_u32(xbox) + (uint32_t)(g & 1) * Cfg::XBOX + lane * 128;
-        const uint32_t out_row = smem_u32(obox) + lane * 128;
+        // shared-window addresses of this lane's row in the in-box / out-box (16-byte chunk i lives at swz_chunk(i))
+        const uint32_t in_row = smem_u32(xbox) + (uint32_t)(g & 1) * Cfg::XBOX + lane * ROWB;
+        const uint32_t out_row = smem_u32(obox) + lane * ROWB;
         const uint32_t bias_a = smem_u32(sBias) + col0 * 4;
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the out-box
         __syncwarp();
@@ -360,15 +374,16 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // fence in front of the TMA store is reached (MEMBAR.ALL.CTA waits for every store in flight: ~300 cycles when it
         // came right behind the last store); the statistics are computed while they drain
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 xv = lds_f4(in_row + ((i ^ sw) << 4));
+        for (int i = 0; i < XW / 4; ++i) {
+          const uint32_t off = swz_chunk<ROWB>(i, lane) << 4;
+          const float4 xv = lds_f4(in_row + off);
           const float4 b4 = lds_f4(bias_a + 16 * i);
           float4 v;
           v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
           v.y = __uint_as_float(acc[4 * i + 1]) + b4.y + xv.y;
           v.z = __uint_as_float(acc[4 * i + 2]) + b4.z + xv.z;
           v.w = __uint_as_float(acc[4 * i + 3]) + b4.w + xv.w;
-          sts_f4(out_row + ((i ^ sw) << 4), v);
+          sts_f4(out_row + off, v);
           acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
           acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
         }
@@ -376,7 +391,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         {
           float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains each
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < XW; ++i) {
             const float d = __uint_as_float(acc[i]) - c0;
             s4[i & 3] += d;
             q4[i & 3] = fmaf(d, d, q4[i & 3]);
@@ -384,7 +399,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
           ss += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
-        tmem_st_32x32b_x32(tlane + j * 32, acc);
+        tmem_st_cols(tlane + j * XW, acc);
         fence_proxy_async_smem();
         __syncwarp();                             // every lane has read the in-box and written the out-box
         if (lane == 0) {
@@ -401,22 +416,37 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         fence_proxy_async_smem();
         mbar_arrive(a_free);
       }
-      // ---- combine the two column halves of every row (Chan): n = 192 each ----
-      sPart[c * BM + q * 32 + lane] = make_float4(s, ss, c0, 0.f);
-      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
-      const float4 o4 = sPart[(c ^ 1) * BM + q * 32 + lane];
-      const float inv_n = 1.f / NH;
+      // ---- combine the CG column groups of every row (Chan): n = NW each ----
+      const float inv_n = 1.f / NW;
       const float mean_a = c0 + s * inv_n, m2_a = ss - s * s * inv_n;
-      const float mean_b = o4.z + o4.x * inv_n, m2_b = o4.y - o4.x * o4.x * inv_n;
-      const float dm = mean_b - mean_a;
-      const float mean = 0.5f * (mean_a + mean_b);
-      const float var = (m2_a + m2_b + dm * dm * (0.5f * NH)) * (1.f / LN_N);
+      sPart[c * BM + q * 32 + lane] = make_float2(mean_a, m2_a);
+      asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(32 * CG) : "memory");
+      float mean, var;
+      if constexpr (CG == 2) {
+        const float2 o = sPart[(c ^ 1) * BM + q * 32 + lane];
+        const float dm = o.x - mean_a;
+        mean = 0.5f * (mean_a + o.x);
+        var = (m2_a + o.y + dm * dm * (0.5f * NW)) * (1.f / LN_N);
+      } else {
+        float mg[CG], m2 = 0.f, msum = 0.f;
+#pragma unroll
+        for (int k = 0; k < CG; ++k) {
+          const float2 o = sPart[k * BM + q * 32 + lane];
+          mg[k] = o.x;
+          m2 += o.y;
+          msum += o.x;
+        }
+        mean = msum * (1.f / CG);
+        float between = 0.f;
+#pragma unroll
+        for (int k = 0; k < CG; ++k) between = fmaf(mg[k] - mean, mg[k] - mean, between);
+        var = (m2 + between * (float)NW) * (1.f / LN_N);
+      }
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
       // ---- pass 2: normalise out of TMEM, fp16, 32-column chunks through the warp's staging box (64B-swizzled rows) ----
-      const int sw2 = (lane >> 1) & 3;
       const uint32_t hbox_a = smem_u32(hbox) + lane * 64, g_a = smem_u32(sG), bt_a = smem_u32(sBt);
       auto normalise_chunk = [&](const uint32_t (&v)[32], int j) {
-        const int col0 = c * NH + j * 32;
+        const int col0 = c * NW + j * 32;
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the staging box
         __syncwarp();
 #pragma unroll
@@ -439,7 +469,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           pk.y = pack_act(y[2], y[3]);
           pk.z = pack_act(y[4], y[5]);
           pk.w = pack_act(y[6], y[7]);
-          sts_u4(hbox_a + ((i ^ sw2) << 4), pk);
+          sts_u4(hbox_a + (swz_chunk<64>(i, lane) << 4), pk);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -449,13 +479,13 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
       };
       // (a two-register-buffer version with the TMEM read of chunk j + 1 in flight measured slower: 8.0 k vs 6.0 k
-      //  cycles per tile -- both epilogue passes are instruction-issue bound, not latency bound; profiles/README.md)
+      //  cycles per tile; profiles/README.md)
 #pragma unroll 1
-      for (int j = 0; j < CHUNKS; ++j) {
+      for (int j = 0; j < NW / 32; ++j) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tlane + j * 32, v);
         tmem_ld_wait();
-        if (j == CHUNKS - 1) {
+        if (j == NW / 32 - 1) {
           // last read of this tile's accumulator: hand O back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -465,7 +495,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       if (ew == 0) TRM(0, t, 4, TRM_CLK());
       // the sPart exchange of the next tile must not overtake a slow partner still reading this tile's entry
-      asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(32 * CG) : "memory");
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -485,6 +515,32 @@ bool mlp_resid_ln_supported(int M, int D, int hidden) {
   return D == LN_N && hidden >= HC && hidden % HC == 0 && hidden <= 8192 && M >= 1;
 }
 
+template <int CG>
+static int mlp_resid_ln_launch(const act_t* h_in, const act_t* W1, const float* b1, const act_t* W2, const float* b2,
+                               float* x, const float* ln_w, const float* ln_b, act_t* h_out, int M, int D, int hidden,
+                               float eps, cudaStream_t stream) {
+  using Cfg = MlpCfg<CG>;
+  const int sms = gemm_num_sms();
+  VITED_CHECK(sms >= 2, "mlp_resid_ln: no device");
+  const uint32_t smem = Cfg::smem_bytes(hidden);
+  VITED_CHECK(smem <= 232448, "mlp_resid_ln: hidden=%d needs %u bytes of shared memory", hidden, smem);
+  static PerDeviceOnce once;
+  if (once.first())
+    VITED_CUDA_OK(cudaFuncSetAttribute(mlp_ln_pair_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  CUtensorMap tA, tW1, tW2, tX, tH;
+  if (make_tmap_act_2d(&tA, h_in, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, BM, 128)) return 1;
+  if (make_tmap_act_2d(&tW1, W1, (uint64_t)D, (uint64_t)hidden, (uint64_t)D * 2, 64, HC / 2, 128)) return 1;
+  if (make_tmap_act_2d(&tW2, W2, (uint64_t)hidden, (uint64_t)D, (uint64_t)hidden * 2, 64, NH / 2, 128)) return 1;
+  if (make_tmap_f32_2d(&tX, x, (uint64_t)D, (uint64_t)M, (uint64_t)D * 4, Cfg::XW, 32, Cfg::ROWB)) return 1;
+  if (make_tmap_act_2d(&tH, h_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 32, 32, 64)) return 1;
+  const int tiles = (M + 2 * BM - 1) / (2 * BM);
+  int pairs = sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  VITED_CUDA_OK(launch_pdl(mlp_ln_pair_kernel<CG>, dim3(2 * pairs), dim3(Cfg::kThreads), smem, stream, tA, tW1, tW2, tX, tH,
+                           b1, b2, ln_w, ln_b, M, hidden, eps));
+  return 0;
+}
+
 int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_t* W2, const float* b2, float* x,
                  const float* ln_w, const float* ln_b, act_t* h_out, int M, int D, int hidden, float eps,
                  cudaStream_t stream) {
@@ -492,25 +548,11 @@ int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_
   VITED_CHECK(((reinterpret_cast<uintptr_t>(h_in) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
                 reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0,
               "mlp_resid_ln: operands must be 16-byte aligned");
-  const int sms = gemm_num_sms();
-  VITED_CHECK(sms >= 2, "mlp_resid_ln: no device");
-  const uint32_t smem = MlpCfg::smem_bytes(hidden);
-  VITED_CHECK(smem <= 232448, "mlp_resid_ln: hidden=%d needs %u bytes of shared memory", hidden, smem);
-  static PerDeviceOnce once;
-  if (once.first())
-    VITED_CUDA_OK(cudaFuncSetAttribute(mlp_ln_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  CUtensorMap tA, tW1, tW2, tX, tH;
-  if (make_tmap_act_2d(&tA, h_in, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, BM, 128)) return 1;
-  if (make_tmap_act_2d(&tW1, W1, (uint64_t)D, (uint64_t)hidden, (uint64_t)D * 2, 64, HC / 2, 128)) return 1;
-  if (make_tmap_act_2d(&tW2, W2, (uint64_t)hidden, (uint64_t)D, (uint64_t)hidden * 2, 64, NH / 2, 128)) return 1;
-  if (make_tmap_f32_2d(&tX, x, (uint64_t)D, (uint64_t)M, (uint64_t)D * 4, 32, 32, 128)) return 1;
-  if (make_tmap_act_2d(&tH, h_out, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 32, 32, 64)) return 1;
-  const int tiles = (M + 2 * BM - 1) / (2 * BM);
-  int pairs = sms / 2;
-  if (pairs > tiles) pairs = tiles;
-  VITED_CUDA_OK(launch_pdl(mlp_ln_pair_kernel, dim3(2 * pairs), dim3(MlpCfg::kThreads), smem, stream, tA, tW1, tW2, tX, tH,
-                           b1, b2, ln_w, ln_b, M, hidden, eps));
-  return 0;
+#ifdef VITED_EXPERIMENTAL   // measured neutral (profiles/README.md): not in the product library
+  if (epilogue_warps() == 16)
+    return mlp_resid_ln_launch<4>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
+#endif
+  return mlp_resid_ln_launch<2>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
 }
 
 }  // namespace vited
