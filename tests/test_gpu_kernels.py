@@ -339,18 +339,6 @@ def test_cross_attention(cfg, impl):
     assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
 
 
-@pytest.mark.parametrize('cfg', [(40, 6, 64, 1024, 1), (1, 1, 64, 256, 1), (30, 2, 64, 256, 1), (3, 6, 64, 1024, 1)],
-                         ids=lambda c: 'x'.join(map(str, c)))
-def test_long_attention_class_token_as_work_item(cfg, monkeypatch):
-    """The long-sequence tcgen05 kernel computes the class-token query rows on four CUDA-core warps by default (covered by
-    test_self_attention / test_cross_attention); VITED_L64_CLS_WARPS=0 selects the earlier form -- the class-token query
-    as an extra work item of the tile pipeline -- which must give the same rows."""
-    monkeypatch.setenv('VITED_L64_CLS_WARPS', '0')
-    test_self_attention(cfg, 0)
-    n_seq, H, hd, n_patch, _ = cfg
-    test_cross_attention((n_seq, max(1, n_seq // 3), H, hd, n_patch), 0)
-
-
 @pytest.mark.parametrize('cfg', [(3, 3, 64, 8), (2, 3, 512, 16), (5, 3, 64, 32)])
 def test_im2col_patch_indexing_is_exact(cfg):
     L = _lib()

@@ -30,10 +30,8 @@ def cross_attn(impl):
 
 if len(sys.argv) > 1 and sys.argv[1] == 'time':
     import json
-    # impl 0 twice: class-token query rows on the CUDA-core warps (default) / as an extra work item (VITED_L64_CLS_WARPS=0)
     for name, fn, fl in (('self', self_attn, 4.0 * P * H * 1025 * 1025 * hd), ('cross', cross_attn, 4.0 * P * H * 1025 * 1024 * hd)):
-        for impl, clsw in ((0, '1'), (0, '0'), (2, '1')):
-            os.environ['VITED_L64_CLS_WARPS'] = clsw
+        for impl in (0, 2):
             for _ in range(3):
                 fn(impl)
             torch.cuda.synchronize()
@@ -44,7 +42,7 @@ if len(sys.argv) > 1 and sys.argv[1] == 'time':
                 ts.append(s.elapsed_time(e))
             ts.sort()
             ms = ts[len(ts) // 2]
-            print(json.dumps(dict(op=f'attn_l64_{name}_impl{impl}' + ('_clsitem' if clsw == '0' else ''), pairs=P, ms=ms, tflops=fl / ms / 1e9)))
+            print(json.dumps(dict(op=f'attn_l64_{name}_impl{impl}', pairs=P, ms=ms, tflops=fl / ms / 1e9)))
 else:
     for _ in range(2):
         self_attn(0)

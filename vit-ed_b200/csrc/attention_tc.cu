@@ -316,12 +316,6 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
 //   item per (sequence, head) whose tile has a single live row (group 0 only).
 //   Warps: 0-3 group 0, 4-7 group 1, 8 TMA producer, 9 / 10 MMA issuers of group 0 / 1 (warp-uniform code, elected
 //   lane; warp 9 also owns the TMEM allocation).
-//   CLSW = 1 (default): the class-token QUERY rows do not go through the tile pipeline at all. As an extra item they
-//   cost a full pass over the keys with one live row of 128 and group 1 idle (one item in five: ~13 % of the launch).
-//   Instead four more warps (12-15) compute them on the CUDA cores, one (sequence, head) at a time, straight from
-//   global memory (the K/V rows are in L2 around the time the tile pipeline streams them): 2 x 1025 x 64 FMAs per
-//   row, fp32 throughout. The register file is re-split with setmaxnreg (softmax warps 176, producer / issuers 56,
-//   class-token warps 104); CLSW = 0 keeps the extra-item form (VITED_L64_CLS_WARPS=0, or more than 4096 keys).
 // =====================================================================================================================
 struct L64 {
   static constexpr int HD = 64;
@@ -331,14 +325,10 @@ struct L64 {
   static constexpr int STAGE = 2 * KVB;        // K, V
   static constexpr int NS = 4;                 // K/V ring depth (stages of 128 keys)
   static constexpr int THREADS = 352;
-  static constexpr int THREADS_CLSW = 512;     // + warp 11 (idle, completes the warpgroup) + class-token warps 12-15
   static constexpr int GCOLS = 256;            // TMEM columns per group: S/P buffers at +0 and +64, O at +128
   static constexpr int OCOL = 128;
   static constexpr int BAR_BYTES = 512;
   static constexpr int BYTES = 1024 + 4 * QB + NS * STAGE + BAR_BYTES;   // Q double-buffered per group
-  static constexpr int CLS_MAX_KEYS = 4096;    // class-token warps: probabilities of one row live in shared memory
-  // class-token warps: [keys + 1, rounded up to 32] probabilities, [16][64] partial outputs, [64] query, [8] partials
-  static int cls_bytes(int nk_patch) { return (((nk_patch + 1 + 31) & ~31) + 16 * 64 + 64 + 8) * 4; }
 };
 
 #ifdef VITED_ATTN_TRACE
@@ -352,17 +342,9 @@ struct L64Maps {
   CUtensorMap q_tile, q_row, k_tile, k_row, v_tile, v_row;   // boxes {64, 128} and {64, 1}, 128B swizzle
 };
 
-__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
-template <int CLSW>
-__global__ void __launch_bounds__(CLSW ? L64::THREADS_CLSW : L64::THREADS, 1)
+__global__ void __launch_bounds__(L64::THREADS, 1)
 attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   using C = L64;
-  constexpr int kThreads = CLSW ? C::THREADS_CLSW : C::THREADS;
   extern __shared__ uint8_t attn_tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(attn_tc_smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                          // [group][buffer][128 x 128 B]
@@ -381,14 +363,14 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int H = a.n_heads;
   const int n_qp = a.nq_patch / 256;                         // 256-query blocks per (sequence, head)
-  const int per_bh = n_qp + (a.q_has_cls && !CLSW ? 1 : 0);  // + the class-token item (CLSW: warps 12-15 instead)
+  const int per_bh = n_qp + (a.q_has_cls ? 1 : 0);           // + the class-token item
   const int n_kt = a.nk_patch / 128;                         // full 128-key stages per item
   const int n_st = n_kt + (a.k_has_cls ? 1 : 0);             // stages per item (the last one = class-token key)
   const int U = 2 * n_kt + (a.k_has_cls ? 1 : 0);            // half tiles per item
   const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   // stale rows of the ring enter masked score columns / multiply zero probabilities: they only have to be finite
-  for (int i = tid; i < (4 * C::QB + C::NS * C::STAGE) / 16; i += kThreads)
+  for (int i = tid; i < (4 * C::QB + C::NS * C::STAGE) / 16; i += C::THREADS)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int s = 0; s < C::NS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
@@ -414,119 +396,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
   pdl_wait();           // the prologue above overlapped the previous kernel's tail; global memory only from here on
   auto is_cls_item = [&](int i) { return (((int)blockIdx.x + i * (int)gridDim.x) % per_bh) == n_qp; };
 
-  if (CLSW && warp >= 12) {
-    // ===================== class-token query rows on the CUDA cores (CLSW; warps 12-15 = 128 threads) ===============
-    // One (sequence, head) at a time: s_t = q . k_t (thread = key), softmax over all keys in shared memory, o = P V
-    // (thread = (key group of 16, 8-dim chunk)), fp32 throughout. The unit of (b, h) is done by the CTA that owns the
-    // regular item (b, h, qp) with qp == bh % n_qp: every unit exactly once, spread evenly over the CTAs, and close in
-    // time to the tile pipeline's own pass over the same K/V rows.
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    if (a.q_has_cls) {
-      const int ct = tid - 384;
-      const int NKT = a.nk_patch + (a.k_has_cls ? 1 : 0);
-      float* sS = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES);
-      float* sRed = sS + ((NKT + 31) & ~31);
-      float* sQf = sRed + 16 * 64;
-      float* sW = sQf + 64;
-      const float sl2 = a.scale * kLog2e;
-      auto cls_bar = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
-      auto kv_row = [&](int t, int kvb) -> size_t {
-        return t < a.nk_patch ? (size_t)kvb * a.nk_patch + t : (size_t)a.n_kv_seq * a.nk_patch + kvb;
-      };
-      auto dot8 = [&](const uint4& kk, int c, float (&acc)[4]) {   // 8 elements of the key row against q[8c .. 8c+7]
-        const float4 q0 = *reinterpret_cast<const float4*>(sQf + 8 * c);
-        const float4 q1 = *reinterpret_cast<const float4*>(sQf + 8 * c + 4);
-        const float2 k0 = unpack_act(kk.x), k1 = unpack_act(kk.y), k2 = unpack_act(kk.z), k3 = unpack_act(kk.w);
-        acc[0] = fmaf(k0.x, q0.x, acc[0]); acc[1] = fmaf(k0.y, q0.y, acc[1]);
-        acc[2] = fmaf(k1.x, q0.z, acc[2]); acc[3] = fmaf(k1.y, q0.w, acc[3]);
-        acc[0] = fmaf(k2.x, q1.x, acc[0]); acc[1] = fmaf(k2.y, q1.y, acc[1]);
-        acc[2] = fmaf(k3.x, q1.z, acc[2]); acc[3] = fmaf(k3.y, q1.w, acc[3]);
-      };
-      for (int i = 0; i < n_my; ++i) {
-        const int item = (int)blockIdx.x + i * (int)gridDim.x;
-        const int bh = item / n_qp, qp = item - bh * n_qp;
-        if (bh % n_qp != qp) continue;
-        const int b = bh / H, h = bh - b * H;
-        const int kvb = a.kv_index ? __ldg(a.kv_index + b) : b;
-        if (ct < 64) sQf[ct] = act2f(a.q[((size_t)a.n_seq * a.nq_patch + b) * a.q_ld + h * C::HD + ct]) * sl2;
-        cls_bar();
-        // ---- scores (log2 domain): two key rows in flight per thread ----
-        float mloc = -INFINITY;
-        for (int t0 = ct; t0 < NKT; t0 += 256) {
-          const int t1 = t0 + 128;
-          const bool has1 = t1 < NKT;
-          const uint4* k0p = reinterpret_cast<const uint4*>(a.k + kv_row(t0, kvb) * a.k_ld + h * C::HD);
-          const uint4* k1p = reinterpret_cast<const uint4*>(a.k + kv_row(has1 ? t1 : t0, kvb) * a.k_ld + h * C::HD);
-          uint4 ka[8], kb[8];
-#pragma unroll
-          for (int c = 0; c < 8; ++c) ka[c] = ldg_nc_u4(k0p + c);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) kb[c] = ldg_nc_u4(k1p + c);
-          float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int c = 0; c < 8; ++c) dot8(ka[c], c, a0);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) dot8(kb[c], c, a1);
-          const float s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]);
-          sS[t0] = s0;
-          mloc = fmaxf(mloc, s0);
-          if (has1) {
-            const float s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
-            sS[t1] = s1;
-            mloc = fmaxf(mloc, s1);
-          }
-        }
-        mloc = warp_max(mloc);
-        if (lane == 0) sW[warp - 12] = mloc;
-        cls_bar();
-        const float m = fmaxf(fmaxf(sW[0], sW[1]), fmaxf(sW[2], sW[3]));
-        float lloc = 0.f;
-        for (int t = ct; t < NKT; t += 128) {
-          const float pv = ex2_ftz(sS[t] - m);
-          sS[t] = pv;
-          lloc += pv;
-        }
-        lloc = warp_sum(lloc);
-        if (lane == 0) sW[4 + warp - 12] = lloc;
-        cls_bar();                                   // every probability and the four partial sums are visible
-        const float l = (sW[4] + sW[5]) + (sW[6] + sW[7]);
-        // ---- o = P V: thread = (key group kg of 16, dims 8 dc .. 8 dc + 7); eight value rows in flight ----
-        const int kg = ct >> 3, dc = ct & 7;
-        float o8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int t0 = kg; t0 < NKT; t0 += 128) {
-          uint4 vv[8];
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int t = t0 + 16 * r;
-            vv[r] = ldg_nc_u4(reinterpret_cast<const uint4*>(a.v + kv_row(t < NKT ? t : t0, kvb) * a.v_ld + h * C::HD) + dc);
-          }
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-            const int t = t0 + 16 * r;
-            const float pv = t < NKT ? sS[t] : 0.f;
-            const float2 v0 = unpack_act(vv[r].x), v1 = unpack_act(vv[r].y), v2 = unpack_act(vv[r].z), v3 = unpack_act(vv[r].w);
-            o8[0] = fmaf(pv, v0.x, o8[0]); o8[1] = fmaf(pv, v0.y, o8[1]);
-            o8[2] = fmaf(pv, v1.x, o8[2]); o8[3] = fmaf(pv, v1.y, o8[3]);
-            o8[4] = fmaf(pv, v2.x, o8[4]); o8[5] = fmaf(pv, v2.y, o8[5]);
-            o8[6] = fmaf(pv, v3.x, o8[6]); o8[7] = fmaf(pv, v3.y, o8[7]);
-          }
-        }
-        *reinterpret_cast<float4*>(sRed + kg * 64 + dc * 8) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-        *reinterpret_cast<float4*>(sRed + kg * 64 + dc * 8 + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
-        cls_bar();
-        if (ct < 64) {
-          float acc = 0.f;
-#pragma unroll
-          for (int k = 0; k < 16; ++k) acc += sRed[k * 64 + ct];
-          a.o[((size_t)a.n_seq * a.nq_patch + b) * a.o_ld + h * C::HD + ct] = f2act(acc / l);
-        }
-        cls_bar();                                   // sQf / sS / sRed / sW are free for the next unit
-      }
-    }
-  } else if (warp >= 8) {
-    // warps 8-11 (CLSW: one warpgroup, warp 11 idle) give registers back before they split into their roles
-    if (CLSW) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 8) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
@@ -567,7 +437,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
         }
       }
     }
-    } else if (warp <= 10) {
+  } else if (warp >= 9) {
     // ===================== MMA issuer of group g = warp - 9 (warp-uniform; tcgen05 ops on one elected lane) ==========
     // A lean linear program per item: QK^T(0), QK^T(1), then for every half tile u: PV(u) as soon as P(u) is in TMEM
     // and QK^T(u+2) right behind it into the same score buffer (the tensor pipe runs in issue order). This warp is on
@@ -641,10 +511,8 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
       }
       ++qn;
     }
-    }   // issuer
   } else {
     // ===================== softmax group g = warp / 4: one thread per query row =====================
-    if (CLSW) asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     const int g = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const float sl2 = a.scale * kLog2e;
@@ -797,15 +665,13 @@ static bool l64_shape(const AttnArgs& a) {
 }
 bool attention_tc_supported(const AttnArgs& a) { return a.n_heads >= 1 && (p64_shape(a) || l64_shape(a)); }
 
-template <int CLSW>
-static int attention_tc_l64_launch(const AttnArgs& a, cudaStream_t stream) {
-  const size_t items = (size_t)a.n_seq * a.n_heads * (a.nq_patch / 256 + (a.q_has_cls && !CLSW ? 1 : 0));
+static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
+  const size_t items = (size_t)a.n_seq * a.n_heads * (a.nq_patch / 256 + (a.q_has_cls ? 1 : 0));
   VITED_CHECK(items < ((size_t)1 << 31), "attention_tc: too many work items");
   static PerDeviceOnce once;
   const int sms = device_sm_count();
   if (once.first())
-    VITED_CUDA_OK(cudaFuncSetAttribute(attn_l64_kernel<CLSW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       L64::BYTES + (CLSW ? L64::cls_bytes(L64::CLS_MAX_KEYS) : 0)));
+    VITED_CUDA_OK(cudaFuncSetAttribute(attn_l64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L64::BYTES));
   const uint64_t cols = (uint64_t)a.n_heads * 64;
   const uint64_t q_rows = (uint64_t)a.n_seq * a.nq_patch + (a.q_has_cls ? a.n_seq : 0);
   const uint64_t k_rows = (uint64_t)a.n_kv_seq * a.nk_patch + (a.k_has_cls ? a.n_kv_seq : 0);
@@ -817,19 +683,9 @@ static int attention_tc_l64_launch(const AttnArgs& a, cudaStream_t stream) {
   if (make_tmap_act_2d(&maps.v_tile, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 128, 128)) return 1;
   if (make_tmap_act_2d(&maps.v_row, a.v, cols, k_rows, (uint64_t)a.v_ld * 2, 64, 1, 128)) return 1;
   const unsigned grid = (unsigned)(items < (size_t)sms ? items : (size_t)sms);
-  const size_t smem = L64::BYTES + (CLSW ? L64::cls_bytes(a.nk_patch) : 0);
-  VITED_CUDA_OK(launch_pdl(attn_l64_kernel<CLSW>, dim3(grid), dim3(CLSW ? L64::THREADS_CLSW : L64::THREADS), smem, stream, a,
-                           maps, (int)items));
+  VITED_CUDA_OK(launch_pdl(attn_l64_kernel, dim3(grid), dim3(L64::THREADS), L64::BYTES, stream, a, maps, (int)items));
   VITED_CUDA_OK(cudaGetLastError());
   return 0;
-}
-
-static int attention_tc_l64(const AttnArgs& a, cudaStream_t stream) {
-  // VITED_L64_CLS_WARPS=0: the class-token query as an extra work item of the tile pipeline (read at every launch: A/B)
-  const char* v = getenv("VITED_L64_CLS_WARPS");
-  const bool cls_warps = (v == nullptr || v[0] == 0 || atoi(v) != 0) && a.nk_patch <= L64::CLS_MAX_KEYS &&
-                         (a.q_ld % 8) == 0 && (a.k_ld % 8) == 0 && (a.v_ld % 8) == 0;
-  return cls_warps ? attention_tc_l64_launch<1>(a, stream) : attention_tc_l64_launch<0>(a, stream);
 }
 
 static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream);
