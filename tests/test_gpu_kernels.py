@@ -278,7 +278,7 @@ def _attn_reference(q, k, v, scale):
 @pytest.mark.parametrize('impl', [0, 1, 2], ids=['fast', 'simt', 'mma_sync'])
 @pytest.mark.parametrize('cfg', [
     # (n_seq, H, hd, n_patch, has_cls)  -- self-attention
-    (7, 12, 32, 64, 1), (1, 1, 32, 64, 1), (333, 12, 32, 64, 1), (150, 5, 32, 64, 0),
+    (7, 12, 32, 64, 1), (1, 1, 32, 64, 1), (333, 12, 32, 64, 1), (150, 5, 32, 64, 0), (3, 5, 32, 64, 1), (2000, 12, 32, 64, 1),
     (40, 6, 64, 1024, 1), (1, 1, 64, 256, 1), (9, 3, 64, 512, 0), (30, 2, 64, 256, 1), (3, 6, 64, 1024, 1), (5, 12, 32, 64, 0), (2, 6, 64, 1024, 0), (4, 1, 32, 4, 1),
     (3, 3, 32, 16, 1), (2, 2, 64, 100, 1), (1, 2, 32, 130, 0),
 ], ids=lambda c: 'x'.join(map(str, c)))
@@ -311,7 +311,7 @@ def test_self_attention(cfg, impl):
 @pytest.mark.parametrize('impl', [0, 1, 2], ids=['fast', 'simt', 'mma_sync'])
 @pytest.mark.parametrize('cfg', [
     # (n_pairs, n_ctx, H, hd, n_patch)
-    (9, 4, 12, 32, 64), (1, 1, 12, 32, 64), (401, 7, 12, 32, 64), (37, 5, 6, 64, 1024), (3, 2, 1, 64, 256), (5, 3, 6, 64, 1024), (6, 2, 1, 32, 4), (4, 4, 2, 64, 16),
+    (9, 4, 12, 32, 64), (1, 1, 12, 32, 64), (401, 7, 12, 32, 64), (7, 3, 5, 32, 64), (1500, 9, 12, 32, 64), (37, 5, 6, 64, 1024), (3, 2, 1, 64, 256), (5, 3, 6, 64, 1024), (6, 2, 1, 32, 4), (4, 4, 2, 64, 16),
 ], ids=lambda c: 'x'.join(map(str, c)))
 def test_cross_attention(cfg, impl):
     L = _lib()
@@ -337,6 +337,19 @@ def test_cross_attention(cfg, impl):
     got = torch.cat([o[P * n_patch:].view(P, 1, D), o[:P * n_patch].view(P, n_patch, D)], dim=1).float()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
+
+
+def test_puzzle_attention_two_units_per_tile_variant(monkeypatch):
+    """attention_pair.cu packs two (sequence, head) units into one 128-row tcgen05 tile (block-diagonal scores, the
+    class-token query rows on CUDA-core warps). Correct but slower than the one-unit-per-tile kernel, so it only exists in
+    -DVITED_EXPERIMENTAL builds (select with VITED_LIB=tools/bin/experimental/libvited_b200.so)."""
+    if 'experimental' not in os.environ.get('VITED_LIB', ''):
+        pytest.skip('experimental build only (VITED_LIB=tools/bin/experimental/libvited_b200.so)')
+    monkeypatch.setenv('VITED_P64_PAIR', '1')
+    for cfg in [(333, 12, 32, 64, 1), (150, 5, 32, 64, 0), (3, 5, 32, 64, 1), (1, 1, 32, 64, 1)]:
+        test_self_attention(cfg, 0)
+    for cfg in [(401, 7, 12, 32, 64), (7, 3, 5, 32, 64)]:
+        test_cross_attention(cfg, 0)
 
 
 @pytest.mark.parametrize('cfg', [(3, 3, 64, 8), (2, 3, 512, 16), (5, 3, 64, 32)])

@@ -233,6 +233,15 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
         const float mneg = -mxa * sl2;
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t pk[32];
+#if VITED_SOFTMAX_PACKED
+        {
+          uint64_t sum2[2] = {0ull, 0ull};
+          softmax_exp_pairs<16>(v0, sl2, mneg, pk, sum2);
+          softmax_exp_pairs<16>(v1, sl2, mneg, pk + 16, sum2);
+          f2_unpack(sum2[0], sum[0], sum[1]);
+          f2_unpack(sum2[1], sum[2], sum[3]);
+        }
+#else
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float p0 = ex2_ftz(fmaf(__uint_as_float(v0[2 * j]), sl2, mneg));
@@ -247,6 +256,7 @@ attn_p64_kernel(AttnArgs a, const __grid_constant__ P64Maps maps, int n_units, i
           sum[(2 * j) & 3] += p0; sum[(2 * j + 1) & 3] += p1;
           pk[16 + j] = pack_act(p0, p1);
         }
+#endif
         tmem_st_32x32b_x32(t_stage, pk);
         if (a.k_has_cls) {
           const float pc = ex2_ftz(fmaf(__uint_as_float(vc[0]), sl2, mneg));
@@ -574,6 +584,23 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
           else if (mt > m + 8.f) rescale(mt, m, l);      // lazy: probabilities stay <= 2^8 otherwise
           const float mneg = -m;
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#if VITED_SOFTMAX_PACKED
+          {
+            uint64_t sum2[2] = {0ull, 0ull};
+            {
+              uint32_t pk[16];
+              softmax_exp_pairs<16>(v0, sl2, mneg, pk, sum2);
+              tmem_st_32x32b_x16(t_s, pk);
+            }
+            {
+              uint32_t pk[16];
+              softmax_exp_pairs<16>(v1, sl2, mneg, pk, sum2);
+              tmem_st_32x32b_x16(t_s + 16, pk);
+            }
+            f2_unpack(sum2[0], sum[0], sum[1]);
+            f2_unpack(sum2[1], sum[2], sum[3]);
+          }
+#else
           {
             uint32_t pk[16];
 #pragma unroll
@@ -596,6 +623,7 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
             }
             tmem_st_32x32b_x16(t_s + 16, pk);
           }
+#endif
           l += (sum[0] + sum[1]) + (sum[2] + sum[3]);
         } else {
           // class-token key half tile: column 0 is the only real key
@@ -693,6 +721,12 @@ static int attention_tc_p64(const AttnArgs& a, int cls_only, cudaStream_t stream
 int attention_tc(const AttnArgs& a, cudaStream_t stream) {
   VITED_CHECK(attention_tc_supported(a), "attention_tc: unsupported shape");
   if (l64_shape(a)) return attention_tc_l64(a, stream);
+#ifdef VITED_EXPERIMENTAL
+  // two units per 128-row tile (attention_pair.cu): correct, 30 % slower (profiles/README.md) -- experimental builds
+  // only, selected with VITED_P64_PAIR=1 (read at every launch: A/B runs)
+  const char* pr = getenv("VITED_P64_PAIR");
+  if (pr != nullptr && atoi(pr) != 0 && attention_pair_supported(a)) return attention_pair(a, stream);
+#endif
   return attention_tc_p64(a, 0, stream);
 }
 

@@ -206,6 +206,93 @@ __device__ __forceinline__ float gelu_fast(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 process two fp32 values per issue slot) and the softmax exponentials
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x of both halves for x <= 0 WITHOUT the MUFU pipe: floor(x) by the round-down magic add (the low mantissa bits of
+// x + 1.5 * 2^23 are floor(x) in two's complement), a degree-3 minimax polynomial for 2^frac on [0, 1) (relative error
+// 8.6e-5, a sixth of an fp16 rounding step; p(1) < 2, so the mantissa never carries) and the integer part added to the
+// exponent field. 10 instructions per pair (2 FMNMX, 3 FADD2, 3 FFMA2, 2 LEA) against 2 MUFU.EX2 of 8 pipe cycles each.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  const uint64_t x = f2_pack(x0, x1);
+  const uint64_t xf = f2_add_rm(x, f2_pack(12582912.f, 12582912.f));
+  const uint64_t fl = f2_add(xf, f2_pack(-12582912.f, -12582912.f));
+  float f0, f1;
+  f2_unpack(fl, f0, f1);
+  const uint64_t fr = f2_add(x, f2_pack(-f0, -f1));
+  uint64_t p = f2_fma(f2_pack(0.07706724107265472f, 0.07706724107265472f), fr, f2_pack(0.22764497995376587f, 0.22764497995376587f));
+  p = f2_fma(p, fr, f2_pack(0.6951166391372681f, 0.6951166391372681f));
+  p = f2_fma(p, fr, f2_pack(1.f, 1.f));
+  float p0, p1, m0, m1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(xf, m0, m1);
+  return f2_pack(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(m0) << 23)),
+                 __uint_as_float(__float_as_uint(p1) + (__float_as_uint(m1) << 23)));
+}
+// The exponentials of NP score pairs of one softmax row: pk[j] = fp16x2(2^(v[2j] sl2 + mneg), 2^(v[2j+1] sl2 + mneg)),
+// probabilities accumulated into two packed sums (four chains). -DVITED_SOFTMAX_PACKED=0 keeps the scalar form
+// (FFMA / FADD per element); -DVITED_EXP_POLY=n computes n of every 8 pairs with ex2_poly2 on the FMA pipe.
+#ifndef VITED_SOFTMAX_PACKED
+#define VITED_SOFTMAX_PACKED 1
+#endif
+#ifndef VITED_EXP_POLY
+#define VITED_EXP_POLY 2   // measured on B200 (profiles/r02b_softmax_variants.jsonl): long-sequence attention 0.742 ms scalar,
+#endif                     // 0.712 packed, 0.679 / 0.674 / 0.663 with 1 / 2 / 3 of 8; in the step 2 of 8 is best (power cap)
+template <int NP>
+__device__ __forceinline__ void softmax_exp_pairs(const uint32_t* v, float sl2, float mneg, uint32_t* pk, uint64_t (&sum2)[2]) {
+  const uint64_t s2 = f2_pack(sl2, sl2), m2 = f2_pack(mneg, mneg);
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const uint64_t x = f2_fma(f2_pack(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), s2, m2);
+    uint64_t p;
+    float p0, p1;
+    if ((j & 7) < VITED_EXP_POLY) {
+      p = ex2_poly2(x);
+      f2_unpack(p, p0, p1);
+    } else {
+      float x0, x1;
+      f2_unpack(x, x0, x1);
+      p0 = ex2_approx(x0);
+      p1 = ex2_approx(x1);
+      p = f2_pack(p0, p1);
+    }
+    sum2[j & 1] = f2_add(sum2[j & 1], p);
+    pk[j] = pack_act(p0, p1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

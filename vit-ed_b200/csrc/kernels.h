@@ -154,6 +154,9 @@ int attention(const AttnArgs& a, int impl, cudaStream_t stream);
 // tcgen05/TMEM kernels for the hot decoder shapes (attention_tc.cu); attention() dispatches to them by itself
 bool attention_tc_supported(const AttnArgs& a);
 int attention_tc(const AttnArgs& a, cudaStream_t stream);
+// puzzle shape with two (sequence, head) units per 128-row tile (attention_pair.cu; -DVITED_EXPERIMENTAL builds only)
+bool attention_pair_supported(const AttnArgs& a);
+int attention_pair(const AttnArgs& a, cudaStream_t stream);
 bool attention_tc_cls_supported(const AttnArgs& a);
 int attention_tc_cls(const AttnArgs& a, cudaStream_t stream);
 // class-token query only: q is [n_seq, q_ld] (one row per sequence), o likewise; nq_patch / q_has_cls are ignored.
