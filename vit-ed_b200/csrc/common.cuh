@@ -226,6 +226,13 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_dup(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ uint64_t f2_from_bits(uint32_t lo, uint32_t hi) { return f2_pack(__uint_as_float(lo), __uint_as_float(hi)); }
 __device__ __forceinline__ uint64_t f2_add_rm(uint64_t a, uint64_t b) {
   uint64_t d;
   asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -259,6 +266,22 @@ __device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
   f2_unpack(xf, m0, m1);
   return f2_pack(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(m0) << 23)),
                  __uint_as_float(__float_as_uint(p1) + (__float_as_uint(m1) << 23)));
+}
+// TWICE the GELU of both halves (gelu_fast's approximation, same coefficients): 2 gelu(v) = v + |v| (1 - 2^(-Q(|v|))).
+// |v| and -|v| are operand modifiers of FFMA2 / FMUL2, so a pair costs 2 FFMA2 + FMUL2 + 2 MUFU.EX2 + FFMA2 + FADD2 = 7
+// issue slots against 14 for two gelu_fast calls. The factor 1/2 is left to the consumer: the fused MLP kernel
+// multiplies the fc2 accumulator by 0.5 in the FMA that adds bias and residual (exact: a power of two).
+__device__ __forceinline__ uint64_t gelu2x_fast2(uint64_t x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  const uint64_t a2 = f2_pack(fabsf(x0), fabsf(x1));
+  uint64_t q = f2_fma(a2, f2_dup(-0.0275597216f), f2_dup(-0.488495773f));
+  q = f2_fma(a2, q, f2_dup(-1.140745f));
+  q = f2_mul(q, a2);                        // -Q(|v|)
+  float q0, q1;
+  f2_unpack(q, q0, q1);
+  const uint64_t e2 = f2_pack(ex2_approx(q0), ex2_approx(q1));
+  return f2_add(x2, f2_fma(f2_pack(-fabsf(x0), -fabsf(x1)), e2, a2));
 }
 // The exponentials of NP score pairs of one softmax row: pk[j] = fp16x2(2^(v[2j] sl2 + mneg), 2^(v[2j+1] sl2 + mneg)),
 // probabilities accumulated into two packed sums (four chains). -DVITED_SOFTMAX_PACKED=0 keeps the scalar form

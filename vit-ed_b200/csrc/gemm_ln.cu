@@ -229,24 +229,28 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t off = swz_chunk<ROWB>(i, lane) << 4;
           const float4 xv = lds_f4(in_row + off);
           const float4 b4 = lds_f4(bias_a + 16 * i);
+          // packed fp32 pairs: the epilogue passes are issue bound (16 epilogue warps changed nothing), FADD2 / FFMA2
+          // halve their arithmetic instructions
           float4 v;
-          v.x = __uint_as_float(acc[4 * i + 0]) + b4.x + xv.x;
-          v.y = __uint_as_float(acc[4 * i + 1]) + b4.y + xv.y;
-          v.z = __uint_as_float(acc[4 * i + 2]) + b4.z + xv.z;
-          v.w = __uint_as_float(acc[4 * i + 3]) + b4.w + xv.w;
+          f2_unpack(f2_add(f2_from_bits(acc[4 * i + 0], acc[4 * i + 1]), f2_add(f2_pack(b4.x, b4.y), f2_pack(xv.x, xv.y))), v.x, v.y);
+          f2_unpack(f2_add(f2_from_bits(acc[4 * i + 2], acc[4 * i + 3]), f2_add(f2_pack(b4.z, b4.w), f2_pack(xv.z, xv.w))), v.z, v.w);
           sts_f4(out_row + off, v);
           acc[4 * i + 0] = __float_as_uint(v.x); acc[4 * i + 1] = __float_as_uint(v.y);
           acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
         }
         if (j == 0) c0 = __uint_as_float(acc[0]);
         {
-          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains each
+          uint64_t s2[2] = {0ull, 0ull}, q2[2] = {0ull, 0ull};                 // four independent chains each
+          const uint64_t nc0 = f2_dup(-c0);
 #pragma unroll
-          for (int i = 0; i < XW; ++i) {
-            const float d = __uint_as_float(acc[i]) - c0;
-            s4[i & 3] += d;
-            q4[i & 3] = fmaf(d, d, q4[i & 3]);
+          for (int i = 0; i < XW / 2; ++i) {
+            const uint64_t d = f2_add(f2_from_bits(acc[2 * i], acc[2 * i + 1]), nc0);
+            s2[i & 1] = f2_add(s2[i & 1], d);
+            q2[i & 1] = f2_fma(d, d, q2[i & 1]);
           }
+          float s4[4], q4[4];
+          f2_unpack(s2[0], s4[0], s4[1]); f2_unpack(s2[1], s4[2], s4[3]);
+          f2_unpack(q2[0], q4[0], q4[1]); f2_unpack(q2[1], q4[2], q4[3]);
           s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
           ss += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
@@ -288,6 +292,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         var = (m2 + between * (float)NW) * (1.f / LN_N);
       }
       const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+      const uint64_t nmean2 = f2_dup(-mean), rstd2 = f2_dup(rstd);
       if (who >= 0) TRL(who, t, 3);
       // ---- pass 2: normalise out of TMEM, fp16, HW-column slabs through the warp's staging box ----
       const uint32_t hbox_a = smem_u32(hbox) + lane * ROWB, g_a = smem_u32(sG), bt_a = smem_u32(sBt);
@@ -315,14 +320,10 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
             const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
             float y[8];
-            y[0] = fmaf((__uint_as_float(v[8 * i + 0]) - mean) * rstd, g0.x, t0.x);
-            y[1] = fmaf((__uint_as_float(v[8 * i + 1]) - mean) * rstd, g0.y, t0.y);
-            y[2] = fmaf((__uint_as_float(v[8 * i + 2]) - mean) * rstd, g0.z, t0.z);
-            y[3] = fmaf((__uint_as_float(v[8 * i + 3]) - mean) * rstd, g0.w, t0.w);
-            y[4] = fmaf((__uint_as_float(v[8 * i + 4]) - mean) * rstd, g1v.x, t1.x);
-            y[5] = fmaf((__uint_as_float(v[8 * i + 5]) - mean) * rstd, g1v.y, t1.y);
-            y[6] = fmaf((__uint_as_float(v[8 * i + 6]) - mean) * rstd, g1v.z, t1.z);
-            y[7] = fmaf((__uint_as_float(v[8 * i + 7]) - mean) * rstd, g1v.w, t1.w);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 0], v[8 * i + 1]), nmean2), rstd2), f2_pack(g0.x, g0.y), f2_pack(t0.x, t0.y)), y[0], y[1]);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 2], v[8 * i + 3]), nmean2), rstd2), f2_pack(g0.z, g0.w), f2_pack(t0.z, t0.w)), y[2], y[3]);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 4], v[8 * i + 5]), nmean2), rstd2), f2_pack(g1v.x, g1v.y), f2_pack(t1.x, t1.y)), y[4], y[5]);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 6], v[8 * i + 7]), nmean2), rstd2), f2_pack(g1v.z, g1v.w), f2_pack(t1.z, t1.w)), y[6], y[7]);
             uint4 pk;
             pk.x = pack_act(y[0], y[1]);
             pk.y = pack_act(y[2], y[3]);
