@@ -339,6 +339,44 @@ def test_cross_attention(cfg, impl):
     assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
 
 
+@pytest.mark.parametrize('impl', [0, 2], ids=['fast', 'mma_sync'])
+def test_long_attention_lazy_rescale_paths(impl):
+    """Scores that grow from key block to key block force the lazy rescale of the running maximum (and of the O row in
+    TMEM) again and again; scores that shrink never trigger it. Both against fp32 torch. (Random-init weights and randn
+    inputs never move a row maximum by more than the 2^8 threshold: until this test existed the rescale path had never
+    run, and it hung -- warp-collective tcgen05 instructions under a per-thread condition.)"""
+    L = _lib()
+    n_seq, H, hd, n_patch = 3, 2, 64, 512
+    D = H * hd
+    rows = n_seq * n_patch + n_seq
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for direction in (1.0, -1.0):
+        qkv = torch.randn(rows, 3 * D, device='cuda', generator=g)
+        # key magnitudes ramp over the sequence so that the row maxima move by far more than the 2^8 threshold
+        ramp = torch.linspace(0.2, 6.0, n_patch, device='cuda')
+        if direction < 0:
+            ramp = ramp.flip(0)
+        qkv[:n_seq * n_patch, D:2 * D] *= ramp.repeat(n_seq)[:, None]
+        qkv[:, :D] *= 2.0
+        qkv = qkv.to(_act())
+        o = torch.full((rows, D), float('nan'), dtype=_act(), device='cuda')
+        scale = hd ** -0.5
+        L.check(L.lib.vited_op_attention(_ptr(qkv), 3 * D, ctypes.c_void_p(qkv.data_ptr() + 2 * D), 3 * D,
+                                         ctypes.c_void_p(qkv.data_ptr() + 4 * D), 3 * D, _ptr(o), D, n_seq, H, hd, n_patch,
+                                         1, n_patch, 1, n_seq, None, scale, impl, _stream()), 'op_attention')
+        torch.cuda.synchronize()
+        patch = qkv[:n_seq * n_patch].view(n_seq, n_patch, 3 * D)
+        seq = torch.cat([qkv[n_seq * n_patch:].view(n_seq, 1, 3 * D), patch], dim=1)
+        q, k, v = [seq[..., i * D:(i + 1) * D].reshape(n_seq, -1, H, hd).permute(0, 2, 1, 3) for i in range(3)]
+        if direction > 0:   # the inputs must really move the row maxima by more than 2^8 between key blocks
+            s_blocks = ((q.float() @ k.float().transpose(-1, -2)) * scale * 1.4426950408889634)[..., 1:].reshape(n_seq, H, -1, n_patch // 64, 64)
+            assert (s_blocks.amax(-1)[..., -1] - s_blocks.amax(-1)[..., 0]).max().item() > 8.0
+        ref = _attn_reference(q, k, v, scale).permute(0, 2, 1, 3).reshape(n_seq, -1, D)
+        got = torch.cat([o[n_seq * n_patch:].view(n_seq, 1, D).float(), o[:n_seq * n_patch].view(n_seq, n_patch, D).float()], dim=1)
+        assert torch.isfinite(got).all()
+        assert (got - ref).abs().max().item() < 2e-2 * _r16(), f'max err {(got - ref).abs().max().item()}'
+
+
 def test_puzzle_attention_two_units_per_tile_variant(monkeypatch):
     """attention_pair.cu packs two (sequence, head) units into one 128-row tcgen05 tile (block-diagonal scores, the
     class-token query rows on CUDA-core warps). Correct but slower than the one-unit-per-tile kernel, so it only exists in

@@ -28,9 +28,16 @@ def cross_attn(impl):
                                      P, H, hd, Np, 1, Np, 0, 32, idx.data_ptr(), hd ** -0.5, impl, None), 'attn')
 
 
+def self_attn_nocls(impl):
+    # the same launch without class tokens (1024 queries / keys per sequence): the regular work items alone
+    L.check(L.lib.vited_op_attention(qkv.data_ptr(), 3 * D, qkv.data_ptr() + 2 * D, 3 * D, qkv.data_ptr() + 4 * D, 3 * D,
+                                     o.data_ptr(), D, P, H, hd, Np, 0, Np, 0, P, None, hd ** -0.5, impl, None), 'attn')
+
+
 if len(sys.argv) > 1 and sys.argv[1] == 'time':
     import json
-    for name, fn, fl in (('self', self_attn, 4.0 * P * H * 1025 * 1025 * hd), ('cross', cross_attn, 4.0 * P * H * 1025 * 1024 * hd)):
+    for name, fn, fl in (('self', self_attn, 4.0 * P * H * 1025 * 1025 * hd), ('cross', cross_attn, 4.0 * P * H * 1025 * 1024 * hd),
+                         ('self_nocls', self_attn_nocls, 4.0 * P * H * 1024 * 1024 * hd)):
         for impl in (0, 2):
             for _ in range(3):
                 fn(impl)

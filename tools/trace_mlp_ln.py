@@ -27,3 +27,10 @@ for t in range(1, 12):
     wp = m[5] - tr[1, t - 1, 5]
     ww = m[6] - tr[1, t - 1, 6]
     print(f' {t:2d} | {m[1]-m[0]:6d} {m[3]-m[1]:7d} [{m[3]-m[2]:6d}] {m[4]-m[3]:7d} ({wp:6d} {ww:6d}) | {e[1]-e[0]:7d} ({e[6]:6d}) {e[2]-e[1]:6d} {e[3]-e[2]:6d} {e[4]-e[3]:6d} | {tr[1, t + 1, 0] - m[0]:7d}')
+buf2 = np.zeros(32 * 8, dtype=np.int64)
+if hasattr(lib, 'vited_debug_mlp_trace2') and lib.vited_debug_mlp_trace2(buf2.ctypes.data_as(vp)) == 0:
+    t2 = buf2.reshape(32, 8)
+    print('pass 1 of epilogue warp (q0, c0), cycles summed over its 6 chunks: TMEM load + wait for the residual box | wait for the '
+          'previous store (out-box free) | add + st.shared | statistics | tcgen05.st + proxy fence + syncwarp | TMA issue (lane 0)')
+    for t in range(1, 12):
+        print(f' {t:2d} | ' + ' '.join(f'{int(v):6d}' for v in t2[t, :6]) + f' | sum {int(t2[t, :6].sum()):6d}')

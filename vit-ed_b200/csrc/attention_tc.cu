@@ -535,13 +535,19 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
     // waiter and the parity wait cannot alias. (A single barrier per group can: with both final PVs already complete, a
     // wait for the older parity equals the parity of the current, incomplete phase and never returns.)
     auto wait_pv = [&](uint32_t jj, int tag) { mbar_wait(&o_done[g * 2 + (jj & 1)], (jj >> 1) & 1u, tag); };
-    // the running max moved by more than the threshold: wait for the group's previous PV, rescale the own O row
-    auto rescale = [&](float mt, float& m, float& l) {
+    // The running max of some row of this warp moved by more than the threshold: wait for the group's previous PV and
+    // rescale the O rows. The decision is taken PER WARP (__any_sync at the call sites) and every lane runs the sequence:
+    // tcgen05.ld / st / wait are .sync.aligned, i.e. warp-collective -- executed under a per-thread condition (as this
+    // was first written) they hang as soon as a real rescale happens, which random-init weights never trigger and the
+    // kernel tests did not reach until test_long_attention_lazy_rescale_paths. Lanes that do not need it multiply by 1.
+    auto rescale = [&](bool need, float mt, float& m, float& l) {
       wait_pv(j - 1, 68);
       tc_fence_after();
-      const float f = ex2_ftz(m - mt);
-      l *= f;
-      m = mt;
+      const float f = need ? ex2_ftz(m - mt) : 1.f;
+      if (need) {
+        l *= f;
+        m = mt;
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t ov[32];
@@ -581,7 +587,10 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
               mx[e] = fmaxf(mx[e], fmaxf(__uint_as_float(v0[c + e]), __uint_as_float(v1[c + e])));
           const float mt = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * sl2;
           if (u == 0) m = mt;
-          else if (mt > m + 8.f) rescale(mt, m, l);      // lazy: probabilities stay <= 2^8 otherwise
+          {
+            const bool need = u != 0 && mt > m + 8.f;      // lazy: probabilities stay <= 2^8 otherwise
+            if (__any_sync(0xffffffffu, need)) rescale(need, mt, m, l);
+          }
           const float mneg = -m;
           float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #if VITED_SOFTMAX_PACKED
@@ -632,7 +641,10 @@ attn_l64_kernel(AttnArgs a, const __grid_constant__ L64Maps maps, int n_items) {
           tmem_ld_wait();
           const float mt = __uint_as_float(vc[0]) * sl2;
           if (u == 0) m = mt;
-          else if (mt > m + 8.f) rescale(mt, m, l);
+          {
+            const bool need = u != 0 && mt > m + 8.f;
+            if (__any_sync(0xffffffffu, need)) rescale(need, mt, m, l);
+          }
           const float pc = ex2_ftz(mt - m);
           l += pc;
           uint32_t pc8[8] = {pack_act(pc, 0.f), 0u, 0u, 0u, 0u, 0u, 0u, 0u};

@@ -151,6 +151,7 @@ struct GemmCfg {
 template <int ACT>
 __device__ __forceinline__ void epilogue_tile(const uint32_t (&v0)[32], const uint32_t (&v1)[32],
                                               const float* __restrict__ bias, int n0, int N, uint8_t* rowp, int lane) {
+  const uint32_t rowp_s = smem_u32(rowp);
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
     const uint32_t* v = ch == 0 ? v0 : v1;
@@ -158,12 +159,10 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t (&v0)[32], const ui
     float f[32];
     if (nc + 32 <= N) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i) {   // packed fp32 pairs: one FADD2 per two columns
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nc) + i);
-        f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b4.x;
-        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
-        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
-        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+        f2_unpack(f2_add(f2_from_bits(v[4 * i + 0], v[4 * i + 1]), f2_pack(b4.x, b4.y)), f[4 * i + 0], f[4 * i + 1]);
+        f2_unpack(f2_add(f2_from_bits(v[4 * i + 2], v[4 * i + 3]), f2_pack(b4.z, b4.w)), f[4 * i + 2], f[4 * i + 3]);
       }
     } else {
 #pragma unroll
@@ -183,7 +182,7 @@ __device__ __forceinline__ void epilogue_tile(const uint32_t (&v0)[32], const ui
       pk.y = pack_act(f[8 * i + 2], f[8 * i + 3]);
       pk.z = pack_act(f[8 * i + 4], f[8 * i + 5]);
       pk.w = pack_act(f[8 * i + 6], f[8 * i + 7]);
-      *reinterpret_cast<uint4*>(rowp + (((ch * 4 + i) ^ (lane & 7)) << 4)) = pk;
+      sts_u4(rowp_s + (((ch * 4 + i) ^ (lane & 7)) << 4), pk);   // explicit st.shared on a 32-bit address
     }
   }
 }

@@ -67,7 +67,12 @@ constexpr uint32_t kColS = LN_N;   // first TMEM column of the two hidden-chunk 
 __device__ long long g_mlp_trace[2 * 32 * 8];   // [0 = GELU/epilogue warp (q0,c0), 1 = MMA warp][tile][event]
 #define TRM(who, t, ev, val) do { if (blockIdx.x == 0 && lane == 0 && (t) < 32) g_mlp_trace[((who) * 32 + (t)) * 8 + (ev)] = (val); } while (0)
 #define TRM_CLK() clock64()
+__device__ long long g_mlp_trace2[32 * 8];      // pass-1 breakdown of epilogue warp (q0, c0) per tile, summed over its chunks
+#define TR2(t, ev, val) do { if (blockIdx.x == 0 && ew == 0 && lane == 0 && (t) < 32) g_mlp_trace2[(t) * 8 + (ev)] = (val); } while (0)
+#define TR2_ACC(accu, c0, c1) do { accu += (c1) - (c0); } while (0)
 #else
+#define TR2(t, ev, val) do { } while (0)
+#define TR2_ACC(accu, c0, c1) do { } while (0)
 #define TRM(who, t, ev, val) do { } while (0)
 #define TRM_CLK() 0ll
 #endif
@@ -359,19 +364,23 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // ---- pass 1: v = acc / 2 + b2 + x (the hidden operands are 2 GELU); park v in TMEM, write it back to the residual
       //      stream, shifted statistics ----
       float s = 0.f, ss = 0.f, c0 = 0.f;
+      long long p1_ld = 0, p1_sw = 0, p1_v = 0, p1_st = 0, p1_fence = 0, p1_tma = 0; (void)p1_ld; (void)p1_sw; (void)p1_v; (void)p1_st; (void)p1_fence; (void)p1_tma;
 #pragma unroll 1
       for (int j = 0; j < CHUNKS; ++j, ++g) {
         const int col0 = c * NW + j * XW;
+        const long long k0 = TRM_CLK(); (void)k0;
         uint32_t acc[XW];
         tmem_ld_cols(tlane + j * XW, acc);
         mbar_wait(&my_xfull[g & 1], (uint32_t)(g >> 1) & 1u, 31);
         tmem_ld_wait();
+        const long long k1 = TRM_CLK(); (void)k1;
         // shared-window addresses of this lane's row in the in-box / out-box (16-byte chunk i lives at swz_chunk(i))
         const uint32_t in_row = smem_u32(xbox) + (uint32_t)(g & 1) * Cfg::XBOX + lane * ROWB;
         const uint32_t out_row = smem_u32(obox) + lane * ROWB;
         const uint32_t bias_a = smem_u32(sBias) + col0 * 4;
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the out-box
         __syncwarp();
+        const long long k2 = TRM_CLK(); (void)k2;
         // first the updated row: it goes to the out-box at once, so that the stores have drained by the time the proxy
         // fence in front of the TMA store is reached (MEMBAR.ALL.CTA waits for every store in flight: ~300 cycles when it
         // came right behind the last store); the statistics are computed while they drain
@@ -390,6 +399,7 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           acc[4 * i + 2] = __float_as_uint(v.z); acc[4 * i + 3] = __float_as_uint(v.w);
         }
         if (j == 0) c0 = __uint_as_float(acc[0]);
+        const long long k3 = TRM_CLK(); (void)k3;
         {
           uint64_t s2[2] = {0ull, 0ull}, q2[2] = {0ull, 0ull};                 // four independent chains each
           const uint64_t nc0 = f2_dup(-c0);
@@ -405,16 +415,22 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
           ss += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
+        const long long k4 = TRM_CLK(); (void)k4;
         tmem_st_cols(tlane + j * XW, acc);
         fence_proxy_async_smem();
         __syncwarp();                             // every lane has read the in-box and written the out-box
+        const long long k5 = TRM_CLK(); (void)k5;
         if (lane == 0) {
           if (j + 2 < CHUNKS) issue_x(j + 2, g + 2);   // refill the in-box right away (boxes never cross a tile here)
           tma_store_2d(&tmX, obox, col0, row0);
           tma_store_commit();
         }
+        const long long k6 = TRM_CLK(); (void)k6;
+        TR2_ACC(p1_ld, k0, k1); TR2_ACC(p1_sw, k1, k2); TR2_ACC(p1_v, k2, k3); TR2_ACC(p1_st, k3, k4); TR2_ACC(p1_fence, k4, k5);
+        TR2_ACC(p1_tma, k5, k6);
       }
       tmem_st_wait();
+      TR2(t, 0, p1_ld); TR2(t, 1, p1_sw); TR2(t, 2, p1_v); TR2(t, 3, p1_st); TR2(t, 4, p1_fence); TR2(t, 5, p1_tma);
       if (ew == 0) TRM(0, t, 3, TRM_CLK());
       // the residual boxes are done: once the last out-box store has been read, the h-tile producer may refill the region
       if (lane == 0) {
@@ -563,5 +579,8 @@ int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_
 #ifdef VITED_MLP_TRACE
 extern "C" __attribute__((visibility("default"))) int vited_debug_mlp_trace(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, vited::g_mlp_trace, sizeof(long long) * 2 * 32 * 8);
+}
+extern "C" __attribute__((visibility("default"))) int vited_debug_mlp_trace2(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, vited::g_mlp_trace2, sizeof(long long) * 32 * 8);
 }
 #endif
