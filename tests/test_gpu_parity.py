@@ -203,6 +203,64 @@ def test_hisfrag_model_retrieval_metrics_reported(hisfrag_case):
     np.testing.assert_allclose(m_dev[:2], m_cuda[:2], rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('gain', [4.0, 10.0])
+def test_sharp_attention_matches_oracle_on_the_production_shape(gain):
+    """Weights of a TRAINED model give attention logits far larger than random-init ones. A production-shaped model
+    (embed_dim 384, 6 heads of 64, 256 patch tokens, 1 + 2 layers: fused Linear + LN / fused MLP kernels and the tcgen05
+    long-sequence attention) with every query / key projection scaled up so that the softmax is sharp and row maxima
+    move by far more than the lazy-rescale threshold from key block to key block; 9 fragments = 45 pairs = 11,565 token
+    rows (the fused path), against the fp32 oracle. Until the kernel-level rescale test existed, the rescale path of the
+    long-sequence attention had never run (and hung): this is the same check at model level."""
+    import vited_b200
+    from oracle import vited_oracle as orc
+    from vited_b200 import grid, synthetic
+    kw = dict(img_size=256, patch_size=16, num_classes=1, embed_dim=384, depth=1, c_depth=2, num_heads=6)
+    sd = synthetic.synthetic_state_dict(synthetic.state_dict_shapes(**kw), seed=11)
+    d = kw['embed_dim']
+    for k in list(sd):
+        if k.endswith('attn.qkv.weight') or k.endswith('attn.qkv.bias'):
+            sd[k] = sd[k].clone()
+            sd[k][:2 * d] *= gain                      # q and k rows of the fused qkv projection
+        elif k.endswith('cross_attn.q.weight') or k.endswith('cross_attn.q.bias'):
+            sd[k] = sd[k] * gain
+        elif k.endswith('cross_attn.kv.weight') or k.endswith('cross_attn.kv.bias'):
+            sd[k] = sd[k].clone()
+            sd[k][:d] *= gain                          # k rows
+    model = vited_b200.VisionTransformerCustom(mlp_ratio=4., qkv_bias=True, **kw)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    images, _ = synthetic.synthetic_fragments(3, 3, kw['img_size'], seed=9, writer_seed=4)
+    want = orc.score_fragment_grid(sd, kw['num_heads'], images)
+    got = grid.score_fragments(model, images.cuda()).cpu()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs().max().item()
+    rel = ((got - want).norm() / want.norm()).item()
+    print(f'[{vited_b200.ACT_NAME}] sharp attention (q / k gain {gain}): max |logit - fp32 oracle| {err:.5f}, relative L2 {rel:.2e}, '
+          f'logit range [{want.min().item():.2f}, {want.max().item():.2f}]')
+    # Sharp softmaxes amplify the 16-bit rounding of q and k (scores of several tens of nats): what the operand type
+    # alone costs is measured by re-running the oracle's arithmetic with the engine's rounding points
+    # (tests/analysis/sim_operand_dtype.py). gain 4: 1.4e-3, inside the north-star 2e-2; gain 10: 6e-2 with fp16
+    # operands (0.19 with bf16) -- the kernels must stay within that budget, and must not hang.
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('sim_operand_dtype', os.path.join(os.path.dirname(__file__), 'analysis',
+                                                                                      'sim_operand_dtype.py'))
+    simmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(simmod)
+    n = images.shape[0]
+    a = torch.tensor([i for i in range(n) for j in range(i, n)])
+    b = torch.tensor([j for i in range(n) for j in range(i, n)])
+    outs = []
+    for dt in (None, vited_b200.act_dtype()):
+        sim = simmod.Sim(sd, kw['num_heads'], dt)
+        with torch.no_grad():
+            outs.append(sim.decode(sim.encode(images)[a], images[b])[:, 0])
+    budget = (outs[1] - outs[0]).abs().max().item()
+    assert (outs[0] - want[a, b]).abs().max().item() < 1e-3          # the simulation's fp32 pass is the oracle
+    print(f'    16-bit operand rounding alone (CPU simulation): {budget:.5f}')
+    assert err < max(2e-2, 2.0 * budget) and rel < max(2e-2, 2.0 * budget / want.abs().max().item())
+
+
 def test_grid_properties_puzzle_model():
     """Size-independent properties on the real puzzle model: grid == pair-wise API; row sharding is exact;
     chunking and layer-0 caching do not change results; every off-diagonal entry is written."""
