@@ -523,7 +523,12 @@ def run_hisfrag(args):
     model.load_state_dict(synthetic.synthetic_state_dict(model, seed=0), strict=True)
     model = model.to(dev).eval()
     n = args.items
-    images = synthetic.synthetic_images(n, 512, seed=1000, smooth=False).to(dev)
+    if n <= 512:
+        images = synthetic.synthetic_images(n, 512, seed=1000, smooth=False).to(dev)
+    else:   # built in blocks of 128 so that eight ranks do not hold 8 x 40 GB of host temporaries (4096 fragments)
+        images = torch.empty(n, 3, 512, 512, device=dev)
+        for c0 in range(0, n, 128):
+            images[c0:c0 + 128] = synthetic.synthetic_images(min(128, n - c0), 512, seed=1000 + c0, smooth=False).to(dev)
     n_pairs = n * (n + 1) // 2
     if world == 1:
         lo, hi = 0, n
