@@ -197,6 +197,8 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (lane == 0) {
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = pair + t * num_pairs;
+        // (an L2 prefetch of these rows issued at g1_done of the previous tile -- a whole epilogue ahead of the load --
+        //  measured 0.5470 vs 0.5455 ms: no gain; profiles/README.md item 43)
         mbar_wait(a_free, (uint32_t)(t & 1) ^ 1u, 12);     // the previous tile's residual boxes are done with the region
         if (rank == 0) mbar_arrive_expect_tx(a_full, 2 * Cfg::A_BYTES);
         for (int kb = 0; kb < KB1; ++kb)
