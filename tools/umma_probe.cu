@@ -39,6 +39,8 @@ struct Params {
   uint32_t b_lbo, b_sbo, b_swz, b_kstep;
   uint32_t b_kblock_elems, b_kblock_bytes;
   uint32_t idesc;
+  int d_lane;              // lane offset of the D address (M = 64 layout probe)
+  int prefill;             // 1: fill the D columns of all 128 lanes with a sentinel first
 };
 
 __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* out, Params p) {
@@ -79,7 +81,17 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  if (p.prefill) {
+    for (int c0 = 0; c0 < p.N; c0 += 8) {
+      const uint32_t sv = __float_as_uint(12345.f);
+      const uint32_t taddr = tbase + c0 + ((uint32_t)(warp * 32) << 16);
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(sv) : "memory");
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
   __syncthreads();
+  const uint32_t tD = tbase + ((uint32_t)p.d_lane << 16);
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     for (int ks = 0; ks < p.K / 16; ++ks) {
@@ -90,12 +102,12 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
       const uint32_t acc = ks > 0 ? 1u : 0u;
       if (p.a_from_tmem) {
         const uint32_t ta = tA + ks * 8;
-        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(tbase),
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(tD),
                      "r"(ta), "l"(db), "r"(p.idesc), "r"(acc)
                      : "memory");
       } else {
         const uint64_t da = make_desc(smem_u32(sA) + a_off, p.a_lbo, p.a_sbo, p.a_swz);
-        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tbase),
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tD),
                      "l"(da), "l"(db), "r"(p.idesc), "r"(acc)
                      : "memory");
       }
@@ -196,6 +208,20 @@ int main(int argc, char** argv) {
     p.b_sbo = swap ? 16 : group;
     p.b_kstep = 2 * group; p.b_kblock_elems = 1 << 20; p.b_kblock_bytes = 0;
     p.idesc = idesc_base | (1u << 16) | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(p.M >> 4) << 24);
+  } else if (!strcmp(var, "m64")) {
+    // D[64x80] = Q[64x32] * K[80x32]^T with M = 64: WHERE in TMEM do the 64 rows land, and can the D address carry a lane
+    // offset (argv[2])? The answer decides whether two 64-row units can share the 128 lanes of one column range.
+    p.M = 64; p.N = 80; p.K = 32;
+    A.resize(64 * 32); B.resize(80 * 32);
+    for (auto& x : A) x = rnd();
+    for (auto& x : B) x = rnd();
+    put(a_img, 64, 32, 64, A);
+    put(b_img, 80, 32, 64, B);
+    p.a_lbo = 16; p.a_sbo = 512; p.a_swz = 4; p.a_kstep = 32; p.a_kblock_elems = 32; p.a_kblock_bytes = 0;
+    p.b_lbo = 16; p.b_sbo = 512; p.b_swz = 4; p.b_kstep = 32; p.b_kblock_elems = 32; p.b_kblock_bytes = 0;
+    p.idesc = idesc_base | ((uint32_t)(p.N >> 3) << 17) | ((uint32_t)(p.M >> 4) << 24);
+    p.d_lane = swap;       // second argument = lane offset here
+    p.prefill = 1;
   } else {
     printf("unknown variant %s\n", var);
     return 1;
@@ -216,6 +242,31 @@ int main(int argc, char** argv) {
   CK(cudaDeviceSynchronize());
   std::vector<float> out((size_t)128 * p.N);
   CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  if (!strcmp(var, "m64")) {
+    // which logical row does every TMEM lane hold?
+    printf("variant=m64 d_lane=%d: lane <- row ('.' = untouched sentinel, '?' = something else)\n", p.d_lane);
+    for (int l = 0; l < 128; ++l) {
+      int found = -2;
+      bool sentinel = true;
+      for (int n = 0; n < p.N; ++n) sentinel = sentinel && out[(size_t)l * p.N + n] == 12345.f;
+      if (sentinel) found = -1;
+      else
+        for (int r = 0; r < 64 && found == -2; ++r) {
+          double e = 0;
+          for (int n = 0; n < p.N; ++n) {
+            double ref = 0;
+            for (int k = 0; k < p.K; ++k) ref += (double)A[r * p.K + k] * B[n * p.K + k];
+            e = fmax(e, fabs(ref - out[(size_t)l * p.N + n]));
+          }
+          if (e < 1e-2) found = r;
+        }
+      if (found == -1) printf("  .");
+      else if (found == -2) printf("  ?");
+      else printf(" %2d", found);
+      if ((l & 31) == 31) printf("   | lanes %d-%d\n", l - 31, l);
+    }
+    return 0;
+  }
   double maxerr = 0, maxref = 0;
   for (int m = 0; m < 128; ++m)
     for (int n = 0; n < p.N; ++n) {
