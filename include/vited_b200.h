@@ -68,14 +68,9 @@ enum {
                                    (embed_dim 384, large row counts); 0 = separate resid_ln kernel                  */
   VITED_OPT_KV_BUDGET_MB = 7,   /* vited_score_grid processes context rows in blocks whose K/V cache (all decoder
                                    layers) fits this many MB (default 8000; Hisfrag: 18.9 MB per fragment)          */
-  VITED_OPT_FUSE_MLP = 8,       /* 1 (default) = the MLP sub-block (fc1, GELU, fc2), its residual add and the next
+  VITED_OPT_FUSE_MLP = 8        /* 1 (default) = the MLP sub-block (fc1, GELU, fc2), its residual add and the next
                                    layer's LayerNorm run in one kernel, hidden activations never written (needs
                                    FUSE_LN; embed_dim 384, large row counts); 0 = fc1 GEMM + fused fc2 GEMM          */
-  VITED_OPT_FOLD_LN = 9         /* 1 = the weight / bias of every block LayerNorm are folded into the Linear that
-                                   consumes its output (qkv, q, kv, fc1: W diag(g), b + W beta, from the fp32 weights
-                                   as loaded) and the LayerNorm kernels emit the plain normalised row. Switching it on
-                                   for the first time after weights were loaded drops them (the fp32 sources were not
-                                   kept): vited_num_weights_loaded returns 0 until they are loaded again. Default 0  */
 };
 
 /* Library-wide last error message (thread-local). */

@@ -308,43 +308,6 @@ def test_grid_properties_puzzle_model():
     np.testing.assert_allclose(both.cpu().numpy(), full.cpu().numpy(), rtol=0, atol=1e-2)
 
 
-@pytest.mark.parametrize('name,n_items', [('puzzle_patch8_64', 24), ('small_hd32', 9)])
-def test_fold_ln_option_matches_oracle(name, n_items, monkeypatch):
-    """Option FOLD_LN: LayerNorm weight / bias folded into the consumer Linear at load time (W diag(g), b + W beta),
-    every block LayerNorm emits the plain normalised row. Mathematically the same function; checked against the fp32
-    oracle at the same tolerance as the default path, on the fused launch sequence (puzzle model, 552 pairs = 35,880
-    rows) and on the unfused one (embed_dim != 384). Switching the option off again restores the default results bit
-    for bit, and a reload of the weights under the option is folded again."""
-    import vited_b200
-    from oracle import vited_oracle as orc
-    from vited_b200 import grid
-    monkeypatch.delenv('VITED_FOLD_LN', raising=False)   # (a run of the suite with every engine folded sets it)
-    model, sd, kw, images = _grid_case(name, n_items)
-    images_d = images.cuda()
-    want = orc.score_puzzle_grid(sd, kw['num_heads'], images, batch=138)
-    base = grid.score_puzzle(model, images_d).cpu()
-    model.set_option(vited_b200.OPT_FOLD_LN, 1)
-    folded = grid.score_puzzle(model, images_d).cpu()
-    tol = TIGHT if vited_b200.ACT_NAME == 'fp16' else TOL
-    assert (base - want).abs().max().item() < tol
-    assert (folded - want).abs().max().item() < tol, (folded - want).abs().max().item()
-    assert not torch.equal(folded, base)                  # the option did change the arithmetic
-    # new weights while the option is on: folded again (LayerNorm parameters far from the identity)
-    sd2 = {k: v.clone() for k, v in sd.items()}
-    for k in sd2:
-        if '.norm' in k:
-            sd2[k] = sd2[k] * 1.5 + (0.2 if k.endswith('bias') else 0.0)
-    model.load_state_dict(sd2, strict=True)
-    folded2 = grid.score_puzzle(model, images_d).cpu()
-    want2 = orc.score_puzzle_grid(sd2, kw['num_heads'], images, batch=138)
-    assert (folded2 - want2).abs().max().item() < TOL, (folded2 - want2).abs().max().item()
-    # off again: the default path, bit for bit
-    model.load_state_dict(sd, strict=True)
-    model.set_option(vited_b200.OPT_FOLD_LN, 0)
-    again = grid.score_puzzle(model, images_d).cpu()
-    assert torch.equal(again, base)
-
-
 def test_argmax_agreement_puzzle_model():
     """>= 99.9 % identical argmax adjacency vs the fp32 oracle is the north-star bar; on a few hundred pairs the
     resolution is coarser, so this asserts: no flip on any pair whose fp32 top-2 margin exceeds 2e-2, and the max

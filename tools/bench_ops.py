@@ -75,14 +75,12 @@ def main():
             xx = torch.randn(M, 384, device='cuda')
             lw = torch.ones(384, device='cuda'); lb = torch.zeros(384, device='cuda')
             hh = torch.empty(M, 384, dtype=L.act_dtype(), device='cuda')
+            ms = timeit(lambda: L.check(L.lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), xx.data_ptr(), lw.data_ptr(),
+                                                                      lb.data_ptr(), hh.data_ptr(), M, 384, K, 1e-6, st), 'gemm_ln'), flush=flush)
             fl = 2.0 * M * 384 * K
             by = M * K * 2 + 384 * K * 2 + M * 384 * (4 + 4 + 2)
-            # affine = LayerNorm weight / bias applied in the epilogue; plain = folded into the consumer Linear (FOLD_LN)
-            for tag, pw, pb in (('', lw.data_ptr(), lb.data_ptr()),) + ((('_plain', None, None),) if epi == '8' else ()):
-                ms = timeit(lambda: L.check(L.lib.vited_op_gemm_resid_ln(A.data_ptr(), W.data_ptr(), b.data_ptr(), xx.data_ptr(), pw,
-                                                                          pb, hh.data_ptr(), M, 384, K, 1e-6, st), 'gemm_ln'), flush=flush)
-                out.append(dict(op=f'gemm_ln_{name}' + ('_epi16' if epi == '16' else '') + tag, M=M, N=384, K=K, ms=ms,
-                                tflops=fl / ms / 1e9, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+            out.append(dict(op=f'gemm_ln_{name}' + ('_epi16' if epi == '16' else ''), M=M, N=384, K=K, ms=ms, tflops=fl / ms / 1e9,
+                            gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
             del A, W, xx, hh
         # fused MLP sub-block + residual + LayerNorm (fc1 -> GELU -> fc2, hidden activations never written)
         hin = torch.randn(M, 384, device='cuda').to(L.act_dtype())
@@ -94,14 +92,13 @@ def main():
         hh = torch.empty(M, 384, dtype=L.act_dtype(), device='cuda')
         for epi in epis:
             os.environ['VITED_EPI_WARPS'] = epi
+            ms = timeit(lambda: L.check(L.lib.vited_op_mlp_resid_ln(hin.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                                                     xx.data_ptr(), lw.data_ptr(), lb.data_ptr(), hh.data_ptr(), M, 384, 1536,
+                                                                     1e-6, st), 'mlp_ln'), flush=flush)
             fl = 4.0 * M * 384 * 1536
             by = M * 384 * (2 + 4 + 4 + 2) + 4 * 384 * 1536
-            for tag, pw, pb in (('', lw.data_ptr(), lb.data_ptr()),) + ((('_plain', None, None),) if epi == '8' else ()):
-                ms = timeit(lambda: L.check(L.lib.vited_op_mlp_resid_ln(hin.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
-                                                                         xx.data_ptr(), pw, pb, hh.data_ptr(), M, 384, 1536,
-                                                                         1e-6, st), 'mlp_ln'), flush=flush)
-                out.append(dict(op='mlp_ln' + ('_epi16' if epi == '16' else '') + tag, M=M, D=384, hidden=1536, ms=ms,
-                                tflops=fl / ms / 1e9, tflops_frac=fl / ms / 1e9 / tf, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
+            out.append(dict(op='mlp_ln' + ('_epi16' if epi == '16' else ''), M=M, D=384, hidden=1536, ms=ms, tflops=fl / ms / 1e9,
+                            tflops_frac=fl / ms / 1e9 / tf, gbs=by / ms / 1e6, gbs_frac=by / ms / 1e6 / hbm))
         os.environ.pop('VITED_EPI_WARPS', None)
         del hin, xx, hh
     if want('ln'):

@@ -1,4 +1,5 @@
 #!/usr/bin/env bash
+# (ran on commit 2388076, which carried the FOLD_LN option; the option was measured and removed again: profiles/README.md item 46)
 # Round 2, third session (10 GPU-minutes left): the whole GPU suite on the session's code (default path + the new
 # FOLD_LN tests), A/B of FOLD_LN through bench.py (lean form), the parity suite with every engine folded
 # (VITED_FOLD_LN=1), the M = 64 layout probe. Most valuable first: the call may be cut short.

@@ -43,7 +43,6 @@ OPT_PRUNE_TAIL = 5
 OPT_FUSE_LN = 6
 OPT_KV_BUDGET_MB = 7
 OPT_FUSE_MLP = 8
-OPT_FOLD_LN = 9
 
 _vp = ctypes.c_void_p
 _i = ctypes.c_int

@@ -55,13 +55,8 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct Linear { act_t* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
 struct LNorm { float* w = nullptr; float* b = nullptr; };
-// A Linear fed by a LayerNorm output (qkv, q, kv, fc1) can carry that LayerNorm's affine part (option FOLD_LN):
-// wsrc = the fp32 weight as loaded, wf / bf = act(W diag(g)) / b + W beta, ln = the producing LayerNorm.
-struct Linear {
-  act_t* w = nullptr; float* b = nullptr; int out = 0, in = 0;
-  const LNorm* ln = nullptr; float* wsrc = nullptr; act_t* wf = nullptr; float* bf = nullptr;
-};
 struct EncBlock { LNorm norm1, norm2; Linear qkv, proj, fc1, fc2; };
 struct DecBlock { LNorm norm1, norm_cross, norm_context, norm2; Linear qkv, proj, q, kv, cproj, fc1, fc2; };
 
@@ -70,7 +65,6 @@ struct Slot {
   bool to_act;
   int64_t numel;
   bool loaded;
-  Linear* lin = nullptr;   // weight of a LayerNorm-fed Linear: its fp32 source is staged for the fold
 };
 
 }  // namespace vited
@@ -101,13 +95,6 @@ struct vited_engine {
   int prune_tail = 1;   // last decoder layer: only the class-token row continues past self-attention
   int fuse_ln = 1;      // residual + LayerNorm in the epilogue of the N = 384 GEMMs (gemm_ln.cu)
   int fuse_mlp = 1;     // fc1 + GELU + fc2 + residual + LayerNorm in one kernel (mlp_ln.cu); needs fuse_ln
-  // LayerNorm weight / bias folded into the Linear that consumes the LayerNorm output: every block LayerNorm then emits
-  // the plain normalised row (the full-row epilogues lose their parameter loads). Off by default.
-  int fold_ln = 0;
-  bool fold_dirty = true;            // a weight changed since the last fold
-  std::vector<Linear*> consumers;    // the LayerNorm-fed Linears
-  float* ones = nullptr;             // identity LayerNorm parameters for the unfused resid_ln kernel
-  float* zeros = nullptr;
   int kv_budget_mb = 8000;  // K/V cache budget of one block of context rows in vited_score_grid
   int64_t launches = 0;
   // optional per-kernel timing (bench.py's roofline): one event before every launch, intervals summed per class
@@ -147,7 +134,7 @@ static int alloc_act(vited_engine* e, act_t** p, size_t n) {
   return 0;
 }
 static void reg(vited_engine* e, const std::string& name, void* dst, bool to_act, int64_t numel) {
-  e->slots[name] = Slot{dst, to_act, numel, false, nullptr};
+  e->slots[name] = Slot{dst, to_act, numel, false};
   e->names.push_back(name);
 }
 static int make_linear(vited_engine* e, const std::string& prefix, Linear* l, int out, int in, bool bias) {
@@ -164,36 +151,6 @@ static int make_ln(vited_engine* e, const std::string& prefix, LNorm* n, int D) 
   TRY(alloc_f32(e, &n->b, D));
   reg(e, prefix + ".weight", n->w, false, D);
   reg(e, prefix + ".bias", n->b, false, D);
-  return 0;
-}
-// `l` (registered under `prefix`) only ever sees the output of LayerNorm `n` (vision_transformer.py:124-127, :268-272)
-static void fed_by(vited_engine* e, const std::string& prefix, Linear* l, const LNorm* n) {
-  l->ln = n;
-  e->slots[prefix + ".weight"].lin = l;
-  e->consumers.push_back(l);
-}
-// buffers of the fold (FOLD_LN): fp32 staging copy + folded weight / bias per LayerNorm-fed Linear
-static int fold_alloc(vited_engine* e) {
-  for (Linear* l : e->consumers) {
-    if (l->wsrc) continue;
-    const size_t n = (size_t)l->out * l->in;
-    TRY(alloc_f32(e, &l->wsrc, n));
-    TRY(alloc_act(e, &l->wf, n));
-    TRY(alloc_f32(e, &l->bf, l->out));
-  }
-  if (!e->ones) {
-    TRY(alloc_f32(e, &e->ones, e->D));
-    TRY(alloc_f32(e, &e->zeros, e->D));
-    std::vector<float> one((size_t)e->D, 1.f);
-    VITED_CUDA_OK(cudaMemcpy(e->ones, one.data(), one.size() * 4, cudaMemcpyHostToDevice));
-  }
-  return 0;
-}
-static int fold_all(vited_engine* e, cudaStream_t s) {
-  for (Linear* l : e->consumers)
-    TRY(fold_ln_into_linear(l->wsrc, l->b, l->ln->w, l->ln->b, l->wf, l->bf, l->out, l->in, s));
-  VITED_CUDA_OK(cudaStreamSynchronize(s));   // later calls may come on another stream
-  e->fold_dirty = false;
   return 0;
 }
 
@@ -236,8 +193,6 @@ static int build(vited_engine* e) {
     TRY(make_ln(e, p + ".norm2", &b.norm2, D));
     TRY(make_linear(e, p + ".mlp.fc1", &b.fc1, e->hidden, D, true));
     TRY(make_linear(e, p + ".mlp.fc2", &b.fc2, D, e->hidden, true));
-    fed_by(e, p + ".attn.qkv", &b.qkv, &b.norm1);
-    fed_by(e, p + ".mlp.fc1", &b.fc1, &b.norm2);
   }
   e->dec.resize(c.c_depth);
   for (int l = 0; l < c.c_depth; ++l) {
@@ -254,10 +209,6 @@ static int build(vited_engine* e) {
     TRY(make_ln(e, p + ".norm2", &b.norm2, D));
     TRY(make_linear(e, p + ".mlp.fc1", &b.fc1, e->hidden, D, true));
     TRY(make_linear(e, p + ".mlp.fc2", &b.fc2, D, e->hidden, true));
-    fed_by(e, p + ".attn.qkv", &b.qkv, &b.norm1);
-    fed_by(e, p + ".cross_attn.q", &b.q, &b.norm_cross);
-    fed_by(e, p + ".cross_attn.kv", &b.kv, &b.norm_context);
-    fed_by(e, p + ".mlp.fc1", &b.fc1, &b.norm2);
   }
   TRY(make_ln(e, "norm", &e->norm, D));
   TRY(alloc_f32(e, &e->head_w, (size_t)e->C * D));
@@ -289,18 +240,6 @@ static void prof_mark(vited_engine* e, const char* name, double flops, double by
   e->recs.push_back({ev, prof_class(e, name), flops, bytes});
 }
 
-// FOLD_LN: a LayerNorm-fed Linear runs on its folded weight / bias, every block LayerNorm without its affine part
-static inline bool folded(const vited_engine* e, const Linear& l) { return e->fold_ln && l.wf != nullptr; }
-static inline const act_t* lin_w(const vited_engine* e, const Linear& l) { return folded(e, l) ? l.wf : l.w; }
-static inline const float* lin_b(const vited_engine* e, const Linear& l) { return folded(e, l) ? l.bf : l.b; }
-// output rows [r0, r0 + n) of a Linear as a Linear of its own (the last layer's k|v and q parts of qkv)
-static Linear linear_rows(const Linear& l, int r0, int n) {
-  Linear r = l;
-  r.w = l.w + (size_t)r0 * l.in; r.b = l.b + r0; r.out = n;
-  if (l.wf) { r.wf = l.wf + (size_t)r0 * l.in; r.bf = l.bf + r0; }
-  return r;
-}
-
 static int L_gemm(vited_engine* e, const act_t* A, const Linear& l, act_t* Cout, int M, int act, cudaStream_t s) {
   if (e->profile) {
     char nm[64];
@@ -309,7 +248,7 @@ static int L_gemm(vited_engine* e, const act_t* A, const Linear& l, act_t* Cout,
   } else {
     e->launches++;
   }
-  return gemm_act(A, lin_w(e, l), lin_b(e, l), Cout, M, l.out, l.in, act, e->gemm_impl, s);
+  return gemm_act(A, l.w, l.b, Cout, M, l.out, l.in, act, e->gemm_impl, s);
 }
 // fused x += A W^T + b; h = LN(x)  (gemm_ln.cu). Caller has checked use_fused_ln().
 static bool use_fused_ln(vited_engine* e, size_t rows, const Linear& l) {
@@ -325,7 +264,7 @@ static int L_gemm_ln(vited_engine* e, const act_t* A, const Linear& l, float* x,
   } else {
     e->launches++;
   }
-  return gemm_resid_ln(A, l.w, l.b, x, e->fold_ln ? nullptr : ln.w, e->fold_ln ? nullptr : ln.b, h, M, l.out, l.in, 1e-6f, s);
+  return gemm_resid_ln(A, l.w, l.b, x, ln.w, ln.b, h, M, l.out, l.in, 1e-6f, s);
 }
 // fused x += fc2(GELU(fc1(h))) ; h = LN(x)  (mlp_ln.cu)
 static bool use_fused_mlp(vited_engine* e, size_t rows, const Linear& fc1, const Linear& fc2) {
@@ -342,14 +281,13 @@ static int L_mlp_ln(vited_engine* e, const act_t* h_in, const Linear& fc1, const
   } else {
     e->launches++;
   }
-  return mlp_resid_ln(h_in, lin_w(e, fc1), lin_b(e, fc1), fc2.w, fc2.b, x, e->fold_ln ? nullptr : ln.w,
-                      e->fold_ln ? nullptr : ln.b, h_out, M, fc1.in, fc1.out, 1e-6f, s);
+  return mlp_resid_ln(h_in, fc1.w, fc1.b, fc2.w, fc2.b, x, ln.w, ln.b, h_out, M, fc1.in, fc1.out, 1e-6f, s);
 }
 static int L_resid_ln(vited_engine* e, float* x, const act_t* delta, const float* gsrc, const int* gidx, int n_src,
                       const LNorm* ln, act_t* h, int n_seq, int has_cls, int write_x, cudaStream_t s, int g_off = 0) {
   ResidLnArgs a;
   a.x = x; a.delta = delta; a.gather_src = gsrc; a.gather_idx = gidx; a.gather_off = g_off; a.n_src_seq = n_src;
-  a.ln_w = ln ? (e->fold_ln ? e->ones : ln->w) : nullptr; a.ln_b = ln ? (e->fold_ln ? e->zeros : ln->b) : nullptr; a.h = h;
+  a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
   a.n_seq = n_seq; a.n_patch = e->Ne; a.has_cls = has_cls; a.D = e->D; a.write_x = write_x; a.eps = 1e-6f;
   {
     const double rows = (double)n_seq * (e->Ne + (has_cls ? 1 : 0));
@@ -401,7 +339,7 @@ static int L_resid_ln_rows(vited_engine* e, float* x, const act_t* delta, const 
                            const LNorm* ln, act_t* h, int rows, cudaStream_t s, int g_off = 0) {
   ResidLnArgs a;
   a.x = x; a.delta = delta; a.gather_src = gsrc_cls_rows; a.gather_idx = gidx; a.gather_off = g_off; a.n_src_seq = 0;
-  a.ln_w = ln ? (e->fold_ln ? e->ones : ln->w) : nullptr; a.ln_b = ln ? (e->fold_ln ? e->zeros : ln->b) : nullptr; a.h = h;
+  a.ln_w = ln ? ln->w : nullptr; a.ln_b = ln ? ln->b : nullptr; a.h = h;
   a.n_seq = rows; a.n_patch = 1; a.has_cls = 0; a.D = e->D; a.write_x = 1; a.eps = 1e-6f;
   prof_mark(e, "resid_ln", 0.0, (double)rows * e->D * 12.0, s);
   return resid_ln(a, s);
@@ -432,14 +370,10 @@ struct DeviceScope {
   DeviceScope& operator=(const DeviceScope&) = delete;
 };
 
-static int check_ready(vited_engine* e, void* stream) {
+static int check_ready(vited_engine* e) {
   VITED_CHECK(e != nullptr, "null engine");
   VITED_CHECK(e->loaded == (int)e->names.size(), "weights not loaded: %d of %d state_dict tensors received", e->loaded,
               (int)e->names.size());
-  if (e->fold_ln && e->fold_dirty) {
-    DeviceScope scope(e->device);
-    TRY(fold_all(e, (cudaStream_t)stream));
-  }
   return 0;
 }
 
@@ -619,8 +553,8 @@ static int decode_chunk(vited_engine* e, int P, const int* ci, const int* xj, co
         if (first) TRY(L_resid_ln(e, x, nullptr, xsrc, xj, n_src, &b.norm1, h, P, 1, 1, s, x_off));
         else if (!h_is_norm1) TRY(L_resid_ln(e, x, delta, nullptr, nullptr, 0, &b.norm1, h, P, 1, 1, s));
         // keys/values for every token, the query for the class token only (qkv rows: [0,D) q, [D,3D) k|v)
-        const Linear w_kv = linear_rows(b.qkv, (int)D, 2 * (int)D);
-        const Linear w_q = linear_rows(b.qkv, 0, (int)D);
+        Linear w_kv = b.qkv; w_kv.w = b.qkv.w + D * D; w_kv.b = b.qkv.b + D; w_kv.out = 2 * (int)D;
+        Linear w_q = b.qkv; w_q.out = (int)D;
         TRY(L_gemm(e, h, w_kv, qkv, (int)rows, ACT_NONE, s));          // [rows, 2D]
         TRY(L_gemm(e, h_c, w_q, q_c, P, ACT_NONE, s));                 // [P, D]
         TRY(L_attn_cls(e, q, (int)D, qkv, qkv + D, 2 * (int)D, o, P, 1, P, nullptr, s));
@@ -694,14 +628,6 @@ int vited_create(const vited_config* cfg, int device, vited_engine** out) {
     vited_destroy(e);
     return 1;
   }
-  const char* fl = getenv("VITED_FOLD_LN");   // A/B runs; vited_set_option(VITED_OPT_FOLD_LN) is the API
-  if (fl && atoi(fl)) {
-    if (fold_alloc(e) != 0) {
-      vited_destroy(e);
-      return 1;
-    }
-    e->fold_ln = 1;
-  }
   *out = e;
   return 0;
 }
@@ -731,21 +657,6 @@ int vited_set_option(vited_engine* e, int option, int64_t value) {
     case VITED_OPT_PRUNE_TAIL: e->prune_tail = value ? 1 : 0; return 0;
     case VITED_OPT_FUSE_LN: e->fuse_ln = value ? 1 : 0; return 0;
     case VITED_OPT_FUSE_MLP: e->fuse_mlp = value ? 1 : 0; return 0;
-    case VITED_OPT_FOLD_LN: {
-      if (value) {
-        const bool staged = !e->consumers.empty() && e->consumers[0]->wsrc != nullptr;
-        DeviceScope scope(e->device);
-        TRY(fold_alloc(e));
-        if (!staged && e->loaded > 0) {
-          // the fold reads the fp32 weights as loaded, which were not kept: they have to be loaded again
-          for (auto& kv : e->slots) kv.second.loaded = false;
-          e->loaded = 0;
-        }
-      }
-      e->fold_ln = value ? 1 : 0;
-      e->fold_dirty = true;
-      return 0;
-    }
     case VITED_OPT_KV_BUDGET_MB:
       VITED_CHECK(value >= 1, "kv budget must be positive");
       e->kv_budget_mb = value;
@@ -773,9 +684,6 @@ int vited_load_weight(vited_engine* e, const char* name, const float* data, int6
   } else {
     VITED_CUDA_OK(cudaMemcpyAsync(sl.dst, data, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
   }
-  if (sl.lin && sl.lin->wsrc)
-    VITED_CUDA_OK(cudaMemcpyAsync(sl.lin->wsrc, data, (size_t)numel * 4, cudaMemcpyDeviceToDevice, s));
-  e->fold_dirty = true;
   VITED_CUDA_OK(cudaStreamSynchronize(s));
   if (!sl.loaded) {
     sl.loaded = true;
@@ -792,7 +700,7 @@ const char* vited_weight_name(vited_engine* e, int i) {
 }
 
 int vited_encode(vited_engine* e, const float* images, int B, float* out_tokens, void* stream) {
-  TRY(check_ready(e, stream));
+  TRY(check_ready(e));
   DeviceScope scope(e->device);
   VITED_CHECK(B >= 0 && (B == 0 || (images && out_tokens)), "vited_encode: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
@@ -829,7 +737,7 @@ static int decode_impl(vited_engine* e, const float* ctx_tokens, const float* im
 
 int vited_decode(vited_engine* e, const float* ctx_tokens, const float* images, int B, float* out_logits,
                  void* stream) {
-  TRY(check_ready(e, stream));
+  TRY(check_ready(e));
   DeviceScope scope(e->device);
   VITED_CHECK(B >= 0 && (B == 0 || (ctx_tokens && images && out_logits)), "vited_decode: bad arguments");
   const size_t img = (size_t)e->cfg.in_chans * e->cfg.img_size * e->cfg.img_size;
@@ -837,7 +745,7 @@ int vited_decode(vited_engine* e, const float* ctx_tokens, const float* images, 
 }
 
 int vited_forward_pairs(vited_engine* e, const float* pairs, int B, float* out_logits, void* stream) {
-  TRY(check_ready(e, stream));
+  TRY(check_ready(e));
   DeviceScope scope(e->device);
   VITED_CHECK(B >= 0 && (B == 0 || (pairs && out_logits)), "vited_forward_pairs: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
@@ -856,7 +764,7 @@ int vited_forward_pairs(vited_engine* e, const float* pairs, int B, float* out_l
 
 int vited_score_grid(vited_engine* e, const float* images, int N, int mode, int row_begin, int row_end, float* out,
                      void* stream) {
-  TRY(check_ready(e, stream));
+  TRY(check_ready(e));
   DeviceScope scope(e->device);
   VITED_CHECK(mode == VITED_GRID_ORDERED_OFFDIAG || mode == VITED_GRID_UPPER_TRI_DIAG, "unknown grid mode %d", mode);
   VITED_CHECK(N >= 0 && row_begin >= 0 && row_begin <= row_end && row_end <= N, "bad row range [%d, %d) for N=%d",

@@ -56,10 +56,7 @@ __device__ unsigned long long g_ln_trace[3 * 32 * 8];   // [0 = epilogue warp (q
 #define TRL(who, t, ev) do { } while (0)
 #endif
 
-// AFFINE = false: the LayerNorm weight / bias have been folded into the consumer Linear at load time (engine option
-// FOLD_LN), so pass 2 emits the plain normalised row and its warp-uniform parameter loads (four of its five
-// shared-memory accesses per eight outputs) disappear.
-template <int CG, bool AFFINE>
+template <int CG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LnCfg<CG>::kThreads, 1)
 gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
@@ -95,10 +92,8 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   for (int i = threadIdx.x; i < LN_N; i += Cfg::kThreads) {
     sBias[i] = bias[i];
-    if constexpr (AFFINE) {
-      sG[i] = ln_w[i];
-      sBt[i] = ln_b[i];
-    }
+    sG[i] = ln_w[i];
+    sBt[i] = ln_b[i];
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -301,7 +296,6 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (who >= 0) TRL(who, t, 3);
       // ---- pass 2: normalise out of TMEM, fp16, HW-column slabs through the warp's staging box ----
       const uint32_t hbox_a = smem_u32(hbox) + lane * ROWB, g_a = smem_u32(sG), bt_a = smem_u32(sBt);
-      (void)g_a; (void)bt_a;
 #pragma unroll 1
       for (int jj = 0; jj < Cfg::SLABS; ++jj) {
         if (lane == 0) tma_store_wait_read();
@@ -321,21 +315,15 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
+            const float4 g0 = lds_f4(g_a + col0 * 4 + 32 * i);
+            const float4 g1v = lds_f4(g_a + col0 * 4 + 32 * i + 16);
+            const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
+            const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
             float y[8];
-            if constexpr (AFFINE) {
-              const float4 g0 = lds_f4(g_a + col0 * 4 + 32 * i);
-              const float4 g1v = lds_f4(g_a + col0 * 4 + 32 * i + 16);
-              const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
-              const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
-              f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 0], v[8 * i + 1]), nmean2), rstd2), f2_pack(g0.x, g0.y), f2_pack(t0.x, t0.y)), y[0], y[1]);
-              f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 2], v[8 * i + 3]), nmean2), rstd2), f2_pack(g0.z, g0.w), f2_pack(t0.z, t0.w)), y[2], y[3]);
-              f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 4], v[8 * i + 5]), nmean2), rstd2), f2_pack(g1v.x, g1v.y), f2_pack(t1.x, t1.y)), y[4], y[5]);
-              f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 6], v[8 * i + 7]), nmean2), rstd2), f2_pack(g1v.z, g1v.w), f2_pack(t1.z, t1.w)), y[6], y[7]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                f2_unpack(f2_mul(f2_add(f2_from_bits(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]), nmean2), rstd2), y[2 * k], y[2 * k + 1]);
-            }
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 0], v[8 * i + 1]), nmean2), rstd2), f2_pack(g0.x, g0.y), f2_pack(t0.x, t0.y)), y[0], y[1]);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 2], v[8 * i + 3]), nmean2), rstd2), f2_pack(g0.z, g0.w), f2_pack(t0.z, t0.w)), y[2], y[3]);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 4], v[8 * i + 5]), nmean2), rstd2), f2_pack(g1v.x, g1v.y), f2_pack(t1.x, t1.y)), y[4], y[5]);
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 6], v[8 * i + 7]), nmean2), rstd2), f2_pack(g1v.z, g1v.w), f2_pack(t1.z, t1.w)), y[6], y[7]);
             uint4 pk;
             pk.x = pack_act(y[0], y[1]);
             pk.y = pack_act(y[2], y[3]);
@@ -372,7 +360,7 @@ gemm_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 bool gemm_resid_ln_supported(int M, int N, int K) { return N == LN_N && K % 8 == 0 && K >= 8 && M >= 1; }
 
-template <int CG, bool AFFINE>
+template <int CG>
 static int gemm_resid_ln_launch(const act_t* A, const act_t* W, const float* bias, float* x, const float* ln_w,
                                 const float* ln_b, act_t* h, int M, int N, int K, float eps, cudaStream_t stream) {
   using Cfg = LnCfg<CG>;
@@ -380,7 +368,7 @@ static int gemm_resid_ln_launch(const act_t* A, const act_t* W, const float* bia
   VITED_CHECK(sms >= 2, "gemm_resid_ln: no device");
   static PerDeviceOnce once;
   if (once.first())
-    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel<CG, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VITED_CUDA_OK(cudaFuncSetAttribute(gemm_ln_pair_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::SMEM_BYTES));
   CUtensorMap tA, tB, tX, tH;
   if (make_tmap_act_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)K * 2, 64, BM, 128)) return 1;
@@ -390,7 +378,7 @@ static int gemm_resid_ln_launch(const act_t* A, const act_t* W, const float* bia
   const int tiles = (M + 2 * BM - 1) / (2 * BM);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  VITED_CUDA_OK(launch_pdl(gemm_ln_pair_kernel<CG, AFFINE>, dim3(2 * pairs), dim3(Cfg::kThreads), Cfg::SMEM_BYTES, stream, tA, tB, tX,
+  VITED_CUDA_OK(launch_pdl(gemm_ln_pair_kernel<CG>, dim3(2 * pairs), dim3(Cfg::kThreads), Cfg::SMEM_BYTES, stream, tA, tB, tX,
                            tH, bias, ln_w, ln_b, M, K, eps));
   return 0;
 }
@@ -400,13 +388,10 @@ int gemm_resid_ln(const act_t* A, const act_t* W, const float* bias, float* x, c
   VITED_CHECK(gemm_resid_ln_supported(M, N, K), "gemm_resid_ln: unsupported shape M=%d N=%d K=%d (N must be 384)", M, N, K);
   VITED_CHECK(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(x) |
                 reinterpret_cast<uintptr_t>(h)) & 15) == 0, "gemm_resid_ln: operands must be 16-byte aligned");
-  VITED_CHECK((ln_w == nullptr) == (ln_b == nullptr), "gemm_resid_ln: ln_w and ln_b must both be given or both be null");
 #ifdef VITED_EXPERIMENTAL   // measured neutral (profiles/README.md): not in the product library
-  if (epilogue_warps() == 16 && ln_w) return gemm_resid_ln_launch<4, true>(A, W, bias, x, ln_w, ln_b, h, M, N, K, eps, stream);
+  if (epilogue_warps() == 16) return gemm_resid_ln_launch<4>(A, W, bias, x, ln_w, ln_b, h, M, N, K, eps, stream);
 #endif
-  // ln_w == ln_b == null: LayerNorm without its affine part (folded into the consumer Linear, engine option FOLD_LN)
-  if (ln_w == nullptr) return gemm_resid_ln_launch<2, false>(A, W, bias, x, ln_w, ln_b, h, M, N, K, eps, stream);
-  return gemm_resid_ln_launch<2, true>(A, W, bias, x, ln_w, ln_b, h, M, N, K, eps, stream);
+  return gemm_resid_ln_launch<2>(A, W, bias, x, ln_w, ln_b, h, M, N, K, eps, stream);
 }
 
 }  // namespace vited

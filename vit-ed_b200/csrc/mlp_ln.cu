@@ -77,9 +77,7 @@ __device__ long long g_mlp_trace2[32 * 8];      // pass-1 breakdown of epilogue 
 #define TRM_CLK() 0ll
 #endif
 
-// AFFINE = false: LayerNorm weight / bias folded into the consumer Linear at load time (engine option FOLD_LN): pass 2
-// emits the plain normalised row, without its warp-uniform parameter loads (see gemm_ln.cu).
-template <int CG, bool AFFINE>
+template <int CG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MlpCfg<CG>::kThreads, 1)
 mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
                    const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmX,
@@ -123,10 +121,8 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   for (int i = threadIdx.x; i < hidden; i += Cfg::kThreads) sB1[i] = b1[i];
   for (int i = threadIdx.x; i < LN_N; i += Cfg::kThreads) {
     sBias[i] = b2[i];
-    if constexpr (AFFINE) {
-      sG[i] = ln_w[i];
-      sBt[i] = ln_b[i];
-    }
+    sG[i] = ln_w[i];
+    sBt[i] = ln_b[i];
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -474,28 +470,21 @@ mlp_ln_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const uint64_t nmean2 = f2_dup(-mean), rstd2 = f2_dup(rstd);
       // ---- pass 2: normalise out of TMEM, fp16, 32-column chunks through the warp's staging box (64B-swizzled rows) ----
       const uint32_t hbox_a = smem_u32(hbox) + lane * 64, g_a = smem_u32(sG), bt_a = smem_u32(sBt);
-      (void)g_a; (void)bt_a;
       auto normalise_chunk = [&](const uint32_t (&v)[32], int j) {
         const int col0 = c * NW + j * 32;
         if (lane == 0) tma_store_wait_read();     // the previous chunk's store has finished reading the staging box
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          const float4 g0 = lds_f4(g_a + col0 * 4 + 32 * i);
+          const float4 g1v = lds_f4(g_a + col0 * 4 + 32 * i + 16);
+          const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
+          const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
           float y[8];
-          if constexpr (AFFINE) {
-            const float4 g0 = lds_f4(g_a + col0 * 4 + 32 * i);
-            const float4 g1v = lds_f4(g_a + col0 * 4 + 32 * i + 16);
-            const float4 t0 = lds_f4(bt_a + col0 * 4 + 32 * i);
-            const float4 t1 = lds_f4(bt_a + col0 * 4 + 32 * i + 16);
-            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 0], v[8 * i + 1]), nmean2), rstd2), f2_pack(g0.x, g0.y), f2_pack(t0.x, t0.y)), y[0], y[1]);
-            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 2], v[8 * i + 3]), nmean2), rstd2), f2_pack(g0.z, g0.w), f2_pack(t0.z, t0.w)), y[2], y[3]);
-            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 4], v[8 * i + 5]), nmean2), rstd2), f2_pack(g1v.x, g1v.y), f2_pack(t1.x, t1.y)), y[4], y[5]);
-            f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 6], v[8 * i + 7]), nmean2), rstd2), f2_pack(g1v.z, g1v.w), f2_pack(t1.z, t1.w)), y[6], y[7]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              f2_unpack(f2_mul(f2_add(f2_from_bits(v[8 * i + 2 * k], v[8 * i + 2 * k + 1]), nmean2), rstd2), y[2 * k], y[2 * k + 1]);
-          }
+          f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 0], v[8 * i + 1]), nmean2), rstd2), f2_pack(g0.x, g0.y), f2_pack(t0.x, t0.y)), y[0], y[1]);
+          f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 2], v[8 * i + 3]), nmean2), rstd2), f2_pack(g0.z, g0.w), f2_pack(t0.z, t0.w)), y[2], y[3]);
+          f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 4], v[8 * i + 5]), nmean2), rstd2), f2_pack(g1v.x, g1v.y), f2_pack(t1.x, t1.y)), y[4], y[5]);
+          f2_unpack(f2_fma(f2_mul(f2_add(f2_from_bits(v[8 * i + 6], v[8 * i + 7]), nmean2), rstd2), f2_pack(g1v.z, g1v.w), f2_pack(t1.z, t1.w)), y[6], y[7]);
           uint4 pk;
           pk.x = pack_act(y[0], y[1]);
           pk.y = pack_act(y[2], y[3]);
@@ -547,7 +536,7 @@ bool mlp_resid_ln_supported(int M, int D, int hidden) {
   return D == LN_N && hidden >= HC && hidden % HC == 0 && hidden <= 8192 && M >= 1;
 }
 
-template <int CG, bool AFFINE>
+template <int CG>
 static int mlp_resid_ln_launch(const act_t* h_in, const act_t* W1, const float* b1, const act_t* W2, const float* b2,
                                float* x, const float* ln_w, const float* ln_b, act_t* h_out, int M, int D, int hidden,
                                float eps, cudaStream_t stream) {
@@ -558,7 +547,7 @@ static int mlp_resid_ln_launch(const act_t* h_in, const act_t* W1, const float* 
   VITED_CHECK(smem <= 232448, "mlp_resid_ln: hidden=%d needs %u bytes of shared memory", hidden, smem);
   static PerDeviceOnce once;
   if (once.first())
-    VITED_CUDA_OK(cudaFuncSetAttribute(mlp_ln_pair_kernel<CG, AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    VITED_CUDA_OK(cudaFuncSetAttribute(mlp_ln_pair_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   CUtensorMap tA, tW1, tW2, tX, tH;
   if (make_tmap_act_2d(&tA, h_in, (uint64_t)D, (uint64_t)M, (uint64_t)D * 2, 64, BM, 128)) return 1;
   if (make_tmap_act_2d(&tW1, W1, (uint64_t)D, (uint64_t)hidden, (uint64_t)D * 2, 64, HC / 2, 128)) return 1;
@@ -568,7 +557,7 @@ static int mlp_resid_ln_launch(const act_t* h_in, const act_t* W1, const float* 
   const int tiles = (M + 2 * BM - 1) / (2 * BM);
   int pairs = sms / 2;
   if (pairs > tiles) pairs = tiles;
-  VITED_CUDA_OK(launch_pdl(mlp_ln_pair_kernel<CG, AFFINE>, dim3(2 * pairs), dim3(Cfg::kThreads), smem, stream, tA, tW1, tW2, tX, tH,
+  VITED_CUDA_OK(launch_pdl(mlp_ln_pair_kernel<CG>, dim3(2 * pairs), dim3(Cfg::kThreads), smem, stream, tA, tW1, tW2, tX, tH,
                            b1, b2, ln_w, ln_b, M, hidden, eps));
   return 0;
 }
@@ -580,15 +569,11 @@ int mlp_resid_ln(const act_t* h_in, const act_t* W1, const float* b1, const act_
   VITED_CHECK(((reinterpret_cast<uintptr_t>(h_in) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
                 reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(h_out)) & 15) == 0,
               "mlp_resid_ln: operands must be 16-byte aligned");
-  VITED_CHECK((ln_w == nullptr) == (ln_b == nullptr), "mlp_resid_ln: ln_w and ln_b must both be given or both be null");
 #ifdef VITED_EXPERIMENTAL   // measured neutral (profiles/README.md): not in the product library
-  if (epilogue_warps() == 16 && ln_w)
-    return mlp_resid_ln_launch<4, true>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
+  if (epilogue_warps() == 16)
+    return mlp_resid_ln_launch<4>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
 #endif
-  // ln_w == ln_b == null: LayerNorm without its affine part (folded into the consumer Linear, engine option FOLD_LN)
-  if (ln_w == nullptr)
-    return mlp_resid_ln_launch<2, false>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
-  return mlp_resid_ln_launch<2, true>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
+  return mlp_resid_ln_launch<2>(h_in, W1, b1, W2, b2, x, ln_w, ln_b, h_out, M, D, hidden, eps, stream);
 }
 
 }  // namespace vited

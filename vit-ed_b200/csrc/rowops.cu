@@ -335,37 +335,6 @@ int f32_to_act(const float* in, act_t* out, size_t n, cudaStream_t stream) {
   return 0;
 }
 
-// LayerNorm affine folded into the Linear that consumes the LayerNorm output (engine option FOLD_LN):
-//   Linear(g * n + beta) = (W diag(g)) n + (b + W beta),   n = the plain normalised row
-// One CTA per output row o: wf[o, i] = act(w[o, i] * g[i]) from the fp32 weight as loaded (one rounding, like the
-// plain weight), bf[o] = b[o] + sum_i w[o, i] * beta[i] in fp32 (fixed-order tree reduction: deterministic).
-__global__ void __launch_bounds__(128) fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ b,
-                                                      const float* __restrict__ g, const float* __restrict__ beta,
-                                                      act_t* __restrict__ wf, float* __restrict__ bf, int in) {
-  __shared__ float red[128];
-  const size_t row = (size_t)blockIdx.x * in;
-  float acc = 0.f;
-  for (int i = threadIdx.x; i < in; i += 128) {
-    const float wv = w[row + i];
-    wf[row + i] = f2act(wv * g[i]);
-    acc = fmaf(wv, beta[i], acc);
-  }
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int s = 64; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) bf[blockIdx.x] = b[blockIdx.x] + red[0];
-}
-int fold_ln_into_linear(const float* w, const float* b, const float* ln_w, const float* ln_b, act_t* wf, float* bf,
-                        int out, int in, cudaStream_t stream) {
-  if (out <= 0 || in <= 0) return 0;
-  fold_ln_kernel<<<out, 128, 0, stream>>>(w, b, ln_w, ln_b, wf, bf, in);
-  VITED_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 __global__ void add_delta_out_kernel(const float* __restrict__ x, const act_t* __restrict__ delta,
                                      float* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -258,8 +258,6 @@ class VisionTransformerCustom(nn.Module):
         if self._engine is None:
             self._ensure_engine(next(self.parameters()).device)
         _lib.check(_lib.lib.vited_set_option(self._engine, int(option), int(value)), 'vited_set_option')
-        if int(option) == _lib.OPT_FOLD_LN and _lib.lib.vited_num_weights_loaded(self._engine) == 0:
-            self._synced_versions = None   # the engine dropped its weights (it needs their fp32 sources): upload again
 
     def profile_read(self):
         """dict: per-kernel-class device time / algorithmic flops / bytes since OPT_PROFILE was set (resets)."""
