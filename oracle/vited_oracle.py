@@ -11,7 +11,9 @@ absent, so the five timm symbols that file imports were stood in for by tests/go
 timm 0.9.2's published semantics. For the timm-owned arithmetic (PatchEmbed, Mlp, _pos_embed, forward_head,
 LayerNorm eps) parity is therefore UNPINNED by any reference-held vector; for the reference-owned code (Attention,
 Block, CrossAttention, CrossBlock, three-mode forward) and for the integer bookkeeping (pair enumeration, crop
-geometry, sampler split: real reference code imported unchanged) it is pinned.
+geometry, sampler split: real reference code imported unchanged) it is pinned. tests/test_timm_semantics.py cross-checks
+the timm-owned part (shim and oracle) against torchvision's VisionTransformer, an independent implementation of the
+same forward, on the same weights.
 
 Every function cites the reference file:line it restates.
 """
