@@ -167,6 +167,14 @@ def _gloo_worker(rank, world, n, port, q):
         assert len(called) == (1 if owns1 else 0)
         model.num_classes = 1
         frag = grid.score_fragments(model, images)
+        # the resumable form (per-rank file, rows in saved blocks) gives the same matrix on every rank
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, 'test_result_rank{rank}.pt')
+            frag_blocks = grid.score_fragments(model, images, resume_path=path, block_rows=2, save_every=2)
+            assert torch.equal(frag_blocks, frag)
+            saved = torch.load(path.format(rank=rank))
+            assert saved['is_finished'] and tuple(saved['rows']) == grid.hisfrag_row_range(n, world, rank)
         q.put((rank, puzzle.numpy(), frag.numpy(), [m.numpy() for m in many]))
     finally:
         dist.destroy_process_group()
@@ -196,6 +204,52 @@ def test_row_sharding_and_gather_world2_gloo():
         assert np.array_equal(frag, want_frag.numpy()), f'rank {rank} fragment grid differs'
         for got, want in zip(many, want_many):
             assert np.array_equal(got, want.numpy()), f'rank {rank}: a puzzle of the batch differs'
+
+
+class _CrashingModel(_FakeModel):
+    """_FakeModel that records its score_grid calls and raises once `fail_after` of them have been served."""
+    num_classes = 1
+
+    def __init__(self, fail_after=None):
+        self.calls, self.fail_after = [], fail_after
+
+    def score_grid(self, images, mode, row_begin, row_end, out=None):
+        if self.fail_after is not None and len(self.calls) >= self.fail_after:
+            raise RuntimeError('simulated crash')
+        self.calls.append((row_begin, row_end))
+        return super().score_grid(images, mode, row_begin, row_end, out)
+
+
+def test_fragment_grid_crash_resume(tmp_path):
+    """The crash-resume of the reference's test loop (hisfrag.py:181-195: rows already in the per-rank result file are
+    skipped; :243-246: the file is rewritten every SAVE_TMP_FREQ row blocks and after the last one)."""
+    n = 23
+    images = torch.zeros(n, 3, 8, 8)
+    want = grid.score_fragments(_CrashingModel(), images)
+    path = str(tmp_path / 'test_result_rank{rank}.pt')
+    crashing = _CrashingModel(fail_after=4)
+    with pytest.raises(RuntimeError, match='simulated crash'):
+        grid.score_fragments(crashing, images, resume_path=path, block_rows=3, save_every=2)
+    assert crashing.calls == [(0, 3), (3, 6), (6, 9), (9, 12)]
+    saved = torch.load(path.format(rank=0))
+    # saves happen after blocks 0, 2, 4, ... and after the last: rows [0, 9) are on disk, block [9, 12) was lost
+    assert saved['done'] == 9 and not saved['is_finished'] and saved['upper'].shape == (9, n)
+    resumed = _CrashingModel()
+    got = grid.score_fragments(resumed, images, resume_path=path, block_rows=3, save_every=2)
+    assert resumed.calls[0] == (9, 12) and resumed.calls[-1] == (21, 23)
+    assert torch.equal(got, want)
+    assert torch.load(path.format(rank=0))['is_finished']
+    # a finished file is reused without a single scoring call
+    idle = _CrashingModel(fail_after=0)
+    assert torch.equal(grid.score_fragments(idle, images, resume_path=path, block_rows=3), want) and idle.calls == []
+    # a file of another grid is an error, not silently reused; remove_cache_file starts over
+    with pytest.raises(vited_b200.VitedError, match='holds rows'):
+        grid.score_fragments(_CrashingModel(), images[:20], resume_path=path)
+    fresh = _CrashingModel()
+    again = grid.score_fragments(fresh, images, resume_path=path, block_rows=50, remove_cache_file=True)
+    assert fresh.calls == [(0, n)] and torch.equal(again, want)
+    with pytest.raises(vited_b200.VitedError, match='must be positive'):
+        grid.score_fragments(_CrashingModel(), images, resume_path=path, block_rows=0, remove_cache_file=True)
 
 
 def test_puzzle_unit_ranges_cover_configs2():

@@ -175,9 +175,16 @@ def score_puzzles(model, puzzles, n_pieces=None, gather=True, blocks_out=None):
 
 
 @torch.no_grad()
-def score_fragments(model, images, gather=True):
+def score_fragments(model, images, gather=True, resume_path=None, block_rows=64, save_every=5, remove_cache_file=False):
     """images [N,3,S,S] -> symmetric similarity logits [N, N] fp32 (raw logits, no sigmoid: hisfrag.py:230-231,
-    :281-292). Rows are sharded as DistributedIndicatesSampler does (hisfrag.py:170)."""
+    :281-292). Rows are sharded as DistributedIndicatesSampler does (hisfrag.py:170).
+
+    ``resume_path`` switches on the crash-resume of the reference's test loop (hisfrag.py:181-195, :243-246): the
+    rank's rows are then walked in blocks of ``block_rows`` rows (the reference's x1 batches), after every
+    ``save_every`` blocks (SAVE_TMP_FREQ, config.py:225) and after the last one the rows scored so far go to
+    ``resume_path.format(rank=rank)`` together with an ``is_finished`` flag, and a later call with the same grid picks up
+    behind the last saved block (``remove_cache_file=True`` discards the file first, as in the reference). A file
+    written for another grid size or row range is an error, not silently reused."""
     rank, world = _dist_info()
     n = images.shape[0]
     if world == 1:
@@ -186,7 +193,11 @@ def score_fragments(model, images, gather=True):
         sizes = indicates_row_ranges(upper_tri_pairs(n)[:, 0], world)
         ranges = [(sizes[r], sizes[r + 1]) if r + 1 < len(sizes) else (n, n) for r in range(world)]
     lo, hi = ranges[rank]
-    block = model.score_grid(images, _lib.GRID_UPPER_TRI_DIAG, lo, hi)[..., 0]
+    if resume_path is None:
+        block = model.score_grid(images, _lib.GRID_UPPER_TRI_DIAG, lo, hi)[..., 0]
+    else:
+        block = _score_fragment_rows_resumable(model, images, lo, hi, str(resume_path).format(rank=rank), block_rows,
+                                               save_every, remove_cache_file)
     if world > 1 and gather:
         upper = _all_gather_rows(block, ranges, n)
     elif world > 1:
@@ -194,6 +205,44 @@ def score_fragments(model, images, gather=True):
     else:
         upper = block
     return mirror_upper(upper)
+
+
+def _score_fragment_rows_resumable(model, images, lo, hi, path, block_rows, save_every, remove_cache_file):
+    """Rows [lo, hi) of the upper-triangular grid in saved blocks (see score_fragments)."""
+    import os
+    if block_rows < 1 or save_every < 1:
+        raise _lib.VitedError(f'score_fragments: block_rows={block_rows} and save_every={save_every} must be positive')
+    n = images.shape[0]
+    block = images.new_zeros((hi - lo, n), dtype=torch.float32)
+    done = lo
+    if os.path.exists(path):
+        if remove_cache_file:
+            os.unlink(path)
+        else:
+            data = torch.load(path, map_location='cpu')
+            if data.get('n') != n or tuple(data.get('rows', ())) != (lo, hi):
+                raise _lib.VitedError(f'score_fragments: {path} holds rows {data.get("rows")} of a {data.get("n")}-item grid, '
+                                      f'this call scores rows {(lo, hi)} of {n} items')
+            done = int(data['done'])
+            block[:done - lo] = data['upper'].to(block.device)
+            if data['is_finished']:
+                return block
+
+    def save(until, finished):
+        tmp = path + '.tmp'
+        torch.save({'n': n, 'rows': (lo, hi), 'done': until, 'upper': block[:until - lo].cpu(), 'is_finished': finished}, tmp)
+        os.replace(tmp, path)      # a crash during the write leaves the previous file intact
+
+    starts = list(range(done, hi, block_rows))
+    for k, a in enumerate(starts):
+        b = min(a + block_rows, hi)
+        block[a - lo:b - lo] = model.score_grid(images, _lib.GRID_UPPER_TRI_DIAG, a, b)[..., 0]
+        last = k == len(starts) - 1
+        if k % save_every == 0 or last:
+            save(b, last)
+    if not starts:
+        save(hi, True)             # an empty row range (more ranks than chunks) still reports "finished"
+    return block
 
 
 def mirror_upper(upper):
