@@ -325,3 +325,53 @@ def test_row_split_and_crop_geometry_properties():
 
     sampler()
     geometry()
+
+
+def test_score_puzzles_sharding_and_gather_layout_properties(monkeypatch):
+    """grid.score_puzzles for random batches of puzzles and world sizes (more ranks than units, one-piece puzzles,
+    puzzles split across several ranks): every rank's share is scored into its flat buffer, the all-gather is emulated
+    in-process from those buffers, and every rank must end up with the single-process result."""
+    from hypothesis import given, settings, strategies as st
+    import torch.distributed as dist
+
+    class _Model(_FakeModel):
+        def parameters(self):            # a rank that owns no unit asks the model for its device
+            return iter([torch.zeros(1)])
+    model = _Model()
+
+    @settings(max_examples=40, deadline=None)
+    @given(sizes=st.lists(st.integers(1, 9), min_size=1, max_size=5), world=st.integers(1, 7))
+    def run(sizes, world):
+        batch = [torch.zeros(k, 3, 8, 8) for k in sizes]
+        want = [model.score_grid(b, vited_b200.GRID_ORDERED_OFFDIAG, 0, b.shape[0]) for b in batch]
+        # the shares partition the (puzzle, row) units
+        units = [(p, r) for rank in range(world) for p, lo, hi in grid.puzzle_unit_ranges(sizes, world, rank)
+                 for r in range(lo, hi)]
+        assert units == [(p, r) for p, k in enumerate(sizes) for r in range(k)]
+        longest = max(sum((hi - lo) * sizes[p] * 4 for p, lo, hi in grid.puzzle_unit_ranges(sizes, world, r))
+                      for r in range(world))
+        flats = []
+        for rank in range(world):       # phase 1: every rank scores its share (no collective)
+            monkeypatch.setattr(grid, '_dist_info', lambda rank=rank: (rank, world))
+            flat = torch.full((longest,), float('nan'))
+            part = grid.score_puzzles(model, batch, n_pieces=sizes, gather=False, blocks_out=flat)
+            flats.append(flat)
+            for p, lo, hi in grid.puzzle_unit_ranges(sizes, world, rank):
+                blk = part[p] if (lo, hi) == (0, sizes[p]) else part[p][2]
+                assert torch.equal(blk, want[p][lo:hi])
+            owned = {p for p, _, _ in grid.puzzle_unit_ranges(sizes, world, rank)}
+            assert all((part[p] is None) == (p not in owned) for p in range(len(sizes)))
+        if world == 1:
+            return
+
+        def fake_all_gather(out, inp):   # phase 2: the one collective, emulated from the ranks' buffers
+            assert inp.numel() == longest and out.numel() == world * longest
+            out.copy_(torch.cat([torch.nan_to_num(f, nan=0.0) for f in flats]))
+        monkeypatch.setattr(dist, 'all_gather_into_tensor', fake_all_gather)
+        for rank in range(world):
+            monkeypatch.setattr(grid, '_dist_info', lambda rank=rank: (rank, world))
+            got = grid.score_puzzles(model, batch, n_pieces=sizes)
+            for g, w in zip(got, want):
+                assert torch.equal(g, w)
+
+    run()
