@@ -375,3 +375,41 @@ def test_score_puzzles_sharding_and_gather_layout_properties(monkeypatch):
                 assert torch.equal(g, w)
 
     run()
+
+
+def test_score_fragments_sharding_and_gather_properties(monkeypatch):
+    """grid.score_fragments for random grid and world sizes (more ranks than chunks included): the ranks' row blocks,
+    put through an emulated all-gather of padded blocks, give every rank the single-process symmetric matrix."""
+    from hypothesis import assume, given, settings, strategies as st
+    import torch.distributed as dist
+    model = _FakeModel()
+    model.num_classes = 1
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(2, 40), world=st.integers(2, 9))
+    def run(n, world):
+        sizes = grid.indicates_row_ranges(grid.upper_tri_pairs(n)[:, 0], world)
+        assume(all(a <= b for a, b in zip(sizes, sizes[1:])))     # (tiny grids: the reference's boundaries can go backwards)
+        images = torch.zeros(n, 3, 8, 8)
+        monkeypatch.setattr(grid, '_dist_info', lambda: (0, 1))
+        want = grid.score_fragments(model, images)
+        assert torch.equal(want, want.t())
+        blocks = []
+        for rank in range(world):
+            monkeypatch.setattr(grid, '_dist_info', lambda rank=rank: (rank, world))
+            blocks.append(grid.score_fragments(model, images, gather=False))
+        assert sum(b.shape[0] for b in blocks) == n               # the shares partition the rows
+        tallest = max(b.shape[0] for b in blocks)
+
+        def fake_all_gather(bufs, padded):
+            assert padded.shape[0] == tallest and len(bufs) == world
+            for buf, b in zip(bufs, blocks):
+                buf.zero_()
+                buf[:b.shape[0]] = b
+        monkeypatch.setattr(dist, 'all_gather', fake_all_gather)
+        monkeypatch.setattr(dist, 'get_world_size', lambda *a, **k: world)
+        for rank in range(world):
+            monkeypatch.setattr(grid, '_dist_info', lambda rank=rank: (rank, world))
+            assert torch.equal(grid.score_fragments(model, images), want)
+
+    run()
