@@ -191,6 +191,11 @@ def score_fragments(model, images, gather=True, resume_path=None, block_rows=64,
         ranges = [(0, n)]
     else:
         sizes = indicates_row_ranges(upper_tri_pairs(n)[:, 0], world)
+        if any(a > b for a, b in zip(sizes, sizes[1:])):
+            # for grids of a dozen items the reference sampler's row snapping (samplers.py:113-134) yields boundaries
+            # that run backwards; every rank sees the same `sizes`, so all of them stop here, before any collective
+            raise _lib.VitedError(f'score_fragments: the reference sampler cannot split {n} items over {world} ranks '
+                                  f'(row boundaries {sizes})')
         ranges = [(sizes[r], sizes[r + 1]) if r + 1 < len(sizes) else (n, n) for r in range(world)]
     lo, hi = ranges[rank]
     if resume_path is None:
